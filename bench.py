@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the MFCC / mel hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2]
+
+A "step" is one pass of the fused hot path over one batch of synthetic audio.  The default
+workload is BASELINE.json configs[1] (c2): 65,536 x 1 s 16 kHz clips -> lmfe (40 filters) +
+mfcc (13 cepstra) with per-clip CMVN.  `value` is whole-job audio-seconds per second with the
+inputs resident in HBM; `e2e` is the same metric through the host-buffer C-ABI call
+(`ss_features`: pinned host PCM -> H2D -> kernels -> D2H, all inside the timed region).
+One process per GPU (torchrun); clips shard with no data-path collective (weak scaling: every
+rank runs the full batch).  `--impl reference` times the CPU restatement of the reference
+(oracle/oracle_c.c, OpenMP over clips = "rayon over clips") on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT / "mfcc-rust_b200", ROOT / "oracle"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import numpy as np  # noqa: E402
+
+SPEECHPY = dict(sample_rate=16000, fft_points=512, frame_length=0.025, frame_stride=0.01, num_cepstral=13,
+                num_filters=40, low_frequency=0.0, high_frequency=8000.0)
+WORKLOADS = {
+    # name: kind, config, clips per GPU, samples per clip, seconds per clip, outputs
+    "c1": dict(kind="speechpy", cfg=SPEECHPY, n=1, length=16000, outs=("mfcc",), cmvn=0,
+               desc="c1: mfcc on one 1 s 16 kHz clip (latency case)"),
+    "c2": dict(kind="speechpy", cfg=SPEECHPY, n=65536, length=16000, outs=("lmfe", "mfcc"), cmvn=2,
+               desc="c2: 65,536 x 1 s 16 kHz clips -> lmfe(40) + mfcc(13) with per-clip CMVN"),
+    "c3": dict(kind="stft", cfg=dict(sample_rate=22050, fft_points=2048, frame_length=512 / 22050, frame_stride=0.01,
+                                     num_cepstral=13, num_filters=128, low_frequency=0.0, high_frequency=11025.0),
+               n=4096, length=110250, log=0, desc="c3: mel_spectrogram 22.05 kHz n_fft 2048 hop 512 128 mels, 4,096 x 5 s"),
+    "c4": dict(kind="stft", cfg=dict(sample_rate=16000, fft_points=400, frame_length=0.01, frame_stride=0.01,
+                                     num_cepstral=13, num_filters=80, low_frequency=0.0, high_frequency=8000.0),
+               n=8192, length=480000, log=1, desc="c4: Whisper-shaped log-mel n_fft 400 hop 160 80 mels, 8,192 x 30 s"),
+    "c5": dict(kind="speechpy", cfg=SPEECHPY, n=128, length=57_600_000, outs=("mfe", "energy", "ssc", "mfcc"), cmvn=0,
+               desc="c5: 1-hour 16 kHz streams -> mfe + ssc + mfcc, 128 streams per GPU (1,024 over 8 GPUs)"),
+}
+FP32_PEAK_TFLOPS_AT_MAX_CLOCK = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic(w, n_clips):
+    """algorithmic bytes / flops per launch (DESIGN.md 'roofline'): PCM read once + outputs written once."""
+    import speechsauce_oracle as o
+    oc = o.SpeechConfig(**w["cfg"])
+    if w["kind"] == "speechpy":
+        L, S, N = oc.frame_sample_length, oc.frame_step, oc.window_size
+        T = o.num_frames(w["length"], L, S, False)
+        per = {"mfe": oc.num_filters, "energy": 1, "lmfe": oc.num_filters, "ssc": oc.num_filters, "mfcc": oc.num_cepstral}
+        out_floats = T * sum(per[k] for k in w["outs"])
+        taps = int((o.filterbanks(oc.num_filters, oc.freq_size, oc.sample_rate, oc.low_frequency, oc.high_frequency) != 0).sum())
+        flops = T * (2.5 * N * np.log2(N) + 4 * oc.freq_size + 2 * taps + oc.freq_size + 2 * oc.num_filters + 2 * oc.num_cepstral * oc.num_filters)
+    else:
+        W, H = oc.window_size, oc.frame_size
+        T = o.stft_num_frames(w["length"], H)
+        out_floats = T * oc.num_filters
+        taps = int((o.filterbanks(oc.num_filters, oc.freq_size, oc.sample_rate, oc.low_frequency, oc.high_frequency) != 0).sum())
+        flops = T * (W + 2.5 * W * np.log2(W) + 4 * oc.freq_size + 2 * taps + oc.num_filters)
+    bytes_per_clip = 4 * (w["length"] + out_floats)
+    return dict(frames_per_clip=int(T), bytes=float(bytes_per_clip) * n_clips, flops=float(flops) * n_clips)
+
+
+class ClockSampler:
+    """samples SM clock + throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def run_reference(args, w):
+    """The reference arm: the CPU restatement (oracle port, C + OpenMP over clips) on rank 0."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_c
+    import speechsauce_oracle as o
+    cores = oracle_c.max_threads()
+    cfg = oracle_c.make_config(**w["cfg"])
+    if w["kind"] == "speechpy":
+        sample = min(w["n"], 512 * cores) if w["length"] <= 10**6 else cores
+        length = min(w["length"], 16000 * 600)
+    else:
+        sample = 8 * cores
+        length = w["length"]
+    x = o.synth_signal(sample, length, 0x5EED0000 + int(args.config[1]))
+
+    def step():
+        if w["kind"] == "speechpy":
+            kw = {k: True for k in w["outs"] if k != "ssc"}
+            oracle_c.features(x, cfg, cmvn_mode=w["cmvn"], **kw)
+        else:
+            oracle_c.mel_spectrogram2(x, cfg, log=bool(w["log"]))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    secs = sample * length / w["cfg"]["sample_rate"]
+    value = secs / dt
+    alg = algorithmic(dict(w, length=length), sample)
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "frames_per_s": alg["frames_per_clip"] * sample / dt,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "sample": f"{sample} clips x {length} samples per step"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} clips x {length / w['cfg']['sample_rate']:.0f} s per step; restated CPU reference "
+                                   "(oracle/oracle_c.c, C + OpenMP over clips), not the Rust binary (no Rust toolchain)"},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--clips", type=int, default=0, help="override clips per GPU (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--generic", action="store_true", help="force the generic kernel (SS_FLAG_FORCE_GENERIC)")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.config])
+    if args.clips:
+        w["n"] = args.clips
+    if args.impl == "reference":
+        run_reference(args, w)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import speechsauce_b200 as sb
+    from speechsauce_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or sb.lib.ss_device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = sb.SpeechConfig(**w["cfg"], devices=[local], flags=_lib.SS_FLAG_FORCE_GENERIC if args.generic else 0)
+    n, length = w["n"], w["length"]
+    alg = algorithmic(w, n)
+    T = alg["frames_per_clip"]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x5EED0000 + int(args.config[1]) + 1000 * rank)
+    x = torch.empty((n, length), dtype=torch.float32, device=dev)
+    for i in range(0, n, max(1, (1 << 28) // length)):  # generate in slabs to bound temporaries
+        j = min(n, i + max(1, (1 << 28) // length))
+        x[i:j].normal_(0.0, 0.1, generator=gen)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    outs = {}
+    if w["kind"] == "speechpy":
+        dims = {"mfe": cfg.num_filters, "lmfe": cfg.num_filters, "ssc": cfg.num_filters, "mfcc": cfg.num_cepstral}
+        for k in w["outs"]:
+            outs[k] = torch.empty((n, T) if k == "energy" else (n, T, dims[k]), dtype=torch.float32, device=dev)
+        o = _lib.ss_feature_outputs(*[C.c_void_p(outs[k].data_ptr()) if k in outs else None
+                                      for k in ("mfe", "energy", "lmfe", "ssc", "mfcc")], w["cmvn"], 0)
+
+        def step():
+            _lib.check(sb.lib.ss_features_dev(cfg.plan, 0, sp, C.c_void_p(x.data_ptr()), n, length, length, C.byref(o)))
+    else:
+        outs["mel"] = torch.empty((n, cfg.num_filters, T), dtype=torch.float32, device=dev)
+
+        def step():
+            _lib.check(sb.lib.ss_mel_spectrogram_dev(cfg.plan, 0, sp, C.c_void_p(x.data_ptr()), n, length, length,
+                                                     C.c_void_p(outs["mel"].data_ptr()), None, None, w["log"]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = sb.lib.ss_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    launches = sb.lib.ss_kernel_launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_step = ms_total / args.steps
+    audio_s = n * length / w["cfg"]["sample_rate"]
+    value = world * audio_s / (ms_step * 1e-3)
+    frames_s = world * n * T / (ms_step * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI (pinned host PCM, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        n_e = n
+        while n_e * length * 4 > (6 << 30) and n_e > 1:  # keep pinned host buffers bounded (c4 / c5)
+            n_e //= 2
+        try:
+            hx = torch.empty((n_e, length), dtype=torch.float32, pin_memory=True)
+            hx.copy_(x[:n_e])
+            houts = {k: torch.empty((n_e,) + tuple(v.shape[1:]), dtype=torch.float32, pin_memory=True) for k, v in outs.items()}
+            if w["kind"] == "speechpy":
+                ho = _lib.ss_feature_outputs(*[C.c_void_p(houts[k].data_ptr()) if k in houts else None
+                                               for k in ("mfe", "energy", "lmfe", "ssc", "mfcc")], w["cmvn"], 0)
+
+                def estep():
+                    _lib.check(sb.lib.ss_features(cfg.plan, C.c_void_p(hx.data_ptr()), n_e, length, length, C.byref(ho)))
+            else:
+                def estep():
+                    _lib.check(sb.lib.ss_mel_spectrogram(cfg.plan, C.c_void_p(hx.data_ptr()), n_e, length, length,
+                                                         C.c_void_p(houts["mel"].data_ptr()), None, w["log"]))
+            estep()
+            barrier()
+            ke = max(2, min(5, args.steps))
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                estep()  # synchronous: returns after the last D2H copy has landed
+            dt = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item())
+            e2e = {"value": world * n_e * length / w["cfg"]["sample_rate"] / dt, "unit": "audio-s/s",
+                   "h2d_bytes_per_step": int(hx.numel() * 4), "d2h_bytes_per_step": int(sum(v.numel() for v in houts.values()) * 4),
+                   "clips_per_step": n_e, "ms_per_step": dt * 1e3, "steps": ke,
+                   "timing": "host wall clock around the blocking ss_features / ss_mel_spectrogram call"}
+            # spot-check the e2e result against the device-resident one
+            key = "mfcc" if "mfcc" in outs else next(iter(outs))
+            step()
+            torch.cuda.synchronize()
+            assert torch.allclose(houts[key][:4], outs[key][:4].cpu(), atol=1e-5, rtol=1e-5), "e2e result differs from device result"
+            del hx, houts
+        except RuntimeError as ex:  # pinned allocation failed
+            e2e = {"value": None, "error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        import oracle_c
+        import speechsauce_oracle as orc
+        cores = oracle_c.max_threads()
+        ccfg = oracle_c.make_config(**w["cfg"])
+        if w["kind"] == "speechpy":
+            cs = min(n, 2048 * cores) if length <= 10**6 else cores
+            cl = min(length, 16000 * 600)
+            xs = orc.synth_signal(cs, cl, 1)
+            kw = {k: True for k in w["outs"] if k != "ssc"}
+            oracle_c.features(xs[: max(1, cs // 8)], ccfg, cmvn_mode=w["cmvn"], **kw)
+            t0 = time.perf_counter()
+            oracle_c.features(xs, ccfg, cmvn_mode=w["cmvn"], **kw)
+        else:
+            cs, cl = 8 * cores, length
+            xs = orc.synth_signal(cs, cl, 1)
+            t0 = time.perf_counter()
+            oracle_c.mel_spectrogram2(xs, ccfg, log=bool(w["log"]))
+        dt = time.perf_counter() - t0
+        cpu = {"value": cs * cl / w["cfg"]["sample_rate"] / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": f"{cs} clips x {cl / w['cfg']['sample_rate']:.0f} s, {dt:.1f} s wall; restated CPU reference "
+                         "(oracle/oracle_c.c, C + OpenMP over clips), not the Rust binary"}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = alg["bytes"] / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "frames_per_s": frames_s,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "clips_per_gpu": n, "samples_per_clip": length, "frames_per_clip": T,
+                       "l2": "inputs larger than L2" if n * length * 4 > (126 << 20) else "input fits in L2",
+                       "kernel": "k_frames_generic" if (args.generic or not cfg.info.fast_path or w["kind"] != "speechpy") else "k_fast512"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg["bytes"],
+                         "fp32": {"achieved_tflops": alg["flops"] / (ms_step * 1e-3) / 1e12,
+                                  "peak_tflops_at_max_clock": FP32_PEAK_TFLOPS_AT_MAX_CLOCK,
+                                  "frac": alg["flops"] / (ms_step * 1e-3) / 1e12 / FP32_PEAK_TFLOPS_AT_MAX_CLOCK}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/* speechsauce_cuda.h — C ABI of the B200 (sm_100a) MFCC / mel-spectrogram hot path.
+ *
+ * This is the drop-in boundary for speechsauce (secretsauceai/mfcc-rust).  Every entry
+ * point names the reference interface it replaces (file:line relative to the reference
+ * repository root).  The `speechsauce-cuda` Rust crate (mfcc-rust_b200/speechsauce-cuda),
+ * the C++ mirror (mfcc-rust_b200/cpp/speechsauce.hpp) and the Python ctypes mirror
+ * (mfcc-rust_b200/speechsauce_b200) bind exactly these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays are contiguous row-major f32 unless a
+ *     row stride (in elements) is given;
+ *   - the caller owns every host buffer and sizes outputs with ss_num_frames /
+ *     ss_stft_num_frames; the library owns the plan and all device memory;
+ *   - every function returns SS_OK (0) or a negative ss_status; ss_last_error() gives a
+ *     thread-local message.  The library never aborts and never throws across the ABI.
+ *     (The reference panics on the same conditions; the Rust wrapper turns a non-zero
+ *     status back into panic!.)
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     SS_ERR_NO_DEVICE;
+ *   - a plan is not thread-safe (mirrors `SpeechConfig: Send + !Sync`, config.rs:126,130).
+ */
+#ifndef SPEECHSAUCE_CUDA_H
+#define SPEECHSAUCE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SS_OK = 0,
+  SS_ERR_INVALID_ARG = -1, /* a condition on which the reference panics (N < L, H > W/2, hi > sr/2 ...) */
+  SS_ERR_CUDA = -2,        /* a CUDA runtime error; message holds cudaGetErrorString */
+  SS_ERR_UNSUPPORTED = -3, /* valid for the reference but outside this build's limits */
+  SS_ERR_NO_DEVICE = -4,   /* no CUDA device visible */
+  SS_ERR_ALLOC = -5
+} ss_status;
+
+/* ss_config.flags */
+#define SS_FLAG_FRAMING_LITERAL 0x1u /* reproduce processing.rs:110-120 as written (all-zero frames for T > 2) */
+#define SS_FLAG_FORCE_GENERIC   0x2u /* never pick a size-specialised kernel (used by the parity tests) */
+
+/* cmvn_mode */
+#define SS_CMVN_NONE 0
+#define SS_CMVN_MEAN 1     /* processing::cmvn(x, false) */
+#define SS_CMVN_MEAN_VAR 2 /* processing::cmvn(x, true)  */
+
+/* The nine arguments of SpeechConfig::new (config.rs:140-150), in that order, plus flags.
+ * Derived sizes are computed by the library exactly as the reference does (f32
+ * arithmetic): L = round(sr*frame_length), S = round(sr*frame_stride) (processing.rs:77-78),
+ * H = trunc(frame_length*sr) (config.rs:154), F = fft_points/2+1 (config.rs:179). */
+typedef struct {
+  int64_t sample_rate;
+  int64_t fft_points;
+  float frame_length;
+  float frame_stride;
+  int64_t num_cepstral;
+  int64_t num_filters;
+  float low_frequency;
+  float high_frequency; /* <= 0 means sample_rate/2 (SpeechConfigBuilder::new, config.rs:44) */
+  int32_t dc_elimination;
+  uint32_t flags;
+  float dct2_scale; /* 0 -> 2.0, ndrustfft's default nddct2 normalisation (feature.rs:123) */
+} ss_config;
+
+typedef struct {
+  int64_t frame_len;   /* L */
+  int64_t frame_step;  /* S */
+  int64_t hop;         /* H = frame_size */
+  int64_t n_fft;       /* W = window_size */
+  int64_t freq_size;   /* F */
+  int64_t n_pad;       /* W/H - 1, or -1 when the STFT is undefined for this config (H == 0 or H > W/2) */
+  int64_t num_filters;
+  int64_t num_cepstral;
+  float wnorm;         /* config.rs:178 */
+  int32_t n_devices;
+  int32_t fast_path;   /* 1 when a size-specialised kernel serves the speechpy-framing path */
+  int32_t fast_stft;   /* 1 when a size-specialised kernel serves the STFT path */
+} ss_plan_info;
+
+typedef struct ss_plan ss_plan;
+
+/* Output selection for ss_features*: any pointer may be NULL (not computed / not stored). */
+typedef struct {
+  float* mfe;      /* [n][T][nf]  feature::mfe .0      feature.rs:200-233 */
+  float* energy;   /* [n][T]      feature::mfe .1      feature.rs:216-219 */
+  float* lmfe;     /* [n][T][nf]  feature::lmfe        feature.rs:242-245 */
+  float* ssc;      /* [n][T][nf]  feature::ssc         README.md:15 (defined in DESIGN.md) */
+  float* mfcc;     /* [n][T][nc]  feature::mfcc        feature.rs:99-148 */
+  int32_t mfcc_cmvn_mode; /* SS_CMVN_*: processing::cmvn applied per clip to the mfcc block */
+  int32_t reserved;
+} ss_feature_outputs;
+
+/* ---- library / device ---------------------------------------------------------------- */
+int ss_device_count(void);
+const char* ss_last_error(void);
+const char* ss_version(void);
+/* pinned host memory helpers for callers that want full PCIe rate */
+int ss_host_alloc(void** ptr, size_t bytes);
+int ss_host_free(void* ptr);
+
+/* ---- plan (replaces SpeechConfig's FFT plan / window / overlap memory, config.rs:99-185) */
+int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_plan** out);
+void ss_plan_destroy(ss_plan* plan);
+int ss_plan_get_info(const ss_plan* plan, ss_plan_info* info);
+/* STFT overlap memory held by the plan (config.rs:126,162): [W-H] floats.  The reference
+ * never resets it (functions.rs:89-93); these two calls make the hidden state explicit. */
+int ss_plan_get_analysis_mem(const ss_plan* plan, float* out, int64_t n);
+int ss_plan_set_analysis_mem(ss_plan* plan, const float* in, int64_t n); /* in == NULL -> zeros */
+
+/* ---- frame counts (host arithmetic, usable without a device) ---------------------------- */
+/* processing.rs:91-92,101-102: f32 division, ceil with zero padding, floor without; no "+1".
+ * Returns -1 where the reference underflows (n < L, or no padding and fewer than one frame). */
+int64_t ss_num_frames(int64_t n, int64_t frame_len, int64_t frame_step, int zero_padding);
+/* functions.rs:97 (without n_pad): ceil(ttd as f32 / hop as f32) */
+int64_t ss_stft_num_frames(int64_t ttd, int64_t hop);
+
+/* ---- speechpy-framing features (host buffers; clips are sharded over the plan's devices) - */
+/* pcm: [n_clips][clip_len] with row stride `row_stride` elements. T = ss_num_frames(clip_len, L, S, 0). */
+int ss_features(ss_plan* plan, const float* pcm, int64_t n_clips, int64_t clip_len,
+                int64_t row_stride, const ss_feature_outputs* outs);
+int ss_mfe(ss_plan* plan, const float* pcm, int64_t n_clips, int64_t clip_len, int64_t row_stride,
+           float* feat, float* energy);                       /* feature.rs:200 */
+int ss_lmfe(ss_plan* plan, const float* pcm, int64_t n_clips, int64_t clip_len, int64_t row_stride,
+            float* out);                                      /* feature.rs:242 */
+int ss_mfcc(ss_plan* plan, const float* pcm, int64_t n_clips, int64_t clip_len, int64_t row_stride,
+            float* out, int cmvn_mode);                       /* feature.rs:99 */
+int ss_ssc(ss_plan* plan, const float* pcm, int64_t n_clips, int64_t clip_len, int64_t row_stride,
+           float* out);                                       /* README.md:15 */
+
+/* ---- STFT family ---------------------------------------------------------------------- */
+/* functions::stft2 (functions.rs:86-123); stft1 (functions.rs:199-233) is ch == 1.
+ * out_ri: [ch][T'][F][2] interleaved re/im, T' = ss_stft_num_frames(ttd, H); the last n_pad
+ * time rows are zero.  analysis_mem_inout: [W-H] overlap memory read before row 0 and
+ * overwritten with the memory after the last row; NULL -> the plan's own memory is used and
+ * updated (the reference's behaviour: state lives in the config and is never reset). */
+int ss_stft(ss_plan* plan, const float* pcm, int64_t ch, int64_t ttd, int64_t row_stride,
+            float* out_ri, float* analysis_mem_inout);
+/* feature::mel_spectrogram2 (feature.rs:163-174); mel_spectrogram1 (feature.rs:151-162) is
+ * ch == 1.  out: [ch][nf][T'] (time-minor).  log_mode 0: as the reference; 1: ln(zero_handling(.)). */
+int ss_mel_spectrogram(ss_plan* plan, const float* pcm, int64_t ch, int64_t ttd, int64_t row_stride,
+                       float* out, float* analysis_mem_inout, int log_mode);
+
+/* ---- standalone processing functions (no config in the reference; run on device 0 of the
+ *      calling thread's default context) ------------------------------------------------- */
+/* processing::preemphasis (processing.rs:31-53): out[i] = in[i] - cof*in[(i-shift) mod n], per row */
+int ss_preemphasis(const float* in, float* out, int64_t n, int64_t shift, float cof);
+int ss_preemphasis_batch(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
+                         int64_t shift, float cof);
+/* processing::stack_frames (processing.rs:65-129), filter = None.  out: [numframes][L];
+ * *numframes is written even when out == NULL (size query). */
+int ss_stack_frames(const float* in, int64_t n, int64_t frame_len, int64_t frame_step,
+                    int zero_padding, uint32_t flags, float* out, int64_t* numframes);
+/* processing::power_spectrum (processing.rs:179-181): (1/n_fft)*|rfft(zero-padded row)|, out [rows][n_fft/2+1] */
+int ss_power_spectrum(const float* frames, int64_t rows, int64_t frame_len, int64_t n_fft, float* out);
+/* processing::cmvn (processing.rs:265-300) on one [rows][cols] matrix / a batch of them */
+int ss_cmvn(const float* in, int64_t rows, int64_t cols, int variance_normalization, float* out);
+int ss_cmvn_batch(const float* in, int64_t n_mats, int64_t rows, int64_t cols,
+                  int variance_normalization, float* out);
+
+/* ---- device-resident variants: device pointers on plan device `dev_index`, enqueued on
+ *      `cuda_stream` (a cudaStream_t; NULL = legacy default stream), no synchronisation.
+ *      Used by the throughput harness and by callers that already hold data in HBM. ------- */
+int ss_features_dev(ss_plan* plan, int dev_index, void* cuda_stream, const float* d_pcm,
+                    int64_t n_clips, int64_t clip_len, int64_t row_stride,
+                    const ss_feature_outputs* d_outs);
+int ss_stft_dev(ss_plan* plan, int dev_index, void* cuda_stream, const float* d_pcm, int64_t ch,
+                int64_t ttd, int64_t row_stride, float* d_out_ri, const float* d_mem_in,
+                float* d_mem_out);
+int ss_mel_spectrogram_dev(ss_plan* plan, int dev_index, void* cuda_stream, const float* d_pcm,
+                           int64_t ch, int64_t ttd, int64_t row_stride, float* d_out,
+                           const float* d_mem_in, float* d_mem_out, int log_mode);
+int ss_preemphasis_dev(void* cuda_stream, const float* d_in, float* d_out, int64_t n_rows, int64_t n,
+                       int64_t row_stride, int64_t shift, float cof);
+int ss_stack_frames_dev(void* cuda_stream, const float* d_in, int64_t n, int64_t frame_len,
+                        int64_t frame_step, int zero_padding, uint32_t flags, float* d_out,
+                        int64_t numframes);
+int ss_power_spectrum_dev(void* cuda_stream, const float* d_frames, int64_t rows, int64_t frame_len,
+                          int64_t n_fft, float* d_out);
+int ss_cmvn_dev(void* cuda_stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols,
+                int variance_normalization, float* d_out);
+
+/* ---- introspection used by the tests and the bench (host tables, launch accounting) ----- */
+/* dense [nf][F] filterbank exactly as feature::filterbanks builds it (feature.rs:36-90) */
+int ss_debug_filterbank(const ss_plan* plan, float* out_nf_by_F);
+/* Vorbis window [W] (config.rs:151-160) */
+int ss_debug_window(const ss_plan* plan, float* out_W);
+/* number of kernels this library has launched from the calling process since load */
+int64_t ss_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECHSAUCE_CUDA_H */

@@ -1,0 +1,131 @@
+// Internal declarations shared by the host layer (ss_api.cu, ss_tables.cpp) and the kernels.
+#pragma once
+#include <cstdint>
+#include <vector_types.h>
+#include <string>
+#include <vector>
+
+#include "speechsauce_cuda.h"
+
+namespace ss {
+
+constexpr float kEps = 1.1920929e-07f;          // f32::EPSILON, functions.rs:70
+constexpr float kCmvnEps = 9.31322574615478515625e-10f;  // 2^-30, processing.rs:266
+constexpr int kMaxStages = 16;
+
+// ---- host-side derived configuration (pure C++, no CUDA; unit-tested without a GPU) ------
+struct Derived {
+  ss_config cfg;
+  int64_t L = 0, S = 0, H = 0, W = 0, F = 0, n_pad = -1;
+  int nf = 0, nc = 0;
+  float wnorm = 0.f;
+  float dct2_scale = 2.f;
+  bool stft_ok = false;      // 0 < H <= W/2
+  bool speechpy_ok = false;  // 0 < L <= W and S > 0
+};
+
+// Mel filterbank in banded (CSR-like) form: filter i covers bins [start[i], start[i]+len[i])
+// with weights w[wofs[i] ...].  Built exactly as feature::filterbanks (feature.rs:36-90).
+struct MelBank {
+  std::vector<int> start, len, wofs;
+  std::vector<float> w;
+  std::vector<int64_t> idx;  // the nf+2 bin edges
+  int max_len = 0;
+  int max_bin = -1;  // highest bin with a non-zero weight
+};
+
+struct FftPlanHost {
+  int n = 0;
+  int n_stages = 0;
+  int radix[kMaxStages] = {0};
+  std::vector<float> tw;  // interleaved cos/sin of e^{-2 pi i q / n}, q = 0..n-1
+};
+
+// Validates the nine SpeechConfig::new arguments and derives L/S/H/F/n_pad/wnorm in f32
+// exactly as the reference does.  Returns an error string ("" on success).
+std::string derive(const ss_config& cfg, Derived* out);
+int64_t rust_round_f32(float x);
+int64_t num_frames(int64_t n, int64_t L, int64_t S, int zero_padding);
+int64_t stft_num_frames(int64_t ttd, int64_t H);
+void build_melbank(const Derived& d, MelBank* out);
+void build_window(const Derived& d, std::vector<float>* out);
+// [nc][nf] DCT-II matrix including dct2_scale (no length-dependent scale)
+void build_dct(const Derived& d, std::vector<float>* out);
+bool build_fft_plan(int n, FftPlanHost* out);
+// balanced assignment of filters to `lanes` lanes (longest-processing-time first)
+void balance_filters(const MelBank& mb, int lanes, std::vector<std::vector<int>>* per_lane);
+
+// ---- device-side parameter blocks --------------------------------------------------------
+struct DevTables {
+  const float2* tw = nullptr;     // [W] twiddles e^{-2 pi i q / W}
+  const float* window = nullptr;  // [W] Vorbis window
+  const int* fstart = nullptr;    // [nf]
+  const int* flen = nullptr;      // [nf]
+  const int* fwofs = nullptr;     // [nf]
+  const float* fw = nullptr;      // banded weights
+  const float* dct = nullptr;     // [nc][nf]
+  int n_stages = 0;
+  int radix[kMaxStages] = {0};
+};
+
+enum Mode : int { kModeSpeechpy = 0, kModeStft = 1, kModePowerSpectrum = 2 };
+
+// One launch of the frame pipeline: `n_rows` rows (clips / channels), `T` frames each.
+struct FrameParams {
+  const float* pcm = nullptr;
+  int64_t n_rows = 0, row_len = 0, row_stride = 0;
+  int64_t T = 0;       // frames computed per row
+  int64_t T_out = 0;   // frames stored per row (STFT: T' including the n_pad zero rows)
+  int N = 0, F = 0;    // FFT size, bins
+  int L = 0, S = 0;    // speechpy: frame length / step; STFT: W / H
+  int nf = 0, nc = 0;
+  int mode = kModeSpeechpy;
+  uint32_t flags = 0;
+  // STFT stream model (functions.rs:86-170): rows are zero-padded to Tp*H and concatenated
+  // behind `mem_in` ([W-H], may be null = zeros); frame j of row r starts at virtual stream
+  // position r*Tp*H + j*H.
+  int64_t Tp = 0;
+  int n_pad = 0;
+  const float* mem_in = nullptr;
+  float* mem_out = nullptr;
+  float wnorm = 0.f;
+  float mag_scale = 0.f;  // speechpy: 1/n_fft (processing.rs:180)
+  // mfcc epilogue (feature.rs:126-146)
+  float scale_rest = 0.f, scale_00 = 0.f;
+  int dc_elim = 1;
+  int cmvn_mode = 0;
+  float ssc_r0 = 1.f, ssc_step = 0.f;
+  int log_mode = 0;
+  // outputs (device pointers, may be null)
+  float* mfe = nullptr;
+  float* energy = nullptr;
+  float* lmfe = nullptr;
+  float* ssc = nullptr;
+  float* mfcc = nullptr;
+  float2* stft_out = nullptr;  // [row][T_out][F]
+  float* mel_out = nullptr;    // [row][nf][T_out]
+  float* pspec_out = nullptr;  // [row][F] (power_spectrum of pre-framed rows)
+  DevTables tab;
+};
+
+// ---- kernel launchers (each returns cudaError_t as int; all enqueue on `stream`) ---------
+int launch_frames_generic(const FrameParams& p, void* stream);
+int launch_stft_mem_update(const FrameParams& p, void* stream);
+// n_fft == 512 register-FFT path for speechpy framing (ss_kernels_fast512.cu)
+bool fast512_supported(const Derived& d, const MelBank& mb);
+struct Fast512Tables;  // opaque device tables
+int fast512_build_tables(const Derived& d, const MelBank& mb, Fast512Tables** out);
+void fast512_free_tables(Fast512Tables* t);
+int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, void* stream);
+
+int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
+                       int64_t shift, float cof, void* stream);
+int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,
+                        float* out, void* stream);
+int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int varnorm, float* out,
+                float* scratch, void* stream);
+size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols);
+
+void count_launch(int n = 1);
+
+}  // namespace ss

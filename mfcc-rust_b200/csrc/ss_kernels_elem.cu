@@ -1,0 +1,231 @@
+// HBM-bound standalone kernels behind the reference's config-less processing functions:
+//   processing::preemphasis   processing.rs:31-53
+//   processing::stack_frames  processing.rs:65-129
+//   processing::cmvn          processing.rs:265-300
+// All are pure streaming kernels: coalesced (float4 where alignment allows) loads and stores,
+// grids sized in multiples of the SM count, no intermediate buffers except the cmvn partial
+// statistics.
+#include <cuda_runtime.h>
+
+#include "ss_internal.h"
+
+namespace ss {
+
+namespace {
+
+constexpr int kSmCountGuess = 148;
+
+// ------------------------------------------------------------------------- preemphasis
+// out[i] = in[i] - cof * in[(i - shift) mod n]   (np.roll semantics, circular, Q17)
+__global__ void __launch_bounds__(256) k_preemphasis(const float* __restrict__ in, float* __restrict__ out,
+                                                     int64_t n_rows, int64_t n, int64_t row_stride,
+                                                     int64_t shift_mod, float cof, int vec_ok, int bx) {
+  const int64_t row = blockIdx.x / bx;
+  const float* x = in + row * row_stride;
+  float* y = out + row * row_stride;
+  const int64_t tid = (blockIdx.x % bx) * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)bx * blockDim.x;
+  if (vec_ok) {
+    // 4 outputs per thread; the rolled operand is generally misaligned, so it is read as
+    // scalars (served by L1 from the lines the aligned stream just brought in).
+    const int64_t n4 = n >> 2;
+    for (int64_t v = tid; v < n4; v += nthreads) {
+      const int64_t i = v << 2;
+      const float4 a = *reinterpret_cast<const float4*>(x + i);
+      int64_t j = i - shift_mod;
+      if (j < 0) j += n;
+      float r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int64_t jj = j + u;
+        if (jj >= n) jj -= n;
+        r[u] = __ldg(x + jj);
+      }
+      float4 o;
+      o.x = a.x - cof * r[0];
+      o.y = a.y - cof * r[1];
+      o.z = a.z - cof * r[2];
+      o.w = a.w - cof * r[3];
+      *reinterpret_cast<float4*>(y + i) = o;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += nthreads) {
+      int64_t j = i - shift_mod;
+      if (j < 0) j += n;
+      y[i] = x[i] - cof * x[j];
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) {
+      int64_t j = i - shift_mod;
+      if (j < 0) j += n;
+      y[i] = x[i] - cof * x[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- stack_frames
+// out[f][j] = x[f*S + j] (zero beyond n: the zero_padding=true tail), or the literal rows.
+__global__ void __launch_bounds__(256) k_stack_frames(const float* __restrict__ in, float* __restrict__ out,
+                                                      int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags) {
+  const int64_t total = T * L;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int64_t f = i / L, j = i - f * L;
+    float v;
+    if (flags & SS_FLAG_FRAMING_LITERAL) {
+      v = (T <= 2 && j < 2 * (L / 2) && j < n) ? in[j] : 0.0f;
+    } else {
+      const int64_t s = f * S + j;
+      v = s < n ? __ldg(in + s) : 0.0f;
+    }
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------- cmvn
+// Pass 1: per (matrix, row block) Welford statistics per column, merged across the block's
+// threads with Chan's formula.  Pass 2: merge the row blocks of the matrix, then normalise.
+// partial layout: [n_mats][nblk][cols][3] = (count, mean, M2)
+struct Wf {
+  float n, mean, m2;
+};
+__device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
+  if (b.n == 0.f) return a;
+  if (a.n == 0.f) return b;
+  Wf r;
+  r.n = a.n + b.n;
+  const float d = b.mean - a.mean;
+  r.mean = a.mean + d * (b.n / r.n);
+  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_cmvn_partial(const float* __restrict__ in, float* __restrict__ partial,
+                                                      int64_t rows, int cols, int64_t rows_per_blk, int nblk) {
+  extern __shared__ float sm[];  // [lanes][cols][3]
+  const int64_t mat = blockIdx.x;
+  const int blk = blockIdx.y;
+  const int lanes = blockDim.x / cols;  // row lanes; threads beyond lanes*cols idle
+  const int lane = threadIdx.x / cols, c = threadIdx.x - lane * cols;
+  const float* x = in + mat * rows * cols;
+  const int64_t r0 = blk * rows_per_blk;
+  const int64_t r1 = min(rows, r0 + rows_per_blk);
+  Wf w = {0.f, 0.f, 0.f};
+  if (lane < lanes) {
+    for (int64_t r = r0 + lane; r < r1; r += lanes) {
+      const float v = __ldg(x + r * cols + c);  // consecutive threads -> consecutive addresses
+      w.n += 1.f;
+      const float d = v - w.mean;
+      w.mean += d / w.n;
+      w.m2 += d * (v - w.mean);
+    }
+    float* s = sm + ((size_t)lane * cols + c) * 3;
+    s[0] = w.n; s[1] = w.mean; s[2] = w.m2;
+  }
+  __syncthreads();
+  if (threadIdx.x < cols) {
+    Wf acc = {0.f, 0.f, 0.f};
+    for (int l = 0; l < lanes; ++l) {
+      const float* s = sm + ((size_t)l * cols + threadIdx.x) * 3;
+      acc = wf_merge(acc, Wf{s[0], s[1], s[2]});
+    }
+    float* o = partial + (((size_t)mat * nblk + blk) * cols + threadIdx.x) * 3;
+    o[0] = acc.n; o[1] = acc.mean; o[2] = acc.m2;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
+                                                    const float* __restrict__ partial, int64_t rows, int cols,
+                                                    int64_t rows_per_blk, int nblk, int varnorm) {
+  extern __shared__ float sm[];  // [cols][2] = mean, 1/(std+eps)
+  const int64_t mat = blockIdx.x;
+  const int blk = blockIdx.y;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    Wf acc = {0.f, 0.f, 0.f};
+    for (int b = 0; b < nblk; ++b) {
+      const float* s = partial + (((size_t)mat * nblk + b) * cols + c) * 3;
+      acc = wf_merge(acc, Wf{s[0], s[1], s[2]});
+    }
+    sm[2 * c] = acc.mean;
+    // processing.rs:283-292: std with ddof 0, divide by (std + 2^-30)
+    sm[2 * c + 1] = varnorm ? 1.0f / (sqrtf(acc.m2 / acc.n) + kCmvnEps) : 1.0f;
+  }
+  __syncthreads();
+  const float* x = in + mat * rows * cols;
+  float* y = out + mat * rows * cols;
+  const int64_t e0 = blk * rows_per_blk * cols;
+  const int64_t e1 = min(rows, (blk + 1) * rows_per_blk) * cols;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int c = (int)(e % cols);
+    const float d = __ldg(x + e) - sm[2 * c];
+    y[e] = varnorm ? d * sm[2 * c + 1] : d;
+  }
+}
+
+inline int64_t cmvn_rows_per_blk(int64_t n_mats, int64_t rows) {
+  // enough blocks to fill the chip a few times over, at least 64 rows per block
+  const int64_t want_blocks = 8 * kSmCountGuess;
+  int64_t per_mat = (want_blocks + n_mats - 1) / n_mats;
+  if (per_mat < 1) per_mat = 1;
+  int64_t rpb = (rows + per_mat - 1) / per_mat;
+  if (rpb < 64) rpb = 64;
+  if (rpb > rows) rpb = rows;
+  return rpb < 1 ? 1 : rpb;
+}
+
+}  // namespace
+
+int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
+                       int64_t shift, float cof, void* stream) {
+  if (n_rows <= 0 || n <= 0) return 0;
+  int64_t sm = shift % n;
+  if (sm < 0) sm += n;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) &&
+                     (row_stride % 4 == 0);
+  int64_t bx = (n / 4 + 255) / 256;
+  const int64_t cap = (8LL * kSmCountGuess + n_rows - 1) / n_rows;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  if (bx * n_rows > 2147483647LL) return (int)cudaErrorInvalidValue;
+  k_preemphasis<<<(unsigned)(bx * n_rows), 256, 0, (cudaStream_t)stream>>>(in, out, n_rows, n, row_stride, sm,
+                                                                           cof, vec_ok, (int)bx);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,
+                        float* out, void* stream) {
+  if (T <= 0) return 0;
+  int64_t blocks = (T * L + 255) / 256;
+  if (blocks > 16LL * kSmCountGuess) blocks = 16LL * kSmCountGuess;
+  k_stack_frames<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, L, S, T, flags);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols) {
+  const int64_t rpb = cmvn_rows_per_blk(n_mats, rows);
+  const int64_t nblk = (rows + rpb - 1) / rpb;
+  return (size_t)n_mats * nblk * cols * 3 * sizeof(float);
+}
+
+int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int varnorm, float* out,
+                float* scratch, void* stream) {
+  if (n_mats <= 0 || rows <= 0 || cols <= 0) return 0;
+  if (cols > 256 || n_mats > 2147483647LL) return (int)cudaErrorInvalidValue;
+  const int64_t rpb = cmvn_rows_per_blk(n_mats, rows);
+  const int nblk = (int)((rows + rpb - 1) / rpb);
+  if (nblk > 65535) return (int)cudaErrorInvalidValue;
+  dim3 grid((unsigned)n_mats, (unsigned)nblk);
+  const int lanes = 256 / (int)cols;
+  k_cmvn_partial<<<grid, 256, (size_t)lanes * cols * 3 * sizeof(float), (cudaStream_t)stream>>>(
+      in, scratch, rows, (int)cols, rpb, nblk);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  k_cmvn_apply<<<grid, 256, (size_t)cols * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      in, out, scratch, rows, (int)cols, rpb, nblk, varnorm);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ss

@@ -1,0 +1,89 @@
+"""Mirror of speechsauce::feature (feature.rs): mfcc, mfe, lmfe, ssc, mel_spectrogram1/2.
+
+1-D inputs follow the reference signatures; 2-D inputs ([n_clips, clip_len]) are the batched
+form the GPU path is built for (clips are sharded over the config's devices)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _rows(signal):
+    x = np.asarray(signal)
+    if x.dtype != np.float32:
+        raise TypeError("speechsauce is f32-only (README.md:17); got %s" % x.dtype)
+    one = x.ndim == 1
+    if one:
+        x = x[None, :]
+    if x.ndim != 2:
+        raise ValueError("signal must be 1-D or 2-D")
+    return np.ascontiguousarray(x), one  # as_standard_layout(), SURVEY 8(b)
+
+
+def _frames(cfg, clip_len):
+    T = lib.ss_num_frames(clip_len, cfg.frame_sample_length, cfg.frame_step, 0)
+    return T
+
+
+def features(signal, cfg, *, mfe=False, energy=False, lmfe=False, ssc=False, mfcc=False, cmvn_mode=0):
+    """ss_features: any subset of outputs from ONE pass over the PCM."""
+    x, one = _rows(signal)
+    n, clip_len = x.shape
+    T = _frames(cfg, clip_len)
+    if T < 1:  # let the library produce the error message
+        T = 0
+    nf, nc = cfg.num_filters, cfg.num_cepstral
+    out = {}
+    if mfe: out["mfe"] = np.empty((n, T, nf), np.float32)
+    if energy: out["energy"] = np.empty((n, T), np.float32)
+    if lmfe: out["lmfe"] = np.empty((n, T, nf), np.float32)
+    if ssc: out["ssc"] = np.empty((n, T, nf), np.float32)
+    if mfcc: out["mfcc"] = np.empty((n, T, nc), np.float32)
+    o = _lib.ss_feature_outputs(*[_lib.fptr(out.get(k)) for k in ("mfe", "energy", "lmfe", "ssc", "mfcc")],
+                                int(cmvn_mode), 0)
+    check(lib.ss_features(cfg.plan, _lib.fptr(x), n, clip_len, clip_len, C.byref(o)))
+    return {k: (v[0] if one else v) for k, v in out.items()}
+
+
+def mfe(signal, cfg):
+    """feature::mfe (feature.rs:200-233) -> (features [T, nf], frame_energies [T])."""
+    r = features(signal, cfg, mfe=True, energy=True)
+    return r["mfe"], r["energy"]
+
+
+def lmfe(signal, cfg):
+    """feature::lmfe (feature.rs:242-245)."""
+    return features(signal, cfg, lmfe=True)["lmfe"]
+
+
+def ssc(signal, cfg):
+    """feature::ssc — named by README.md:15, defined in DESIGN.md."""
+    return features(signal, cfg, ssc=True)["ssc"]
+
+
+def mfcc(signal, cfg, cmvn_mode=0):
+    """feature::mfcc (feature.rs:99-148); cmvn_mode applies processing::cmvn per clip."""
+    return features(signal, cfg, mfcc=True, cmvn_mode=cmvn_mode)["mfcc"]
+
+
+def mel_spectrogram2(signal, cfg, *, log=False, analysis_mem=None):
+    """feature::mel_spectrogram2 (feature.rs:163-174): [ch, ttd] -> [ch, nf, T']."""
+    x, _ = _rows(signal)
+    ch, ttd = x.shape
+    Tp = max(0, lib.ss_stft_num_frames(ttd, max(cfg.frame_size, 1)))
+    out = np.empty((ch, cfg.num_filters, Tp), np.float32)
+    check(lib.ss_mel_spectrogram(cfg.plan, _lib.fptr(x), ch, ttd, ttd, _lib.fptr(out),
+                                 _lib.fptr(analysis_mem), int(log)))
+    return out
+
+
+def mel_spectrogram1(signal, cfg, **kw):
+    """feature::mel_spectrogram1 (feature.rs:151-162), intended semantics: one-row mel_spectrogram2."""
+    x = np.asarray(signal)
+    if x.ndim != 1:
+        raise ValueError("mel_spectrogram1 takes a 1-D signal")
+    return mel_spectrogram2(x[None, :], cfg, **kw)[0]

@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances are BASELINE.json's: rel 1e-4 on power / mel spectra, abs 1e-3 on
+log-mel and MFCC (see conftest.assert_spec_close / assert_log_close)."""
+import numpy as np
+import pytest
+
+import speechsauce_b200 as sb
+import speechsauce_oracle as o
+from conftest import assert_log_close, assert_spec_close
+from speechsauce_b200 import _lib
+from test_host_abi import CONFIGS
+
+pytestmark = pytest.mark.gpu
+GENERIC = _lib.SS_FLAG_FORCE_GENERIC
+
+
+def special_clips(n=16000):
+    t = np.arange(n, dtype=np.float32)
+    noise = o.synth_signal(1, n, 99)[0]
+    sine = (0.5 * np.sin(2 * np.pi * 440.0 * t / 16000.0)).astype(np.float32) + np.float32(0.01) * noise
+    imp = np.zeros(n, np.float32)
+    imp[1234] = 1.0
+    return {"noise": noise, "sine": sine, "zero": np.zeros(n, np.float32), "impulse": imp,
+            "dc": np.full(n, 0.25, np.float32)}
+
+
+@pytest.mark.parametrize("flags", [0, GENERIC], ids=["fast", "generic"])
+@pytest.mark.parametrize("cname", ["c1", "default", "odd"])
+def test_speechpy_features_match_oracle(cname, flags):
+    kw = CONFIGS[cname]
+    cfg = sb.SpeechConfig(**kw, flags=flags)
+    oc = o.SpeechConfig(**kw)
+    if flags == 0 and cname in ("c1", "default"):
+        assert cfg.info.fast_path == 1
+    n = oc.sample_rate
+    for name, x in special_clips(n).items():
+        r = sb.feature.features(x, cfg, mfe=True, energy=True, lmfe=True, ssc=True, mfcc=True)
+        f, e = o.mfe(x, oc)
+        f64, e64 = o.mfe(x, oc, np.float64)
+        assert r["mfe"].shape == f.shape and r["energy"].shape == e.shape
+        assert_spec_close(r["mfe"], f, what=f"{cname}/{name} mfe")
+        assert_spec_close(r["energy"], e, what=f"{cname}/{name} energy")
+        assert_spec_close(r["mfe"], f64, what=f"{cname}/{name} mfe vs f64")
+        assert_log_close(r["lmfe"], np.log(f), what=f"{cname}/{name} lmfe")
+        assert_log_close(r["mfcc"], o.mfcc(x, oc), what=f"{cname}/{name} mfcc")
+        assert_spec_close(r["ssc"], o.ssc(x, oc), rtol=2e-4, what=f"{cname}/{name} ssc")
+        if name == "zero":  # zero_handling, functions.rs:66-71
+            assert (r["mfe"] == o.EPS).all() and (r["energy"] == o.EPS).all()
+
+
+@pytest.mark.parametrize("flags", [0, GENERIC], ids=["fast", "generic"])
+def test_individual_entry_points_and_dc_elimination_off(flags):
+    kw = dict(CONFIGS["c1"], dc_elimination=False)
+    cfg = sb.SpeechConfig(**kw, flags=flags)
+    oc = o.SpeechConfig(**kw)
+    x = o.synth_signal(3, 16000, 5)
+    m = sb.feature.mfcc(x, cfg)
+    assert m.shape == (3, 97, 13)
+    for i in range(3):
+        assert_log_close(m[i], o.mfcc(x[i], oc), atol=2e-3, what="mfcc dc_elimination=False")  # column 0 is unscaled (|c0| ~ 1e3)
+        assert_log_close(m[i][:, 1:], o.mfcc(x[i], oc)[:, 1:], what="mfcc dc_elimination=False cols 1..")
+    f, e = sb.feature.mfe(x[0], cfg)
+    assert_spec_close(f, o.mfe(x[0], oc)[0], what="ss_mfe")
+    assert_log_close(sb.feature.lmfe(x[0], cfg), o.lmfe(x[0], oc), what="ss_lmfe")
+    assert_spec_close(sb.feature.ssc(x[0], cfg), o.ssc(x[0], oc), rtol=2e-4, what="ss_ssc")
+
+
+@pytest.mark.parametrize("flags", [0, GENERIC], ids=["fast", "generic"])
+def test_kws_batch_slice_lmfe_mfcc_cmvn(flags):
+    """config c2 on a 300-clip slice: lmfe + mfcc with per-clip cmvn(mean, var)."""
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], flags=flags)
+    oc = o.SpeechConfig(**CONFIGS["c1"])
+    x = o.synth_signal(300, 16000, 0x5EED0002)
+    for mode in (1, 2):
+        r = sb.feature.features(x, cfg, lmfe=True, mfcc=True, cmvn_mode=mode)
+        for i in (0, 1, 17, 150, 299):
+            assert_log_close(r["lmfe"][i], o.lmfe(x[i], oc), what=f"lmfe clip {i}")
+            want = o.cmvn(o.mfcc(x[i], oc), mode == 2)
+            assert_log_close(r["mfcc"][i], want, what=f"cmvn(mfcc) clip {i} mode {mode}")
+        np.testing.assert_allclose(r["mfcc"].mean(1), 0, atol=2e-5 if mode == 2 else 1e-5)
+        if mode == 2:
+            np.testing.assert_allclose(r["mfcc"].std(1), 1, atol=1e-4)
+
+
+def test_fast_and_generic_paths_agree_on_ragged_shapes():
+    for clip_len, L_s, S_s in [(16000, 0.025, 0.01), (5003, 0.02, 0.01), (1237, 0.032, 0.005), (640, 0.025, 0.01), (561, 0.025, 0.01)]:
+        kw = dict(CONFIGS["c1"], frame_length=L_s, frame_stride=S_s)
+        a = sb.SpeechConfig(**kw)
+        b = sb.SpeechConfig(**kw, flags=GENERIC)
+        oc = o.SpeechConfig(**kw)
+        assert a.info.fast_path == 1 and b.info.fast_path == 0
+        x = o.synth_signal(7, clip_len, clip_len)
+        ra = sb.feature.features(x, a, mfe=True, energy=True, mfcc=True, lmfe=True)
+        rb = sb.feature.features(x, b, mfe=True, energy=True, mfcc=True, lmfe=True)
+        T = o.num_frames(clip_len, oc.frame_sample_length, oc.frame_step, False)
+        assert ra["mfe"].shape == (7, T, 40)
+        assert_spec_close(ra["mfe"], rb["mfe"], what=f"fast vs generic mfe {clip_len}")
+        assert_spec_close(ra["energy"], rb["energy"], what="fast vs generic energy")
+        assert_log_close(ra["mfcc"], rb["mfcc"], what="fast vs generic mfcc")
+        assert_log_close(ra["mfcc"][3], o.mfcc(x[3], oc), what="fast mfcc vs oracle")
+
+
+def test_reference_shape_tests_1M_samples():
+    """speechsauce/src/lib.rs:94-134 re-expressed: default config, 1e6 samples -> (6248, 13), no NaN."""
+    sig = o.synth_signal(1, 1_000_000, 7)[0]
+    m = sb.mfcc(sig, 16000)  # the py-speechsauce call (py-speechsauce/speechsauce/__init__.py:37)
+    assert m.shape == (6248, 13) and not np.isnan(m).any()
+    cfg = sb.SpeechConfigBuilder(16000).build()
+    f, e = sb.feature.mfe(sig, cfg)
+    assert f.shape == (6248, 40) and e.shape == (6248,)
+    oc = o.SpeechConfig(16000)
+    assert_log_close(m, o.mfcc(sig, oc), what="1M-sample mfcc")
+    assert_spec_close(f, o.mfe(sig, oc)[0], what="1M-sample mfe")
+
+
+def test_literal_framing_flag():
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], flags=_lib.SS_FLAG_FRAMING_LITERAL)
+    oc = o.SpeechConfig(**CONFIGS["c1"])
+    x = o.synth_signal(1, 16000, 3)[0]
+    assert_log_close(sb.feature.mfcc(x, cfg), o.mfcc(x, oc, literal_framing=True), what="literal mfcc")
+    short = x[:720]  # T == 2: both rows are x[0..L]
+    assert_spec_close(sb.feature.mfe(short, cfg)[0], o.mfe(short, oc, literal_framing=True)[0], what="literal T=2")
+
+
+def test_feature_errors():
+    cfg = sb.SpeechConfig(**CONFIGS["c1"])
+    with pytest.raises(sb.SpeechsauceError) as ei:
+        sb.feature.mfcc(np.zeros(300, np.float32), cfg)
+    assert ei.value.code == _lib.SS_ERR_INVALID_ARG
+    with pytest.raises(sb.SpeechsauceError):
+        sb.feature.mfcc(np.zeros(500, np.float32), cfg)  # floor((500-400)/160) == 0 frames
+
+
+# ------------------------------------------------------------------ standalone processing functions
+
+
+def test_preemphasis():
+    got = sb.preemphasis(np.array([1, 2, 3, 4, 5], np.float32), 1, 0.98)
+    np.testing.assert_allclose(got, [1 - 4.9, 2 - 0.98, 3 - 1.96, 4 - 2.94, 5 - 3.92], rtol=1e-6)
+    x = o.synth_signal(1, 1_000_003, 1)[0]
+    for shift in (1, 2, -3, 1_000_003):
+        np.testing.assert_array_equal(sb.preemphasis(x, shift, 0.98), o.preemphasis(x, shift, 0.98))
+    xb = o.synth_signal(5, 4001, 2)
+    np.testing.assert_array_equal(sb.preemphasis(xb, 1, 0.97), np.stack([o.preemphasis(r, 1, 0.97) for r in xb]))
+    with pytest.raises(sb.SpeechsauceError):
+        sb.preemphasis(x, 0, 0.98)
+
+
+def test_stack_frames():
+    x = o.synth_signal(1, 100_000, 4)[0]
+    for fl, fs, zp in [(0.02, 0.02, True), (0.025, 0.01, False), (0.025, 0.01, True), (0.02, 0.01, False)]:
+        np.testing.assert_array_equal(sb.processing.stack_frames(x, 16000, fl, fs, None, zp),
+                                      o.stack_frames(x, 16000, fl, fs, zp))
+    np.testing.assert_array_equal(sb.processing.stack_frames(x, 16000, 0.025, 0.01, None, False, literal=True),
+                                  o.stack_frames(x, 16000, 0.025, 0.01, False, literal=True))
+    np.testing.assert_array_equal(sb.processing.stack_frames(x[:720], 16000, 0.025, 0.01, None, False, literal=True),
+                                  o.stack_frames(x[:720], 16000, 0.025, 0.01, False, literal=True))
+    with pytest.raises(sb.SpeechsauceError):
+        sb.processing.stack_frames(x[:100], 16000, 0.025, 0.01, None, False)
+
+
+def test_power_spectrum():
+    P = sb.processing.power_spectrum(np.ones((1, 320), np.float32), 512)
+    k = np.arange(1, 257)
+    want = np.abs(np.sin(np.pi * 320 * k / 512) / np.sin(np.pi * k / 512)) / 512
+    assert abs(P[0, 0] - 0.625) < 1e-6
+    np.testing.assert_allclose(P[0, 1:], want, rtol=1e-4, atol=2e-6)
+    fr = o.synth_signal(33, 400, 8)
+    for nfft in (512, 400, 1024, 2048, 480):
+        assert_spec_close(sb.processing.power_spectrum(fr, nfft), o.power_spectrum(fr, nfft), what=f"power_spectrum {nfft}")
+    with pytest.raises(sb.SpeechsauceError):
+        sb.processing.power_spectrum(fr, 256)  # frame longer than the FFT: ndrustfft panics
+
+
+def test_cmvn():
+    rng = np.random.default_rng(3)
+    v = rng.uniform(0, 1, (50, 100)).astype(np.float32)  # the reference's test (lib.rs:71-91)
+    y = sb.cmvn(v, True)
+    assert y.shape == v.shape
+    np.testing.assert_allclose(y.mean(0), 0, atol=1e-6)
+    np.testing.assert_allclose(y.std(0), 1, atol=1e-5)
+    np.testing.assert_allclose(y, o.cmvn(v, True), atol=2e-5)
+    np.testing.assert_allclose(sb.cmvn(v, False), o.cmvn(v, False), atol=1e-6)
+    big = rng.standard_normal((100_000, 13)).astype(np.float32) * 3 + 5
+    np.testing.assert_allclose(sb.cmvn(big, True), o.cmvn(big, True, np.float64), atol=1e-4)
+    batch = rng.standard_normal((40, 97, 13)).astype(np.float32)
+    got = sb.cmvn(batch, True)
+    for i in (0, 13, 39):
+        np.testing.assert_allclose(got[i], o.cmvn(batch[i], True), atol=2e-5)
+    with pytest.raises(sb.SpeechsauceError):
+        sb.cmvn(np.zeros((0, 4), np.float32))
+
+
+# ----------------------------------------------------------------------------------- STFT family
+
+
+@pytest.mark.parametrize("cname,n_clips,ttd", [("c3", 6, 22050 * 2 + 101), ("c4", 5, 16000 * 2), ("c4", 3, 4001)])
+def test_stft_and_mel_match_oracle(cname, n_clips, ttd):
+    kw = CONFIGS[cname]
+    cfg, oc = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+    x = o.synth_signal(n_clips, ttd, 31)
+    X = sb.functions.stft2(x, cfg)
+    Xo = o.stft2(x, oc)
+    assert X.shape == Xo.shape
+    n_pad = oc.window_size // oc.frame_size - 1
+    assert not X[:, X.shape[1] - n_pad:].any()            # trailing zero rows (Q13)
+    assert_spec_close(X.real, Xo.real, what=f"{cname} stft re")
+    assert_spec_close(X.imag, Xo.imag, what=f"{cname} stft im")
+    np.testing.assert_array_equal(cfg.analysis_mem, oc.analysis_mem)   # state carried like the reference
+    # second call continues from the stored memory (never reset, functions.rs:89-93)
+    X2, Xo2 = sb.functions.stft2(x, cfg), o.stft2(x, oc)
+    assert_spec_close(X2.real, Xo2.real, what=f"{cname} stft 2nd call")
+    cfg2, oc2 = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+    M = sb.feature.mel_spectrogram2(x, cfg2)
+    Mo = o.mel_spectrogram2(x, oc2)
+    assert M.shape == Mo.shape == (n_clips, oc.num_filters, o.stft_num_frames(ttd, oc.frame_size))
+    assert_spec_close(M, Mo, what=f"{cname} mel_spectrogram2")
+    assert not M[:, :, M.shape[2] - n_pad:].any()
+    cfg3, oc3 = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+    assert_log_close(sb.feature.mel_spectrogram2(x, cfg3, log=True), o.log_mel_spectrogram2(x, oc3), what=f"{cname} log-mel")
+    cfg4, oc4 = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+    assert_spec_close(sb.feature.mel_spectrogram1(x[0], cfg4), o.mel_spectrogram1(x[0], oc4), what="mel_spectrogram1")
+    assert_spec_close(sb.functions.stft1(x[1], cfg4).real, o.stft1(x[1], oc4).real, what="stft1 after state")
+
+
+def test_stft_explicit_memory_equals_plan_memory_and_sharding_halo():
+    kw = CONFIGS["c4"]
+    x = o.synth_signal(8, 3200, 77)
+    whole = sb.functions.stft2(x, sb.SpeechConfig(**kw))
+    # process rows [0,3) and [3,8) separately, carrying the overlap memory by hand
+    cfg = sb.SpeechConfig(**kw)
+    mem = np.zeros(400 - 160, np.float32)
+    a = sb.functions.stft2(x[:3], cfg, analysis_mem=mem)
+    b = sb.functions.stft2(x[3:], cfg, analysis_mem=mem)
+    np.testing.assert_array_equal(np.concatenate([a, b]), whole)
+    assert not cfg.analysis_mem.any()  # the plan's own memory was not touched
+
+
+def test_stft_impulse_closed_form():
+    W, H = 400, 160
+    cfg = sb.SpeechConfig(16000, W, 0.01, 0.01, 13, 80, 0.0, 8000.0)
+    ttd, p = 10 * H + 37, 3 * H + 11
+    x = np.zeros((1, ttd), np.float32)
+    x[0, p] = 1.0
+    X = sb.functions.stft2(x, cfg)
+    win = cfg.window
+    k = np.arange(W // 2 + 1)
+    for t in range(X.shape[1] - 1):
+        off = p - ((t + 2) * H - W)
+        want = win[off] * cfg.wnorm * np.exp(-2j * np.pi * k * off / W) if 0 <= off < W else 0 * k
+        np.testing.assert_allclose(X[0, t], want, atol=2e-8)
+
+
+def test_stft_errors():
+    dflt = sb.SpeechConfig(16000)  # H = 320 > W/2: the reference underflows (Q13)
+    with pytest.raises(sb.SpeechsauceError) as ei:
+        sb.functions.stft2(np.zeros((1, 4000), np.float32), dflt)
+    assert ei.value.code == _lib.SS_ERR_INVALID_ARG

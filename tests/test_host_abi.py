@@ -1,0 +1,106 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/speechsauce_cuda.h
+declares, its host logic (derived sizes, frame counts, filterbank, window) matches the oracle, and
+compute calls fail loudly without a device (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import speechsauce_b200 as sb
+import speechsauce_oracle as o
+from speechsauce_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+CONFIGS = {
+    "c1": dict(sample_rate=16000, fft_points=512, frame_length=0.025, frame_stride=0.01, num_cepstral=13,
+               num_filters=40, low_frequency=0.0, high_frequency=8000.0),
+    "default": dict(sample_rate=16000),
+    "c3": dict(sample_rate=22050, fft_points=2048, frame_length=512 / 22050, frame_stride=0.01, num_cepstral=13,
+               num_filters=128, low_frequency=0.0, high_frequency=11025.0),
+    "c4": dict(sample_rate=16000, fft_points=400, frame_length=0.01, frame_stride=0.01, num_cepstral=13,
+               num_filters=80, low_frequency=0.0, high_frequency=8000.0),
+    "odd": dict(sample_rate=8000, fft_points=256, frame_length=0.03, frame_stride=0.0125, num_cepstral=12,
+                num_filters=26, low_frequency=100.0, high_frequency=3800.0),
+}
+
+
+def test_header_symbols_all_exported_and_bound():
+    header = (ROOT / "include" / "speechsauce_cuda.h").read_text()
+    declared = set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ss_plan", "ss_config", "ss_status", "ss_plan_info", "ss_feature_outputs"}
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(sb.lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert b"sm_100a" in sb.lib.ss_version()
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_derived_sizes_and_tables_match_oracle(name):
+    kw = CONFIGS[name]
+    cfg = sb.SpeechConfig(**kw, devices=[])  # host-only plan
+    oc = o.SpeechConfig(**kw)
+    assert cfg.frame_sample_length == oc.frame_sample_length
+    assert cfg.frame_step == oc.frame_step
+    assert cfg.frame_size == oc.frame_size
+    assert cfg.freq_size == oc.freq_size
+    assert np.float32(cfg.wnorm) == np.float32(oc.wnorm)
+    np.testing.assert_array_equal(cfg.window, oc.window)
+    fb = o.filterbanks(oc.num_filters, oc.freq_size, oc.sample_rate, oc.low_frequency, oc.high_frequency)
+    np.testing.assert_array_equal(cfg.filterbank(), fb)
+    stft_ok = 0 < oc.frame_size and 2 * oc.frame_size <= oc.window_size
+    assert cfg.n_pad == (oc.window_size // oc.frame_size - 1 if stft_ok else -1)
+
+
+def test_frame_counts_follow_reference_f32_arithmetic():
+    for n, L, S in [(16000, 400, 160), (16000, 320, 160), (10**6, 320, 160), (57_600_000, 400, 160), (401, 400, 160),
+                    (123457, 400, 160), (2**24 + 3, 400, 160)]:
+        for zp in (0, 1):
+            try:
+                want = o.num_frames(n, L, S, bool(zp))
+                if not zp and want < 1:
+                    want = -1
+            except ValueError:
+                want = -1
+            assert sb.lib.ss_num_frames(n, L, S, zp) == want, (n, L, S, zp)
+    assert sb.lib.ss_num_frames(399, 400, 160, 0) == -1  # usize underflow in the reference
+    for ttd, H in [(110250, 512), (480000, 160), (1, 160), (0, 160), (161, 160)]:
+        assert sb.lib.ss_stft_num_frames(ttd, H) == o.stft_num_frames(ttd, H)
+
+
+def test_invalid_configs_are_errors_not_aborts():
+    with pytest.raises(sb.SpeechsauceError, match="High frequency"):
+        sb.SpeechConfig(16000, high_frequency=9000.0, devices=[])      # feature.rs:47-50
+    with pytest.raises(sb.SpeechsauceError, match="low frequency"):
+        sb.SpeechConfig(16000, low_frequency=-1.0, devices=[])         # feature.rs:51
+    with pytest.raises(sb.SpeechsauceError):
+        sb.SpeechConfig(16000, num_cepstral=41, devices=[])            # slice ..num_cepstral out of range
+
+
+def test_no_cpu_fallback_without_device():
+    if sb.lib.ss_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], devices=[])
+    x = np.zeros(16000, np.float32)
+    for fn in (lambda: sb.feature.mfcc(x, cfg), lambda: sb.feature.mfe(x, cfg),
+               lambda: sb.processing.preemphasis(x), lambda: sb.processing.cmvn(np.zeros((4, 3), np.float32)),
+               lambda: sb.processing.power_spectrum(np.zeros((2, 400), np.float32)),
+               lambda: sb.SpeechConfig(16000)):
+        with pytest.raises(sb.SpeechsauceError) as ei:
+            fn()
+        assert ei.value.code == _lib.SS_ERR_NO_DEVICE
+
+
+def test_argument_errors_precede_device_checks():
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], devices=[])
+    with pytest.raises(sb.SpeechsauceError) as ei:
+        sb.feature.mfcc(np.zeros(300, np.float32), cfg)      # N < L: usize underflow in the reference
+    assert ei.value.code == _lib.SS_ERR_INVALID_ARG
+    dflt = sb.SpeechConfig(16000, devices=[])                # default config: H = 320 > W/2 (Q13)
+    with pytest.raises(sb.SpeechsauceError) as ei:
+        sb.functions.stft2(np.zeros((1, 4000), np.float32), dflt)
+    assert ei.value.code == _lib.SS_ERR_INVALID_ARG
+    with pytest.raises(TypeError):
+        sb.feature.mfcc(np.zeros(16000, np.float64), cfg)    # f32 only (README.md:17)
