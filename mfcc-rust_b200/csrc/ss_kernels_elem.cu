@@ -42,22 +42,23 @@ __global__ void __launch_bounds__(256) k_preemphasis(const float* __restrict__ i
         r[u] = __ldg(x + jj);
       }
       float4 o;
-      o.x = a.x - cof * r[0];
-      o.y = a.y - cof * r[1];
-      o.z = a.z - cof * r[2];
-      o.w = a.w - cof * r[3];
+      // two roundings like the reference's `signal - (cof * rolled)`: no FMA contraction
+      o.x = __fsub_rn(a.x, __fmul_rn(cof, r[0]));
+      o.y = __fsub_rn(a.y, __fmul_rn(cof, r[1]));
+      o.z = __fsub_rn(a.z, __fmul_rn(cof, r[2]));
+      o.w = __fsub_rn(a.w, __fmul_rn(cof, r[3]));
       *reinterpret_cast<float4*>(y + i) = o;
     }
     for (int64_t i = (n4 << 2) + tid; i < n; i += nthreads) {
       int64_t j = i - shift_mod;
       if (j < 0) j += n;
-      y[i] = x[i] - cof * x[j];
+      y[i] = __fsub_rn(x[i], __fmul_rn(cof, x[j]));
     }
   } else {
     for (int64_t i = tid; i < n; i += nthreads) {
       int64_t j = i - shift_mod;
       if (j < 0) j += n;
-      y[i] = x[i] - cof * x[j];
+      y[i] = __fsub_rn(x[i], __fmul_rn(cof, x[j]));
     }
   }
 }

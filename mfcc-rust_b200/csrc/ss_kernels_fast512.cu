@@ -5,18 +5,21 @@
 // power_spectrum, cmvn} (processing.rs:65-181,265-300) for this FFT size.
 //
 // Mapping (see DESIGN.md "fast512"):
-//   * two consecutive real frames A, B are packed as z = A + iB into ONE complex 512-point FFT,
-//     computed by 16 threads (a half-warp) holding 32 complex points each;
-//   * 512 = 32 x 16 (four-step): stage 1 is a 32-point DIT FFT entirely in registers with
-//     compile-time twiddles (6-FFMA butterflies), then the W512^{u*k1} twiddle from a shared
+//   * one real frame = one 256-point complex FFT of z[m] = x[2m] + i x[2m+1] plus the real-FFT
+//     post-processing step, computed by 8 threads (a quarter-warp) holding 32 complex points
+//     each.  Frames are NOT packed two-per-complex-FFT: that trick leaks ~1e-7 of a loud frame
+//     into its partner, which breaks the reference's exact zero_handling on silent frames;
+//   * 256 = 32 x 8 (four-step): stage 1 is a 32-point DIT FFT entirely in registers with
+//     compile-time twiddles (6-FFMA butterflies), then the W256^{u*k1} twiddle from a shared
 //     table, ONE transpose through shared memory (padded, conflict-free, warp-local: only
-//     __syncwarp), stage 2 is two 16-point register FFTs per thread;
-//   * thread u owns output groups k1 = u and k1 = 32-u (u = 0: 0 and 16), so Z[k] and Z[512-k]
-//     sit in the same thread and the A/B spectra separate without another exchange;
-//   * a warp = 2 pairs = 4 consecutive frames; warps never synchronise with each other until the
-//     optional per-clip CMVN at the end of a clip.
+//     __syncwarp), stage 2 is four 8-point register FFTs per thread;
+//   * thread u owns output groups k1 = {u, 32-u, 16-u, 16+u} (u = 0: {0, 16, 8, 24}), so Z[k] and
+//     Z[256-k] sit in the same thread and the post-processing needs no second exchange;
+//   * a warp = 4 consecutive frames; warps never synchronise with each other until the optional
+//     per-clip CMVN at the end of a clip.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <type_traits>
 #include <vector>
 
@@ -28,11 +31,11 @@ namespace {
 
 constexpr int kWarps = 5;
 constexpr int kThreads = kWarps * 32;
-constexpr int kXs = 17;                      // exchange row stride in float2 (16 + 1 pad)
-constexpr int kXchPair = 32 * kXs;           // float2 per pair
-constexpr int kWarpFloats = 2 * kXchPair * 2;  // floats per warp (2 pairs) = 2176
+constexpr int kXs = 10;                      // exchange row stride in float2 (8 + 2 pad: 16-byte rows, conflict-free LDS.128)
+constexpr int kXchFrame = 32 * kXs + 8;      // float2 per frame; +8 shifts the next frame by half the banks
+constexpr int kWarpFloats = 4 * kXchFrame * 2;  // floats per warp (4 frames) = 2624
 constexpr int kPs = 264;                     // P row stride (floats); 264 % 32 == 8
-constexpr int kNfMax = 64, kNcMax = 16, kNwMax = 640, kSlots = 4;
+constexpr int kNfMax = 64, kNcMax = 16, kNwMax = 640, kSlots = 8;
 constexpr int kRow = 68;                     // row stride of log_s and the DCT rows (68/4 odd)
 // per-warp float offsets after the exchange buffer has been consumed
 constexpr int kOffP = 0;
@@ -42,13 +45,17 @@ constexpr int kOffLog = kOffSsc + 4 * kNfMax;  // 1568
 static_assert(kOffLog + 4 * kRow <= kWarpFloats, "per-warp scratch overflows the exchange buffer");
 
 // CTA-shared table blob (float units)
-constexpr int kTabTw = 0;                       // [32][16] float2
-constexpr int kTabFw = kTabTw + 32 * 16 * 2;    // [kNwMax]
-constexpr int kTabFw2 = kTabFw + kNwMax;        // [kNwMax]  w * R[bin] (SSC)
+constexpr int kTwRow = 68;                      // floats per thread row of the W256 table (64 + 4 pad)
+constexpr int kTabTw = 0;                       // [8][kTwRow]: row u = W256^{u k1}, k1 = 0..31 (float2)
+constexpr int kTabTw512 = kTabTw + 8 * kTwRow;  // [256] float2: W512^k, k = 0..255
+constexpr int kTabFw = kTabTw512 + 256 * 2;     // [kNwMax]  w * (1/2n_fft)
+constexpr int kTabFw2 = kTabFw + kNwMax;        // [kNwMax]  w * R[bin] * (1/2n_fft) (SSC)
 constexpr int kTabDct = kTabFw2 + kNwMax;       // [kNcMax][kRow]
-constexpr int kTabSched = kTabDct + kNcMax * kRow;  // int [16][kSlots][4] = filt, b0, len, wofs
-constexpr int kTabNslot = kTabSched + 16 * kSlots * 4;  // int [16]
-constexpr int kTabFloats = kTabNslot + 16;
+constexpr int kTabSched = kTabDct + kNcMax * kRow;  // int [kSlots][8][4] = filt, b0, len, wofs
+constexpr int kTabNslot = kTabSched + 8 * kSlots * 4;  // int [8]
+constexpr int kTabFloats = kTabNslot + 8;
+static_assert(kTabTw512 % 4 == 0 && kTabDct % 4 == 0 && kTabSched % 4 == 0 && kTabFloats % 4 == 0,
+              "16-byte alignment of table sections");
 
 template <int I, int E, class F>
 __device__ __forceinline__ void sfor(F&& f) {
@@ -122,8 +129,8 @@ __device__ __forceinline__ void fft_regs(float2 (&x)[R]) {
   dit_level<R, BITS, 2, JNZ>(t);
   dit_level<R, BITS, 4, R>(t);
   dit_level<R, BITS, 8, R>(t);
-  dit_level<R, BITS, 16, R>(t);
-  if constexpr (R == 32) dit_level<R, BITS, 32, R>(t);
+  if constexpr (R >= 16) dit_level<R, BITS, 16, R>(t);
+  if constexpr (R >= 32) dit_level<R, BITS, 32, R>(t);
   sfor<0, R>([&](auto i) { x[decltype(i)::value] = t[decltype(i)::value]; });
 }
 
@@ -141,10 +148,32 @@ struct FastArgs {
   int quads_per_clip, chunk_quads, chunks_per_clip;
   int fuse_cmvn;      // 0 none, 1 mean, 2 mean+var: whole clip in one CTA, stash in smem
   int stash_floats;
+  int store_hi;       // some filter reads a bin above 128: keep the upper half of P in smem
 };
 
-template <int JMAX>
-__global__ void __launch_bounds__(kThreads, 3) k_fast512(const FastArgs a) {
+// one (k, 256-k) pair of the real-FFT post-processing:
+//   E = (Za + conj Zb)/2, O = (Za - conj Zb)/(2i), T = W512^k O, X[k] = E + T, X[256-k] = conj(E - T).
+// Returns 2|X[k]|, 2|X[256-k]| (the common 1/2 and the 1/n_fft of processing.rs:180 are folded
+// into the mel weights and the energy scale).
+__device__ __forceinline__ float2 rfft_pair_mag(float2 za, float2 zb, float2 w) {
+  const float ex = za.x + zb.x, ey = za.y - zb.y;
+  const float ox = za.y + zb.y, oy = zb.x - za.x;
+  const float tx = ox * w.x - oy * w.y, ty = ox * w.y + oy * w.x;
+  const float ax = ex + tx, ay = ey + ty, bx = ex - tx, by = ey - ty;
+  float2 r;
+  r.x = fast_sqrt(fmaf(ax, ax, ay * ay));
+  r.y = fast_sqrt(fmaf(bx, bx, by * by));
+  return r;
+}
+
+// JMAX: number of 16-sample column groups that can be non-zero (ceil(L/16));
+// EXACT: L == 16*JMAX and every frame start is 8-byte aligned -> unpredicated float2 loads;
+// SSC: also accumulate the spectral-subband-centroid numerator.
+template <int JMAX, bool EXACT, bool SSC>
+#ifndef SS_FAST_MINB
+#define SS_FAST_MINB 3
+#endif
+__global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
   float* warp_s = smem + kTabFloats + (threadIdx.x >> 5) * kWarpFloats;
@@ -154,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fast512(const FastArgs a) {
   for (int i = threadIdx.x; i < kTabFloats; i += kThreads) tab_s[i] = __ldg(a.tab + i);
   __syncthreads();
 
-  const float2* tw_s = reinterpret_cast<const float2*>(tab_s + kTabTw);
+  const float2* tw512_s = reinterpret_cast<const float2*>(tab_s + kTabTw512);
   const float* fw_s = tab_s + kTabFw;
   const float* fw2_s = tab_s + kTabFw2;
   const float* dct_s = tab_s + kTabDct;
@@ -162,19 +191,22 @@ __global__ void __launch_bounds__(kThreads, 3) k_fast512(const FastArgs a) {
   const int* nslot_s = reinterpret_cast<const int*>(tab_s + kTabNslot);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int h = lane >> 4, u = lane & 15;
+  const int fi = lane >> 3, u = lane & 7;  // frame within the quad, thread within the frame
+  const float4* twrow = reinterpret_cast<const float4*>(tab_s + kTabTw + u * kTwRow);
   const int nf = p.nf, nc = p.nc, L = p.L;
   const int64_t T = p.T;
   const bool isz = (u == 0);
-  const int k1b = isz ? 16 : 32 - u;
-  const float mscale = 0.5f * p.mag_scale;  // the 1/2 of the A/B separation folded into 1/n_fft
+  // output groups owned by this thread (k = k1 + 32 k2): A/B and C/D are mirror partners
+  const int k1B = isz ? 16 : 32 - u, k1C = isz ? 8 : 16 - u, k1D = isz ? 24 : 16 + u;
+  const float mscale = 0.5f * p.mag_scale;  // the 1/2 of E/O and 1/n_fft (processing.rs:180)
   const bool want_mel = p.mfe || p.lmfe || p.ssc || p.mfcc;
 
-  float2* xch = reinterpret_cast<float2*>(warp_s) + h * kXchPair;  // this pair's transpose buffer
+  float2* xch = reinterpret_cast<float2*>(warp_s) + fi * kXchFrame;  // this frame's transpose buffer
   float* P_s = warp_s + kOffP;
   float* mel_s = warp_s + kOffMel;
   float* ssc_s = warp_s + kOffSsc;
   float* log_s = warp_s + kOffLog;
+  float* Pf = P_s + fi * kPs;
 
   for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int64_t clip = item / a.chunks_per_clip;
@@ -184,177 +216,190 @@ __global__ void __launch_bounds__(kThreads, 3) k_fast512(const FastArgs a) {
 
     for (int q = chunk * a.chunk_quads + warp; q < q_end; q += kWarps) {
       const int64_t fq = 4 * (int64_t)q;  // first frame of the quad
-      const int64_t fA = fq + 2 * h, fB = fA + 1;
-      const bool vA = fA < T, vB = fB < T;
+      const int64_t fr = fq + fi;
+      const bool valid = fr < T;
 
-      // ---- framing: v[j] = (A[u + 16 j], B[u + 16 j]); zero beyond L (processing.rs:147-156)
+      // ---- framing: v[j] = x[2m] + i x[2m+1], m = u + 8 j; zero beyond L (processing.rs:147-156)
       float2 v[32];
       {
-        const float* pa = rowp + fA * p.S + u;
-        const float* pb = pa + p.S;
+        // an out-of-range frame of the last quad re-reads frame T-1 (always in bounds); its
+        // results are never stored
+        const float* px = rowp + (valid ? fr : T - 1) * p.S + 2 * u;
         sfor<0, 32>([&](auto jj) {
           constexpr int j = decltype(jj)::value;
-          if constexpr (j < JMAX) {
-            const bool in = (u + 16 * j) < L;
-            v[j].x = (vA && in) ? __ldg(pa + 16 * j) : 0.0f;
-            v[j].y = (vB && in) ? __ldg(pb + 16 * j) : 0.0f;
-          } else {
+          if constexpr (j >= JMAX) {
             v[j] = make_float2(0.0f, 0.0f);
+          } else if constexpr (EXACT) {
+            v[j] = __ldg(reinterpret_cast<const float2*>(px + 16 * j));
+          } else {
+            const int n0 = 2 * u + 16 * j;
+            v[j].x = (n0 < L) ? __ldg(px + 16 * j) : 0.0f;
+            v[j].y = (n0 + 1 < L) ? __ldg(px + 16 * j + 1) : 0.0f;
           }
         });
       }
       // ---- stage 1: 32-point FFT over j, in registers
       fft_regs<32, 5, JMAX>(v);
-      // ---- twiddle W512^{u k1} and transpose through shared memory
+      // ---- twiddle W256^{u k1} (two per LDS.128) and transpose through shared memory
       __syncwarp();  // previous quad's readers of this buffer are done
-      sfor<0, 32>([&](auto kk) {
-        constexpr int k1 = decltype(kk)::value;
-        float2 y = v[k1];
-        if constexpr (k1 > 0) {
-          const float2 w = tw_s[k1 * 16 + u];
-          y = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
-        }
-        xch[k1 * kXs + u] = y;
+      sfor<0, 16>([&](auto kk) {
+        constexpr int k1 = 2 * decltype(kk)::value;
+        const float4 w = twrow[k1 / 2];
+        float2 y0 = v[k1], y1 = v[k1 + 1];
+        if constexpr (k1 > 0) y0 = make_float2(y0.x * w.x - y0.y * w.y, y0.x * w.y + y0.y * w.x);
+        y1 = make_float2(y1.x * w.z - y1.y * w.w, y1.x * w.w + y1.y * w.z);
+        xch[k1 * kXs + u] = y0;
+        xch[(k1 + 1) * kXs + u] = y1;
       });
       __syncwarp();
-      float2 g1[16], g2[16];
-      sfor<0, 16>([&](auto tt) {
-        constexpr int t = decltype(tt)::value;
-        g1[t] = xch[u * kXs + t];
-        g2[t] = xch[k1b * kXs + t];
-      });
+      float2 gA[8], gB[8], gC[8], gD[8];
+      {
+        const float4* rA = reinterpret_cast<const float4*>(xch + u * kXs);
+        const float4* rB = reinterpret_cast<const float4*>(xch + k1B * kXs);
+        const float4* rC = reinterpret_cast<const float4*>(xch + k1C * kXs);
+        const float4* rD = reinterpret_cast<const float4*>(xch + k1D * kXs);
+        sfor<0, 4>([&](auto tt) {
+          constexpr int t = decltype(tt)::value;
+          const float4 xa = rA[t], xb = rB[t], xc = rC[t], xd = rD[t];
+          gA[2 * t] = make_float2(xa.x, xa.y); gA[2 * t + 1] = make_float2(xa.z, xa.w);
+          gB[2 * t] = make_float2(xb.x, xb.y); gB[2 * t + 1] = make_float2(xb.z, xb.w);
+          gC[2 * t] = make_float2(xc.x, xc.y); gC[2 * t + 1] = make_float2(xc.z, xc.w);
+          gD[2 * t] = make_float2(xd.x, xd.y); gD[2 * t + 1] = make_float2(xd.z, xd.w);
+        });
+      }
       __syncwarp();  // the buffer is reused for P / mel / log below
-      // ---- stage 2: 16-point FFTs over t
-      fft_regs<16, 4, 16>(g1);
-      fft_regs<16, 4, 16>(g2);
+      // ---- stage 2: 8-point FFTs over t.  g?[k2] = Z[k1? + 32 k2]
+      fft_regs<8, 3, 8>(gA);
+      fft_regs<8, 3, 8>(gB);
+      fft_regs<8, 3, 8>(gC);
+      fft_regs<8, 3, 8>(gD);
 
-      // ---- separate A / B spectra, magnitude (processing.rs:168,180), frame energy
-      float eA = 0.f, eB = 0.f;
-      float* PA = P_s + (2 * h) * kPs;
-      float* PB = PA + kPs;
-      sfor<0, 8>([&](auto mm) {
-        constexpr int m = decltype(mm)::value;
-        {  // bin u + 32 m
-          const float2 Z = g1[m];
-          const float2 Zm = isz ? g1[(16 - m) & 15] : g2[15 - m];
-          const float ax = Z.x + Zm.x, ay = Z.y - Zm.y, bx = Z.y + Zm.y, by = Zm.x - Z.x;
-          const float ma = mscale * fast_sqrt(fmaf(ax, ax, ay * ay));
-          const float mb = mscale * fast_sqrt(fmaf(bx, bx, by * by));
-          PA[u + 32 * m] = ma;
-          PB[u + 32 * m] = mb;
-          eA += ma;
-          eB += mb;
+      // ---- real-FFT post-processing + magnitude (processing.rs:168,180) + frame energy.
+      // u != 0: slot s pairs Z[u+32s] (gA[s]) with Z[256-(u+32s)] = gB[7-s]; likewise gC/gD.
+      // u == 0: groups 0 and 16 are their own mirrors: s=0 -> k=0 (gives bins 0 and 256),
+      //         s=1..3 -> (gA[s], gA[8-s]); s=4..7 -> (gB[s-4], gB[11-s]); bin 128 = |gA[4]| below.
+      float esum = 0.f;
+      sfor<0, 8>([&](auto ss_) {
+        constexpr int s = decltype(ss_)::value;
+        {
+          float2 za, zb;
+          int k;
+          if constexpr (s == 0) {
+            za = gA[0];
+            zb = isz ? gA[0] : gB[7];
+            k = u;
+          } else if constexpr (s < 4) {
+            za = gA[s];
+            zb = isz ? gA[8 - s] : gB[7 - s];
+            k = u + 32 * s;
+          } else {
+            za = isz ? gB[s - 4] : gA[s];
+            zb = isz ? gB[11 - s] : gB[7 - s];
+            k = isz ? 16 + 32 * (s - 4) : u + 32 * s;
+          }
+          const float2 m = rfft_pair_mag(za, zb, tw512_s[k]);
+          // k <= 128 exactly when s < 4 (u == 0: always); the other bin of the pair is >= 128
+          if constexpr (s < 4) {
+            Pf[k] = m.x;
+            if (a.store_hi || k == 0) Pf[256 - k] = m.y;
+          } else {
+            if (isz || a.store_hi) Pf[k] = m.x;
+            if (!isz || a.store_hi) Pf[256 - k] = m.y;
+          }
+          esum += m.x + m.y;
         }
-        {  // bin k1b + 32 m
-          const float2 Z = g2[m];
-          const float2 Zm = isz ? g2[15 - m] : g1[15 - m];
-          const float ax = Z.x + Zm.x, ay = Z.y - Zm.y, bx = Z.y + Zm.y, by = Zm.x - Z.x;
-          const float ma = mscale * fast_sqrt(fmaf(ax, ax, ay * ay));
-          const float mb = mscale * fast_sqrt(fmaf(bx, bx, by * by));
-          PA[k1b + 32 * m] = ma;
-          PB[k1b + 32 * m] = mb;
-          eA += ma;
-          eB += mb;
+        {
+          const int k = k1C + 32 * s;
+          const float2 m = rfft_pair_mag(gC[s], gD[7 - s], tw512_s[k]);
+          if constexpr (s < 4) {
+            Pf[k] = m.x;
+            if (a.store_hi) Pf[256 - k] = m.y;
+          } else {
+            if (a.store_hi) Pf[k] = m.x;
+            Pf[256 - k] = m.y;
+          }
+          esum += m.x + m.y;
         }
       });
-      if (isz) {  // bin 256 (self-mirrored): X_A = Re Z, X_B = Im Z
-        const float ma = 2.0f * mscale * fabsf(g1[8].x), mb = 2.0f * mscale * fabsf(g1[8].y);
-        PA[256] = ma;
-        PB[256] = mb;
-        eA += ma;
-        eB += mb;
+      if (isz) {  // bin 128: X[128] = conj(Z[128]); 2|X| to match the pairs
+        const float m = 2.0f * fast_sqrt(fmaf(gA[4].x, gA[4].x, gA[4].y * gA[4].y));
+        Pf[128] = m;
+        esum += m;
       }
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        eA += __shfl_xor_sync(0xffffffffu, eA, o);
-        eB += __shfl_xor_sync(0xffffffffu, eB, o);
-      }
-      eA = zero_handling(eA);  // feature.rs:219
-      eB = zero_handling(eB);
+      for (int o = 4; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+      const float energy = zero_handling(mscale * esum);  // feature.rs:216-219
       __syncwarp();
 
-      // ---- banded mel reduction (feature.rs:229-230): lane u owns a balanced set of filters
+      // ---- banded mel reduction (feature.rs:229-230).  Filters are sorted by length and dealt to
+      // the 8 lanes slot by slot, so the lanes of a slot run loops of similar length.
       if (want_mel) {
         const int ns = nslot_s[u];
         for (int s = 0; s < ns; ++s) {
-          const int4 e = *reinterpret_cast<const int4*>(sched_s + (u * kSlots + s) * 4);
-          const int filt = e.x, b0 = e.y, len = e.z, wo = e.w;
-          float accA = 0.f, accB = 0.f, numA = 0.f, numB = 0.f;
+          const int4 e = *reinterpret_cast<const int4*>(sched_s + (s * 8 + u) * 4);
+          const int filt = e.x, len = e.z;
+          const float* pp = Pf + e.y;
+          const float* pw = fw_s + e.w;
+          const float* pw2 = fw2_s + e.w;
+          float acc = 0.f, num = 0.f;
+#pragma unroll 4
           for (int i = 0; i < len; ++i) {
-            const float w = fw_s[wo + i], w2 = fw2_s[wo + i];
-            const float pa = PA[b0 + i], pb = PB[b0 + i];
-            accA = fmaf(w, pa, accA);
-            accB = fmaf(w, pb, accB);
-            numA = fmaf(w2, pa, numA);
-            numB = fmaf(w2, pb, numB);
+            const float pv = pp[i];
+            acc = fmaf(pw[i], pv, acc);
+            if (SSC) num = fmaf(pw2[i], pv, num);
           }
-          accA = zero_handling(accA);
-          accB = zero_handling(accB);
-          const int oA = (2 * h) * nf + filt, oB = oA + nf;
-          mel_s[oA] = accA;
-          mel_s[oB] = accB;
-          ssc_s[oA] = __fdividef(numA, accA);
-          ssc_s[oB] = __fdividef(numB, accB);
-          log_s[(2 * h) * kRow + filt] = __logf(accA);
-          log_s[(2 * h + 1) * kRow + filt] = __logf(accB);
+          acc = zero_handling(acc);
+          mel_s[fi * nf + filt] = acc;
+          if (SSC) ssc_s[fi * nf + filt] = __fdividef(num, acc);
+          log_s[fi * kRow + filt] = __logf(acc);
         }
         // zero the float4 padding of the log rows (the buffer held FFT data a moment ago)
-        if (u < ((nf + 3) & ~3) - nf) {
-          log_s[(2 * h) * kRow + nf + u] = 0.0f;
-          log_s[(2 * h + 1) * kRow + nf + u] = 0.0f;
-        }
+        if (u < ((nf + 3) & ~3) - nf) log_s[fi * kRow + nf + u] = 0.0f;
         __syncwarp();
       }
 
       // ---- stores: [clip][t][nf] blocks, 4 consecutive frames = 4*nf contiguous floats
       const int64_t fbase = clip * T + fq;
       const int nvalid = (int)min((int64_t)4, T - fq);
-      if (p.mfe || p.lmfe || p.ssc) {
+      if (p.mfe || p.lmfe || (SSC && p.ssc)) {
         const int tot = nvalid * nf;
         for (int i = lane; i < tot; i += 32) {
           if (p.mfe) p.mfe[fbase * nf + i] = mel_s[i];
-          if (p.ssc) p.ssc[fbase * nf + i] = ssc_s[i];
+          if (SSC && p.ssc) p.ssc[fbase * nf + i] = ssc_s[i];
           if (p.lmfe) {
-            const int fr = i / nf;
-            p.lmfe[fbase * nf + i] = log_s[fr * kRow + (i - fr * nf)];
+            const int f = (i >= nf) + (i >= 2 * nf) + (i >= 3 * nf);
+            p.lmfe[fbase * nf + i] = log_s[f * kRow + (i - f * nf)];
           }
         }
       }
-      if (p.energy && isz) {
-        if (vA) p.energy[clip * T + fA] = eA;
-        if (vB) p.energy[clip * T + fB] = eB;
-      }
-      // ---- ln -> DCT-II -> scale -> c0 (feature.rs:105-146); lane = (pair h, cepstrum u)
-      if (p.mfcc && u < nc) {
-        const float4* la = reinterpret_cast<const float4*>(log_s + (2 * h) * kRow);
-        const float4* lb = reinterpret_cast<const float4*>(log_s + (2 * h + 1) * kRow);
-        const float4* dr = reinterpret_cast<const float4*>(dct_s + u * kRow);
-        float accA = 0.f, accB = 0.f;
+      if (p.energy && isz && valid) p.energy[clip * T + fr] = energy;
+      // ---- ln -> DCT-II -> scale -> c0 (feature.rs:105-146); lane = (frame fi, cepstra u, u+8)
+      if (p.mfcc) {
+        const float4* lg = reinterpret_cast<const float4*>(log_s + fi * kRow);
         const int n4 = (nf + 3) >> 2;
+        const int c1 = u + 8;
+        const float4* d0 = reinterpret_cast<const float4*>(dct_s + u * kRow);
+        const float4* d1 = reinterpret_cast<const float4*>(dct_s + (c1 < nc ? c1 : u) * kRow);
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 2
         for (int i = 0; i < n4; ++i) {
-          const float4 d = dr[i], x = la[i], y = lb[i];
-          accA = fmaf(d.x, x.x, accA); accA = fmaf(d.y, x.y, accA);
-          accA = fmaf(d.z, x.z, accA); accA = fmaf(d.w, x.w, accA);
-          accB = fmaf(d.x, y.x, accB); accB = fmaf(d.y, y.y, accB);
-          accB = fmaf(d.z, y.z, accB); accB = fmaf(d.w, y.w, accB);
+          const float4 x = lg[i], da = d0[i], db = d1[i];
+          acc0 = fmaf(da.x, x.x, acc0); acc1 = fmaf(db.x, x.x, acc1);
+          acc0 = fmaf(da.y, x.y, acc0); acc1 = fmaf(db.y, x.y, acc1);
+          acc0 = fmaf(da.z, x.z, acc0); acc1 = fmaf(db.z, x.z, acc1);
+          acc0 = fmaf(da.w, x.w, acc0); acc1 = fmaf(db.w, x.w, acc1);
         }
         if (u == 0) {
-          if (p.dc_elim) {
-            accA = __logf(eA);
-            accB = __logf(eB);
-          } else if (fA == 0) {
-            accA *= p.scale_00;  // only element [0,0] gets the k=0 scale (feature.rs:128)
-          }
+          if (p.dc_elim) acc0 = __logf(energy);
+          else if (fr == 0) acc0 *= p.scale_00;  // only element [0,0] gets the k=0 scale (feature.rs:128)
         } else {
-          accA *= p.scale_rest;
-          accB *= p.scale_rest;
+          acc0 *= p.scale_rest;
         }
-        if (a.fuse_cmvn) {
-          if (vA) stash[fA * nc + u] = accA;
-          if (vB) stash[fB * nc + u] = accB;
-        } else {
-          if (vA) p.mfcc[(clip * T + fA) * nc + u] = accA;
-          if (vB) p.mfcc[(clip * T + fB) * nc + u] = accB;
+        acc1 *= p.scale_rest;
+        if (valid) {
+          float* dst = a.fuse_cmvn ? stash + fr * nc : p.mfcc + (clip * T + fr) * nc;
+          if (u < nc) dst[u] = acc0;
+          if (c1 < nc) dst[c1] = acc1;
         }
       }
     }
@@ -362,42 +407,52 @@ __global__ void __launch_bounds__(kThreads, 3) k_fast512(const FastArgs a) {
     // ---- per-clip CMVN (processing.rs:265-300) on the stashed [T][nc] block ---------------
     if (a.fuse_cmvn) {
       __syncthreads();
-      float* stat = stash + a.stash_floats;  // [nc][2]
+      // thread = (row lane r, column c): 10 row lanes x 16 columns; partials combined in a fixed order
+      float* part = stash + a.stash_floats;   // [10][16]
+      float* stat = part + 160;               // [16][2]
       const int Ti = (int)T;
-      for (int c = warp; c < nc; c += kWarps) {
-        float s = 0.f;
-        for (int t = lane; t < Ti; t += 32) s += stash[t * nc + c];
+      const int c = threadIdx.x & 15, r = threadIdx.x >> 4;
+      const bool cok = c < nc;
+      float s = 0.f;
+      if (cok) for (int t = r; t < Ti; t += 10) s += stash[t * nc + c];
+      part[r * 16 + c] = s;
+      __syncthreads();
+      float mean = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s / (float)Ti;
-        float inv = 1.0f;
-        if (a.fuse_cmvn == 2) {
-          // std of the mean-subtracted column, ddof 0 (two-pass: mean of y, then squares)
-          float s1 = 0.f;
-          for (int t = lane; t < Ti; t += 32) s1 += stash[t * nc + c] - mean;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          const float my = s1 / (float)Ti;
-          float s2 = 0.f;
-          for (int t = lane; t < Ti; t += 32) {
-            const float d = (stash[t * nc + c] - mean) - my;
-            s2 = fmaf(d, d, s2);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          inv = 1.0f / (sqrtf(s2 / (float)Ti) + kCmvnEps);
+      for (int i = 0; i < 10; ++i) mean += part[i * 16 + c];
+      mean /= (float)Ti;
+      __syncthreads();
+      if (a.fuse_cmvn == 2) {
+        // std of the mean-subtracted column y, ddof 0: sqrt(mean(y^2) - mean(y)^2), mean(y) ~ 0
+        float s1 = 0.f, s2 = 0.f;
+        if (cok) for (int t = r; t < Ti; t += 10) {
+          const float d = stash[t * nc + c] - mean;
+          s1 += d;
+          s2 = fmaf(d, d, s2);
         }
-        if (lane == 0) {
+        part[r * 16 + c] = s1;
+        part[160 + 32 + r * 16 + c] = s2;
+        __syncthreads();
+        if (r == 0) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) { t1 += part[i * 16 + c]; t2 += part[160 + 32 + i * 16 + c]; }
+          const float my = t1 / (float)Ti;
+          const float var = fmaxf(t2 / (float)Ti - my * my, 0.f);
           stat[2 * c] = mean;
-          stat[2 * c + 1] = inv;
+          stat[2 * c + 1] = 1.0f / (sqrtf(var) + kCmvnEps);
         }
+      } else if (r == 0) {
+        stat[2 * c] = mean;
+        stat[2 * c + 1] = 1.0f;
       }
       __syncthreads();
       float* dst = p.mfcc + clip * T * nc;
       const int tot = Ti * nc;
-      for (int i = threadIdx.x; i < tot; i += kThreads) {
-        const int c = i % nc;
-        dst[i] = (stash[i] - stat[2 * c]) * stat[2 * c + 1];
+      for (int i = threadIdx.x, cc = threadIdx.x % nc; i < tot; i += kThreads) {
+        dst[i] = (stash[i] - stat[2 * cc]) * stat[2 * cc + 1];
+        cc += kThreads % nc;   // column of the next element without a division
+        if (cc >= nc) cc -= nc;
       }
       __syncthreads();  // the stash is rewritten by the next clip
     }
@@ -408,6 +463,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fast512(const FastArgs a) {
 
 struct Fast512Tables {
   float* d_tab = nullptr;
+  bool store_hi = true;
 };
 
 bool fast512_supported(const Derived& d, const MelBank& mb) {
@@ -420,45 +476,48 @@ bool fast512_supported(const Derived& d, const MelBank& mb) {
 int fast512_build_tables(const Derived& d, const MelBank& mb, Fast512Tables** out) {
   std::vector<float> h(kTabFloats, 0.f);
   const double pi = 3.14159265358979323846264338327950288;
-  for (int k1 = 0; k1 < 32; ++k1)
-    for (int u = 0; u < 16; ++u) {
-      const double ang = -2.0 * pi * (double)(u * k1) / 512.0;
-      h[kTabTw + 2 * (k1 * 16 + u)] = (float)std::cos(ang);
-      h[kTabTw + 2 * (k1 * 16 + u) + 1] = (float)std::sin(ang);
+  for (int u = 0; u < 8; ++u)
+    for (int k1 = 0; k1 < 32; ++k1) {
+      const double ang = -2.0 * pi * (double)(u * k1) / 256.0;
+      h[kTabTw + u * kTwRow + 2 * k1] = (float)std::cos(ang);
+      h[kTabTw + u * kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
     }
+  for (int k = 0; k < 256; ++k) {
+    const double ang = -2.0 * pi * (double)k / 512.0;
+    h[kTabTw512 + 2 * k] = (float)std::cos(ang);
+    h[kTabTw512 + 2 * k + 1] = (float)std::sin(ang);
+  }
+  // the kernel keeps 2*n_fft*|X| in shared memory; 1/(2 n_fft) is folded into the weights
+  const float mscale = 0.5f * (1.0f / (float)d.W);
   const float r0 = 1.0f, step = d.F > 1 ? ((float)d.cfg.sample_rate / 2.0f - 1.0f) / (float)(d.F - 1) : 0.f;
   for (int i = 0; i < d.nf; ++i)
     for (int k = 0; k < mb.len[i]; ++k) {
       const float w = mb.w[mb.wofs[i] + k];
-      h[kTabFw + mb.wofs[i] + k] = w;
-      h[kTabFw2 + mb.wofs[i] + k] = w * (r0 + step * (float)(mb.start[i] + k));
+      h[kTabFw + mb.wofs[i] + k] = w * mscale;
+      h[kTabFw2 + mb.wofs[i] + k] = w * (r0 + step * (float)(mb.start[i] + k)) * mscale;
     }
   std::vector<float> dct;
   build_dct(d, &dct);
   for (int c = 0; c < d.nc; ++c)
     for (int n = 0; n < d.nf; ++n) h[kTabDct + c * kRow + n] = dct[(size_t)c * d.nf + n];
-  std::vector<std::vector<int>> per_lane;
-  balance_filters(mb, 16, &per_lane);
-  bool ok = true;
-  for (auto& v : per_lane) ok = ok && (int)v.size() <= kSlots;
-  if (!ok) {
-    per_lane.assign(16, {});
-    for (int i = 0; i < d.nf; ++i) per_lane[i % 16].push_back(i);
-  }
+  // filters sorted by length, dealt round-robin: slot s of the 8 lanes holds filters of similar
+  // length, which minimises the sum over slots of the longest loop in the slot
+  std::vector<int> order(d.nf);
+  for (int i = 0; i < d.nf; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return mb.len[x] > mb.len[y]; });
   int* sched = reinterpret_cast<int*>(h.data() + kTabSched);
   int* nslot = reinterpret_cast<int*>(h.data() + kTabNslot);
-  for (int l = 0; l < 16; ++l) {
-    nslot[l] = (int)per_lane[l].size();
-    for (int s = 0; s < (int)per_lane[l].size(); ++s) {
-      const int f = per_lane[l][s];
-      int* e = sched + (l * kSlots + s) * 4;
-      e[0] = f;
-      e[1] = mb.start[f];
-      e[2] = mb.len[f];
-      e[3] = mb.wofs[f];
-    }
+  for (int i = 0; i < d.nf; ++i) {
+    const int s = i / 8, l = i % 8, f = order[i];
+    int* e = sched + (s * 8 + l) * 4;
+    e[0] = f;
+    e[1] = mb.start[f];
+    e[2] = mb.len[f];
+    e[3] = mb.wofs[f];
+    nslot[l] = s + 1;
   }
   Fast512Tables* t = new Fast512Tables;
+  t->store_hi = mb.max_bin > 128;
   cudaError_t e = cudaMalloc(&t->d_tab, kTabFloats * sizeof(float));
   if (e != cudaSuccess) { delete t; return (int)e; }
   e = cudaMemcpy(t->d_tab, h.data(), kTabFloats * sizeof(float), cudaMemcpyHostToDevice);
@@ -499,20 +558,23 @@ int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, v
   }
   a.chunks_per_clip = (int)((qpc + a.chunk_quads - 1) / a.chunk_quads);
   a.n_items = p.n_rows * a.chunks_per_clip;
-  const size_t smem = (size_t)(kTabFloats + kWarps * kWarpFloats + a.stash_floats + (fuse ? 2 * kNcMax : 0)) * sizeof(float);
-  const int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sm_count * 3);
+  a.store_hi = t->store_hi ? 1 : 0;
+  const size_t smem = (size_t)(kTabFloats + kWarps * kWarpFloats + a.stash_floats + (fuse ? 160 + 32 + 160 : 0)) * sizeof(float);
+  const int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sm_count * SS_FAST_MINB);
   if (grid <= 0) return 0;
-  const int jn = (p.L + 15) / 16;
+  // float2 loads need every frame start 8-byte aligned: even stride / step and an aligned base
+  const bool vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
+  const bool ssc = p.ssc != nullptr;
   cudaError_t e;
-#define SS_LAUNCH_FAST(J)                                                                                  \
+#define SS_LAUNCH_FAST(J, X, C)                                                                            \
   do {                                                                                                     \
-    e = cudaFuncSetAttribute(k_fast512<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    e = cudaFuncSetAttribute(k_fast512<J, X, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     if (e != cudaSuccess) return (int)e;                                                                   \
-    k_fast512<J><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);                             \
+    k_fast512<J, X, C><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);                       \
   } while (0)
-  if (jn <= 20) SS_LAUNCH_FAST(20);
-  else if (jn <= 25) SS_LAUNCH_FAST(25);
-  else SS_LAUNCH_FAST(32);
+  if (vec2 && p.L == 320) { if (ssc) SS_LAUNCH_FAST(20, true, true); else SS_LAUNCH_FAST(20, true, false); }
+  else if (vec2 && p.L == 400) { if (ssc) SS_LAUNCH_FAST(25, true, true); else SS_LAUNCH_FAST(25, true, false); }
+  else { if (ssc) SS_LAUNCH_FAST(32, false, true); else SS_LAUNCH_FAST(32, false, false); }
 #undef SS_LAUNCH_FAST
   count_launch();
   e = cudaGetLastError();

@@ -1,9 +1,13 @@
 // Generic frame pipeline for any FFT length that factors into primes <= 61.
 //
-// One CTA processes a tile of TF = 2*PPC consecutive frames of one row (clip / channel).
-// Two real frames are packed into one complex FFT (z = a + i b); the transform is a Stockham
-// autosort FFT that ping-pongs between two shared-memory buffers, radix 4/2 and odd radices
-// through a small O(R^2) DFT with table twiddles.  Everything after the FFT (separation of
+// One CTA processes a tile of 8 (or fewer, for long FFTs) consecutive frames of one row
+// (clip / channel), one thread group per frame.  Each real frame goes through a half-length
+// complex FFT (z[m] = x[2m] + i x[2m+1]) plus the standard real-FFT post-processing step, so a
+// frame's rounding error is relative to that frame alone (two frames are deliberately NOT packed
+// into one complex FFT: the ~1e-7 crosstalk would turn an all-zero frame next to a loud one into
+// tiny non-zeros, and the reference's zero_handling -> EPS would no longer trigger).  The
+// transform is a Stockham autosort FFT that ping-pongs between two shared-memory buffers, radix
+// 4/2 and odd radices through a small O(R^2) DFT with table twiddles.  Everything after the FFT (separation of
 // the two spectra, magnitude, frame energy, banded mel reduction, ln, DCT-II, SSC) happens
 // on-chip; only final outputs are written.
 //
@@ -52,10 +56,11 @@ __device__ __forceinline__ float fetch_stream(const FrameParams& p, int64_t q) {
 
 template <int R>
 __device__ __forceinline__ void stockham_butterfly(const float2* __restrict__ src, float2* __restrict__ dst,
-                                                   const float2* __restrict__ tw, int N, int Ns, int j) {
+                                                   const float2* __restrict__ tw, int N, int Ns, int j,
+                                                   int twmul) {
   const int nb = N / R;
   const int k = j % Ns;
-  const int tstride = N / (Ns * R);
+  const int tstride = twmul * (N / (Ns * R));
   float2 v[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -75,7 +80,7 @@ __device__ __forceinline__ void stockham_butterfly(const float2* __restrict__ sr
     o[2] = csub(a, c);
     o[3] = csub(b, dmi);
   } else {
-    const int rstride = N / R;
+    const int rstride = twmul * (N / R);
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       float2 acc = v[0];
@@ -91,11 +96,11 @@ __device__ __forceinline__ void stockham_butterfly(const float2* __restrict__ sr
 
 // odd radices without a template instantiation (11..61): values live in local memory
 __device__ void stockham_butterfly_any(const float2* __restrict__ src, float2* __restrict__ dst,
-                                       const float2* __restrict__ tw, int N, int Ns, int R, int j) {
+                                       const float2* __restrict__ tw, int N, int Ns, int R, int j, int twmul) {
   const int nb = N / R;
   const int k = j % Ns;
-  const int tstride = N / (Ns * R);
-  const int rstride = N / R;
+  const int tstride = twmul * (N / (Ns * R));
+  const int rstride = twmul * (N / R);
   float2 v[61];
   for (int r = 0; r < R; ++r) {
     v[r] = src[j + r * nb];
@@ -109,141 +114,128 @@ __device__ void stockham_butterfly_any(const float2* __restrict__ src, float2* _
   }
 }
 
-__global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, const int ppc, const int tpg,
+__global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, const int fpc, const int tpg,
                                                         const int64_t tiles_per_row) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.N, F = p.F, nf = p.nf, nc = p.nc;
-  const int TF = 2 * ppc;
-  float2* fftbuf = reinterpret_cast<float2*>(smem_raw);  // [ppc][2][N]
-  float* mel_s = reinterpret_cast<float*>(fftbuf + (size_t)ppc * 2 * N);  // [TF][nf]
+  const bool even = (N & 1) == 0;
+  const int M = even ? N / 2 : N;  // complex FFT length: real FFT through a half-length complex FFT
+  const int twmul = even ? 2 : 1;  // the table holds W_N^q; the M-point FFT needs W_M = W_N^2
+  const int TF = fpc;
+  float2* fftbuf = reinterpret_cast<float2*>(smem_raw);                   // [fpc][2][M+1]
+  float* mel_s = reinterpret_cast<float*>(fftbuf + (size_t)fpc * 2 * (M + 1));  // [TF][nf]
   float* ssc_s = mel_s + TF * nf;                                         // [TF][nf]
   float* log_s = ssc_s + TF * nf;                                         // [TF][nf]
   float* energy_s = log_s + TF * nf;                                      // [TF]
-  float* red_s = energy_s + TF;                                           // [8 warps][2]
+  float* red_s = energy_s + TF;                                           // [8 warps]
 
   const int tid = threadIdx.x;
   const int g = tid / tpg, lt = tid % tpg;
   const int64_t row = blockIdx.x / tiles_per_row;
   const int64_t t0 = (blockIdx.x % tiles_per_row) * TF;
   const bool stft = p.mode == kModeStft;
-  const int64_t fA = t0 + 2 * g, fB = fA + 1;
-  float2* bufA = fftbuf + (size_t)g * 2 * N;
-  float2* bufB = bufA + N;
+  const int64_t fr = t0 + g;  // this thread group's frame
+  float2* bufA = fftbuf + (size_t)g * 2 * (M + 1);
+  float2* bufB = bufA + (M + 1);
 
-  // ---- 1. framing (+ window) straight into the FFT buffer --------------------------------
-  if (!stft) {
+  // ---- 1. framing (+ window) straight into the FFT buffer: z[m] = x[2m] + i x[2m+1] ---------
+  {
     const float* rowp = p.pcm + row * p.row_stride;
-    for (int n = lt; n < N; n += tpg)
-      bufA[n] = make_float2(fetch_speechpy(p, rowp, fA, n), fetch_speechpy(p, rowp, fB, n));
-  } else {
     const int64_t span = p.Tp * (int64_t)p.S;
     const int64_t memlen = p.N - p.S;
-    const int64_t rbase = memlen + row * span;  // stream index of this row's sample 0
-    const int64_t qA = row * span + (fA + p.n_pad) * (int64_t)p.S;
-    const int64_t qB = qA + p.S;
-    const float* rowp = p.pcm + row * p.row_stride;
-    for (int n = lt; n < N; n += tpg) {
-      float a = 0.f, b = 0.f;
-      const float w = __ldg(&p.tab.window[n]);
-      if (fA < p.T) {
-        int64_t q = qA + n;
-        if (q >= rbase) { int64_t o = q - rbase; a = o < p.row_len ? rowp[o] : 0.f; }
-        else a = fetch_stream(p, q);
+    const int64_t rbase = memlen + row * span;  // stream index of this row's sample 0 (STFT)
+    const int64_t q0 = row * span + (fr + p.n_pad) * (int64_t)p.S;
+    auto sample = [&](int n) -> float {
+      if (n >= N) return 0.f;
+      if (!stft) return fetch_speechpy(p, rowp, fr, n);
+      if (fr >= p.T) return 0.f;
+      const int64_t q = q0 + n;
+      float v;
+      if (q >= rbase) {
+        const int64_t o = q - rbase;
+        v = o < p.row_len ? rowp[o] : 0.f;
+      } else {
+        v = fetch_stream(p, q);
       }
-      if (fB < p.T) {
-        int64_t q = qB + n;
-        if (q >= rbase) { int64_t o = q - rbase; b = o < p.row_len ? rowp[o] : 0.f; }
-        else b = fetch_stream(p, q);
-      }
-      bufA[n] = make_float2(a * w, b * w);
-    }
+      return v * __ldg(&p.tab.window[n]);
+    };
+    if (even)
+      for (int m = lt; m < M; m += tpg) bufA[m] = make_float2(sample(2 * m), sample(2 * m + 1));
+    else
+      for (int m = lt; m < M; m += tpg) bufA[m] = make_float2(sample(m), 0.f);
   }
   __syncthreads();
 
-  // ---- 2. Stockham FFT -------------------------------------------------------------------
+  // ---- 2. Stockham FFT of length M ------------------------------------------------------------
   float2* src = bufA;
   float2* dst = bufB;
   int Ns = 1;
   for (int s = 0; s < p.tab.n_stages; ++s) {
     const int R = p.tab.radix[s];
-    const int nb = N / R;
+    const int nb = M / R;
     for (int j = lt; j < nb; j += tpg) {
       switch (R) {
-        case 2: stockham_butterfly<2>(src, dst, p.tab.tw, N, Ns, j); break;
-        case 4: stockham_butterfly<4>(src, dst, p.tab.tw, N, Ns, j); break;
-        case 3: stockham_butterfly<3>(src, dst, p.tab.tw, N, Ns, j); break;
-        case 5: stockham_butterfly<5>(src, dst, p.tab.tw, N, Ns, j); break;
-        case 7: stockham_butterfly<7>(src, dst, p.tab.tw, N, Ns, j); break;
-        default: stockham_butterfly_any(src, dst, p.tab.tw, N, Ns, R, j); break;
+        case 2: stockham_butterfly<2>(src, dst, p.tab.tw, M, Ns, j, twmul); break;
+        case 4: stockham_butterfly<4>(src, dst, p.tab.tw, M, Ns, j, twmul); break;
+        case 3: stockham_butterfly<3>(src, dst, p.tab.tw, M, Ns, j, twmul); break;
+        case 5: stockham_butterfly<5>(src, dst, p.tab.tw, M, Ns, j, twmul); break;
+        case 7: stockham_butterfly<7>(src, dst, p.tab.tw, M, Ns, j, twmul); break;
+        default: stockham_butterfly_any(src, dst, p.tab.tw, M, Ns, R, j, twmul); break;
       }
     }
     __syncthreads();
     float2* t = src; src = dst; dst = t;
     Ns *= R;
   }
-  const float2* X = src;                      // Z[k] = A[k] + i B[k]
-  float* PA = reinterpret_cast<float*>(dst);  // the other buffer is free now
-  float* PB = PA + F;
+  const float2* Z = src;                      // Z[k], k < M
+  float* P = reinterpret_cast<float*>(dst);   // the other buffer is free now: F <= 2(M+1) floats
 
-  // ---- 3. separate the two real spectra, magnitude / power -------------------------------
-  float eA = 0.f, eB = 0.f;
-  for (int k = lt; k < F; k += tpg) {
-    const float2 Z = X[k];
-    const float2 Zm = X[(N - k) % N];
-    float2 xa = make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
-    float2 xb = make_float2(0.5f * (Z.y + Zm.y), -0.5f * (Z.x - Zm.x));
+  // ---- 3. real-FFT post-processing, magnitude / power ---------------------------------------
+  //   X[k] = E + W_N^k O,  X[M-k] = conj(E - W_N^k O),  E = (Z[k]+conj Z[M-k])/2, O = (Z[k]-conj Z[M-k])/(2i)
+  float esum = 0.f;
+  const bool fvalid = fr < p.T;
+  auto emit = [&](int k, float2 x) {
     if (!stft) {
-      // processing.rs:168,180: (1/n_fft) * sqrt(re^2 + im^2)
-      const float a = p.mag_scale * sqrtf(xa.x * xa.x + xa.y * xa.y);
-      const float b = p.mag_scale * sqrtf(xb.x * xb.x + xb.y * xb.y);
-      PA[k] = a;
-      PB[k] = b;
-      eA += a;
-      eB += b;
-      if (p.pspec_out) {
-        if (fA < p.T) p.pspec_out[(row * p.T + fA) * F + k] = a;
-        if (fB < p.T) p.pspec_out[(row * p.T + fB) * F + k] = b;
-      }
+      const float a = p.mag_scale * sqrtf(x.x * x.x + x.y * x.y);  // processing.rs:168,180
+      P[k] = a;
+      esum += a;
+      if (p.pspec_out && fvalid) p.pspec_out[(row * p.T + fr) * F + k] = a;
     } else {
-      xa.x *= p.wnorm; xa.y *= p.wnorm;  // functions.rs:166-169
-      xb.x *= p.wnorm; xb.y *= p.wnorm;
-      if (p.stft_out) {
-        if (fA < p.T_out) p.stft_out[(row * p.T_out + fA) * F + k] = fA < p.T ? xa : make_float2(0.f, 0.f);
-        if (fB < p.T_out) p.stft_out[(row * p.T_out + fB) * F + k] = fB < p.T ? xb : make_float2(0.f, 0.f);
-      }
-      PA[k] = xa.x * xa.x + xa.y * xa.y;  // feature.rs:164: |X|^2
-      PB[k] = xb.x * xb.x + xb.y * xb.y;
+      x.x *= p.wnorm;  // functions.rs:166-169
+      x.y *= p.wnorm;
+      if (p.stft_out && fr < p.T_out) p.stft_out[(row * p.T_out + fr) * F + k] = fvalid ? x : make_float2(0.f, 0.f);
+      P[k] = x.x * x.x + x.y * x.y;  // feature.rs:164: |X|^2
     }
+  };
+  if (even) {
+    for (int k = lt; k <= M / 2; k += tpg) {
+      const float2 a = Z[k], b = Z[(M - k) % M];
+      const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+      const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+      const float2 Tw = cmul(O, __ldg(&p.tab.tw[k]));
+      emit(k, make_float2(E.x + Tw.x, E.y + Tw.y));
+      if (M - k != k) emit(M - k, make_float2(E.x - Tw.x, -(E.y - Tw.y)));
+    }
+  } else {
+    for (int k = lt; k < F; k += tpg) emit(k, Z[k]);
   }
   // ---- 4. frame energy (feature.rs:216-219) ----------------------------------------------
   if (!stft) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      eA += __shfl_xor_sync(0xffffffffu, eA, o);
-      eB += __shfl_xor_sync(0xffffffffu, eB, o);
-    }
-    if ((tid & 31) == 0) {
-      red_s[(tid >> 5) * 2] = eA;
-      red_s[(tid >> 5) * 2 + 1] = eB;
-    }
+    for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+    if ((tid & 31) == 0) red_s[tid >> 5] = esum;
   }
   __syncthreads();
   if (!stft && lt == 0) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < tpg / 32; ++w) {
-      a += red_s[((tid >> 5) + w) * 2];
-      b += red_s[((tid >> 5) + w) * 2 + 1];
-    }
-    energy_s[2 * g] = zero_handling(a);
-    energy_s[2 * g + 1] = zero_handling(b);
+    float a = 0.f;
+    for (int w = 0; w < tpg / 32; ++w) a += red_s[(tid >> 5) + w];
+    energy_s[g] = zero_handling(a);
   }
 
   // ---- 5. banded mel reduction (feature.rs:229 / :173), SSC numerator --------------------
   const bool want_mel = stft ? (p.mel_out != nullptr) : (p.mfe || p.lmfe || p.ssc || p.mfcc);
   if (want_mel) {
-    for (int idx = lt; idx < 2 * nf; idx += tpg) {
-      const int fr = idx / nf, i = idx - fr * nf;
-      const float* P = fr ? PB : PA;
+    for (int i = lt; i < nf; i += tpg) {
       const int b0 = __ldg(&p.tab.fstart[i]), len = __ldg(&p.tab.flen[i]);
       const float* w = p.tab.fw + __ldg(&p.tab.fwofs[i]);
       float acc = 0.f, acc2 = 0.f;
@@ -252,7 +244,7 @@ __global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, con
         acc += pw;
         acc2 += pw * (p.ssc_r0 + p.ssc_step * (float)(b0 + q));
       }
-      const int o = (2 * g + fr) * nf + i;
+      const int o = g * nf + i;
       if (!stft) {
         acc = zero_handling(acc);  // feature.rs:230
         mel_s[o] = acc;
@@ -271,8 +263,8 @@ __global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, con
     const int64_t obase = (row * p.T + t0);
     if (p.mfe || p.lmfe || p.ssc) {
       for (int idx = tid; idx < TF * nf; idx += nthreads) {
-        const int fr = idx / nf;
-        if (t0 + fr >= p.T) break;
+        const int f = idx / nf;
+        if (t0 + f >= p.T) break;
         if (p.mfe) p.mfe[obase * nf + idx] = mel_s[idx];
         if (p.lmfe) p.lmfe[obase * nf + idx] = log_s[idx];
         if (p.ssc) p.ssc[obase * nf + idx] = ssc_s[idx];
@@ -281,28 +273,28 @@ __global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, con
     if (p.energy && tid < TF && t0 + tid < p.T) p.energy[obase + tid] = energy_s[tid];
     if (p.mfcc) {
       for (int idx = tid; idx < TF * nc; idx += nthreads) {
-        const int fr = idx / nc, c = idx - fr * nc;
-        const int64_t t = t0 + fr;
+        const int f = idx / nc, c = idx - f * nc;
+        const int64_t t = t0 + f;
         if (t >= p.T) break;
-        const float* lg = log_s + fr * nf;
+        const float* lg = log_s + f * nf;
         const float* dm = p.tab.dct + c * nf;
         float acc = 0.f;
         for (int n = 0; n < nf; ++n) acc += lg[n] * __ldg(&dm[n]);
         // feature.rs:126-131: [0,0] *= 1/sqrt(4n); columns 1.. *= 1/sqrt(2n); rest of column 0 untouched
         if (c == 0) acc = (t == 0) ? acc * p.scale_00 : acc;
         else acc *= p.scale_rest;
-        if (c == 0 && p.dc_elim) acc = logf(energy_s[fr]);  // feature.rs:137-146
+        if (c == 0 && p.dc_elim) acc = logf(energy_s[f]);  // feature.rs:137-146
         p.mfcc[obase * nc + idx] = acc;
       }
     }
   } else if (p.mel_out) {
     // [row][m][t], time-minor (feature.rs:173); rows t >= T are the reference's zero tail
     for (int idx = tid; idx < nf * TF; idx += nthreads) {
-      const int m = idx / TF, fr = idx - m * TF;
-      const int64_t t = t0 + fr;
+      const int m = idx / TF, f = idx - m * TF;
+      const int64_t t = t0 + f;
       if (t >= p.T_out) continue;
       float v = 0.f;
-      if (t < p.T) v = mel_s[fr * nf + m];
+      if (t < p.T) v = mel_s[f * nf + m];
       else if (p.log_mode) v = logf(kEps);
       p.mel_out[(row * nf + m) * p.T_out + t] = v;
     }
@@ -322,11 +314,12 @@ __global__ void k_stft_mem_update(const FrameParams p) {
 int launch_frames_generic(const FrameParams& p, void* stream) {
   const int N = p.N;
   if (N > 8192) return (int)cudaErrorInvalidValue;
-  int ppc = 8;
-  while (ppc > 1 && (size_t)ppc * 2 * N * sizeof(float2) > 128 * 1024) ppc >>= 1;
-  const int tpg = 256 / ppc;
-  const int TF = 2 * ppc;
-  const size_t smem = (size_t)ppc * 2 * N * sizeof(float2) + (size_t)(3 * TF * p.nf + TF + 16) * sizeof(float);
+  const int M = (N & 1) ? N : N / 2;
+  int fpc = 8;  // frames per CTA
+  while (fpc > 1 && (size_t)fpc * 2 * (M + 1) * sizeof(float2) > 128 * 1024) fpc >>= 1;
+  const int tpg = 256 / fpc;
+  const int TF = fpc;
+  const size_t smem = (size_t)fpc * 2 * (M + 1) * sizeof(float2) + (size_t)(3 * TF * p.nf + TF + 16) * sizeof(float);
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   const int64_t frames = p.mode == kModeStft ? p.T_out : p.T;
   const int64_t tiles_per_row = (frames + TF - 1) / TF;
@@ -335,7 +328,7 @@ int launch_frames_generic(const FrameParams& p, void* stream) {
   if (nblocks > 2147483647LL) return (int)cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_frames_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_frames_generic<<<(unsigned)nblocks, 256, smem, (cudaStream_t)stream>>>(p, ppc, tpg, tiles_per_row);
+  k_frames_generic<<<(unsigned)nblocks, 256, smem, (cudaStream_t)stream>>>(p, fpc, tpg, tiles_per_row);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -136,9 +136,12 @@ void build_dct(const Derived& d, std::vector<float>* out) {
 }
 
 bool build_fft_plan(int n, FftPlanHost* p) {
+  // real FFT of even length n = complex FFT of length n/2 + post-processing; odd n: full length.
+  // The stage list factorises that complex length; the twiddle table is W_n^q for q < n.
   p->n = n;
   p->n_stages = 0;
-  int m = n;
+  int m = (n % 2 == 0) ? n / 2 : n;
+  if (m == 1) { p->radix[p->n_stages++] = 1; }
   auto push = [&](int r) {
     if (p->n_stages >= kMaxStages) return false;
     p->radix[p->n_stages++] = r;

@@ -82,6 +82,43 @@ def test_kws_batch_slice_lmfe_mfcc_cmvn(flags):
             np.testing.assert_allclose(r["mfcc"].std(1), 1, atol=1e-4)
 
 
+@pytest.mark.parametrize("flags", [0, GENERIC], ids=["fast", "generic"])
+def test_silence_next_to_sound_has_no_crosstalk(flags):
+    """An all-zero frame next to a loud one must still give exactly EPS (zero_handling), and a very
+    quiet frame next to a loud one must keep its own relative accuracy.  (Packing two real frames
+    into one complex FFT fails both; the kernels use one real FFT per frame.)"""
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], flags=flags)
+    oc = o.SpeechConfig(**CONFIGS["c1"])
+    loud = o.synth_signal(1, 16000, 41)[0] * np.float32(10.0)
+    gated = loud.copy()
+    gated[:8000] = 0.0                      # digital silence, then sound
+    quiet = loud.copy()
+    quiet[:8000] *= np.float32(1e-6)        # -120 dB background, then sound
+    for name, x in (("gated", gated), ("quiet", quiet)):
+        r = sb.feature.features(x, cfg, mfe=True, energy=True, lmfe=True, mfcc=True)
+        f, e = o.mfe(x, oc)
+        silent = ~frames_touching(x, 400, 160, 97)
+        if name == "gated":
+            assert silent.sum() > 40
+            assert (r["mfe"][silent] == o.EPS).all() and (r["energy"][silent] == o.EPS).all()
+        assert_spec_close(r["mfe"], f, what=f"{name} mfe")
+        assert_spec_close(r["energy"], e, what=f"{name} energy")
+        # per-frame relative accuracy: the tolerance floor scales with that frame, not the clip
+        for t in range(97):
+            assert_spec_close(r["mfe"][t], f[t], what=f"{name} mfe frame {t}")
+        assert_log_close(r["lmfe"], np.log(f), what=f"{name} lmfe")
+        assert_log_close(r["mfcc"], o.mfcc(x, oc), what=f"{name} mfcc")
+
+
+def frames_touching(x, L, S, T):
+    """True for frames that contain at least one non-zero sample"""
+    nz = np.flatnonzero(x)
+    out = np.zeros(T, bool)
+    for t in range(T):
+        out[t] = ((nz >= t * S) & (nz < t * S + L)).any()
+    return out
+
+
 def test_fast_and_generic_paths_agree_on_ragged_shapes():
     for clip_len, L_s, S_s in [(16000, 0.025, 0.01), (5003, 0.02, 0.01), (1237, 0.032, 0.005), (640, 0.025, 0.01), (561, 0.025, 0.01)]:
         kw = dict(CONFIGS["c1"], frame_length=L_s, frame_stride=S_s)
