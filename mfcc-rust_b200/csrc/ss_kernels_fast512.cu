@@ -35,7 +35,7 @@ constexpr int kXs = 10;                      // exchange row stride in float2 (8
 constexpr int kXchFrame = 32 * kXs + 8;      // float2 per frame; +8 shifts the next frame by half the banks
 constexpr int kWarpFloats = 4 * kXchFrame * 2;  // floats per warp (4 frames) = 2624
 constexpr int kPs = 264;                     // P row stride (floats); 264 % 32 == 8
-constexpr int kNfMax = 64, kNcMax = 16, kNwMax = 640, kSlots = 8;
+constexpr int kNfMax = 64, kNcMax = 16;
 constexpr int kRow = 68;                     // row stride of log_s and the DCT rows (68/4 odd)
 // per-warp float offsets after the exchange buffer has been consumed
 constexpr int kOffP = 0;
@@ -48,13 +48,13 @@ static_assert(kOffLog + 4 * kRow <= kWarpFloats, "per-warp scratch overflows the
 constexpr int kTwRow = 68;                      // floats per thread row of the W256 table (64 + 4 pad)
 constexpr int kTabTw = 0;                       // [8][kTwRow]: row u = W256^{u k1}, k1 = 0..31 (float2)
 constexpr int kTabTw512 = kTabTw + 8 * kTwRow;  // [256] float2: W512^k, k = 0..255
-constexpr int kTabFw = kTabTw512 + 256 * 2;     // [kNwMax]  w * (1/2n_fft)
-constexpr int kTabFw2 = kTabFw + kNwMax;        // [kNwMax]  w * R[bin] * (1/2n_fft) (SSC)
-constexpr int kTabDct = kTabFw2 + kNwMax;       // [kNcMax][kRow]
-constexpr int kTabSched = kTabDct + kNcMax * kRow;  // int [kSlots][8][4] = filt, b0, len, wofs
-constexpr int kTabNslot = kTabSched + 8 * kSlots * 4;  // int [8]
-constexpr int kTabFloats = kTabNslot + 8;
-static_assert(kTabTw512 % 4 == 0 && kTabDct % 4 == 0 && kTabSched % 4 == 0 && kTabFloats % 4 == 0,
+constexpr int kTabDct = kTabTw512 + 256 * 2;    // [kNcMax][kRow]
+constexpr int kTabFixed = kTabDct + kNcMax * kRow;  // floats before the per-plan mel program
+// mel program (per plan, nit iterations): int2 desc[nit][8] = {first bin (multiple of 4), flush},
+// then float4 w[nit][8], then float4 w2[nit][8] (SSC).  flush: -2 keep accumulating, -1 end of a
+// slot on an unused lane, >= 0 end of a slot: filter index to store.
+constexpr int kMaxIt = 48;
+static_assert(kTabTw512 % 4 == 0 && kTabDct % 4 == 0 && kTabFixed % 4 == 0,
               "16-byte alignment of table sections");
 
 template <int I, int E, class F>
@@ -149,6 +149,8 @@ struct FastArgs {
   int fuse_cmvn;      // 0 none, 1 mean, 2 mean+var: whole clip in one CTA, stash in smem
   int stash_floats;
   int store_hi;       // some filter reads a bin above 128: keep the upper half of P in smem
+  int nit;            // iterations of the mel program
+  int tab_floats;     // kTabFixed + nit * 8 * (2 + 4 + (SSC ? 4 : 0))
 };
 
 // one (k, 256-k) pair of the real-FFT post-processing:
@@ -170,25 +172,25 @@ __device__ __forceinline__ float2 rfft_pair_mag(float2 za, float2 zb, float2 w) 
 // EXACT: L == 16*JMAX and every frame start is 8-byte aligned -> unpredicated float2 loads;
 // SSC: also accumulate the spectral-subband-centroid numerator.
 template <int JMAX, bool EXACT, bool SSC>
+#ifndef SS_PREFETCH
+#define SS_PREFETCH 0  // software-pipelined global loads: measured slower (register pressure -> spills)
+#endif
 #ifndef SS_FAST_MINB
 #define SS_FAST_MINB 3
 #endif
 __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
-  float* warp_s = smem + kTabFloats + (threadIdx.x >> 5) * kWarpFloats;
-  float* stash = smem + kTabFloats + kWarps * kWarpFloats;  // [T][nc] when fuse_cmvn
+  float* warp_s = smem + a.tab_floats + (threadIdx.x >> 5) * kWarpFloats;
+  float* const stash0 = smem + a.tab_floats + kWarps * kWarpFloats;  // 2 x [T][nc] when fuse_cmvn
+  float* stash = stash0;
   const FrameParams& p = a.p;
 
-  for (int i = threadIdx.x; i < kTabFloats; i += kThreads) tab_s[i] = __ldg(a.tab + i);
+  for (int i = threadIdx.x; i < a.tab_floats; i += kThreads) tab_s[i] = __ldg(a.tab + i);
   __syncthreads();
 
   const float2* tw512_s = reinterpret_cast<const float2*>(tab_s + kTabTw512);
-  const float* fw_s = tab_s + kTabFw;
-  const float* fw2_s = tab_s + kTabFw2;
   const float* dct_s = tab_s + kTabDct;
-  const int* sched_s = reinterpret_cast<const int*>(tab_s + kTabSched);
-  const int* nslot_s = reinterpret_cast<const int*>(tab_s + kTabNslot);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fi = lane >> 3, u = lane & 7;  // frame within the quad, thread within the frame
@@ -214,30 +216,41 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
     const int q_end = min(a.quads_per_clip, (chunk + 1) * a.chunk_quads);
     const float* rowp = p.pcm + clip * p.row_stride;
 
-    for (int q = chunk * a.chunk_quads + warp; q < q_end; q += kWarps) {
+    // framing: v[j] = x[2m] + i x[2m+1], m = u + 8 j; zero beyond L (processing.rs:147-156).
+    // The loads for quad q + kWarps are issued in the middle of quad q (after its FFT registers
+    // are dead), so their latency hides behind the mel / DCT / store phase.
+    float2 v[32];
+    auto load_quad = [&](int q) {
+      const int64_t fr = 4 * (int64_t)q + fi;
+      // an out-of-range frame of the last quad re-reads frame T-1 (always in bounds); its results
+      // are never stored
+      const float* px = rowp + (fr < T ? fr : T - 1) * p.S + 2 * u;
+      sfor<0, 32>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        if constexpr (j >= JMAX) {
+          v[j] = make_float2(0.0f, 0.0f);
+        } else if constexpr (EXACT) {
+          v[j] = __ldg(reinterpret_cast<const float2*>(px + 16 * j));
+        } else {
+          const int n0 = 2 * u + 16 * j;
+          v[j].x = (n0 < L) ? __ldg(px + 16 * j) : 0.0f;
+          v[j].y = (n0 + 1 < L) ? __ldg(px + 16 * j + 1) : 0.0f;
+        }
+      });
+    };
+    const int q_first = chunk * a.chunk_quads + warp;
+#if SS_PREFETCH
+    if (q_first < q_end) load_quad(q_first);
+#endif
+
+    for (int q = q_first; q < q_end; q += kWarps) {
       const int64_t fq = 4 * (int64_t)q;  // first frame of the quad
       const int64_t fr = fq + fi;
       const bool valid = fr < T;
+#if !SS_PREFETCH
+      load_quad(q);
+#endif
 
-      // ---- framing: v[j] = x[2m] + i x[2m+1], m = u + 8 j; zero beyond L (processing.rs:147-156)
-      float2 v[32];
-      {
-        // an out-of-range frame of the last quad re-reads frame T-1 (always in bounds); its
-        // results are never stored
-        const float* px = rowp + (valid ? fr : T - 1) * p.S + 2 * u;
-        sfor<0, 32>([&](auto jj) {
-          constexpr int j = decltype(jj)::value;
-          if constexpr (j >= JMAX) {
-            v[j] = make_float2(0.0f, 0.0f);
-          } else if constexpr (EXACT) {
-            v[j] = __ldg(reinterpret_cast<const float2*>(px + 16 * j));
-          } else {
-            const int n0 = 2 * u + 16 * j;
-            v[j].x = (n0 < L) ? __ldg(px + 16 * j) : 0.0f;
-            v[j].y = (n0 + 1 < L) ? __ldg(px + 16 * j + 1) : 0.0f;
-          }
-        });
-      }
       // ---- stage 1: 32-point FFT over j, in registers
       fft_regs<32, 5, JMAX>(v);
       // ---- twiddle W256^{u k1} (two per LDS.128) and transpose through shared memory
@@ -299,25 +312,17 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
           }
           const float2 m = rfft_pair_mag(za, zb, tw512_s[k]);
           // k <= 128 exactly when s < 4 (u == 0: always); the other bin of the pair is >= 128
-          if constexpr (s < 4) {
-            Pf[k] = m.x;
-            if (a.store_hi || k == 0) Pf[256 - k] = m.y;
-          } else {
-            if (isz || a.store_hi) Pf[k] = m.x;
-            if (!isz || a.store_hi) Pf[256 - k] = m.y;
-          }
+          // bins <= 131 are always stored (the mel program reads P in aligned groups of 4 up to
+          // bin 131); the rest of the upper half only when a filter reaches above bin 128
+          if (a.store_hi || k <= 131) Pf[k] = m.x;
+          if (a.store_hi || k >= 125) Pf[256 - k] = m.y;
           esum += m.x + m.y;
         }
         {
           const int k = k1C + 32 * s;
           const float2 m = rfft_pair_mag(gC[s], gD[7 - s], tw512_s[k]);
-          if constexpr (s < 4) {
-            Pf[k] = m.x;
-            if (a.store_hi) Pf[256 - k] = m.y;
-          } else {
-            if (a.store_hi) Pf[k] = m.x;
-            Pf[256 - k] = m.y;
-          }
+          if (a.store_hi || k <= 131) Pf[k] = m.x;
+          if (a.store_hi || k >= 125) Pf[256 - k] = m.y;
           esum += m.x + m.y;
         }
       });
@@ -325,33 +330,48 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
         const float m = 2.0f * fast_sqrt(fmaf(gA[4].x, gA[4].x, gA[4].y * gA[4].y));
         Pf[128] = m;
         esum += m;
+        if (a.store_hi) { Pf[257] = 0.f; Pf[258] = 0.f; Pf[259] = 0.f; }  // tail of the last aligned group
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
       const float energy = zero_handling(mscale * esum);  // feature.rs:216-219
       __syncwarp();
+#if SS_PREFETCH
+      if (q + kWarps < q_end) load_quad(q + kWarps);  // v[] is dead from here on: prefetch the next quad
+#endif
 
-      // ---- banded mel reduction (feature.rs:229-230).  Filters are sorted by length and dealt to
-      // the 8 lanes slot by slot, so the lanes of a slot run loops of similar length.
+      // ---- banded mel reduction (feature.rs:229-230) as a flat "program": filters are sorted by
+      // length and dealt to the 8 lanes slot by slot; every lane of a slot runs the slot's padded
+      // length (zero weights beyond its own filter), four taps per iteration with 16-byte loads of
+      // both the weights and P.  Padded taps only read bins this quad has just written, so no
+      // stale shared memory can leak in through 0 * x.
       if (want_mel) {
-        const int ns = nslot_s[u];
-        for (int s = 0; s < ns; ++s) {
-          const int4 e = *reinterpret_cast<const int4*>(sched_s + (s * 8 + u) * 4);
-          const int filt = e.x, len = e.z;
-          const float* pp = Pf + e.y;
-          const float* pw = fw_s + e.w;
-          const float* pw2 = fw2_s + e.w;
-          float acc = 0.f, num = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < len; ++i) {
-            const float pv = pp[i];
-            acc = fmaf(pw[i], pv, acc);
-            if (SSC) num = fmaf(pw2[i], pv, num);
+        const int2* desc = reinterpret_cast<const int2*>(tab_s + kTabFixed) + u;
+        const float4* pw = reinterpret_cast<const float4*>(tab_s + kTabFixed + a.nit * 16) + u;
+        const float4* pw2 = pw + a.nit * 8;
+        float acc = 0.f, num = 0.f;
+#pragma unroll 1
+        for (int it = 0; it < a.nit; ++it) {
+          const int2 d = desc[it * 8];
+          const float4 w = pw[it * 8];
+          const float4 pv = *reinterpret_cast<const float4*>(Pf + d.x);
+          acc = fmaf(w.x, pv.x, acc); acc = fmaf(w.y, pv.y, acc);
+          acc = fmaf(w.z, pv.z, acc); acc = fmaf(w.w, pv.w, acc);
+          if (SSC) {
+            const float4 w2 = pw2[it * 8];
+            num = fmaf(w2.x, pv.x, num); num = fmaf(w2.y, pv.y, num);
+            num = fmaf(w2.z, pv.z, num); num = fmaf(w2.w, pv.w, num);
           }
-          acc = zero_handling(acc);
-          mel_s[fi * nf + filt] = acc;
-          if (SSC) ssc_s[fi * nf + filt] = __fdividef(num, acc);
-          log_s[fi * kRow + filt] = __logf(acc);
+          if (d.y != -2) {  // end of a slot (the same iteration on every lane)
+            if (d.y >= 0) {
+              acc = zero_handling(acc);
+              mel_s[fi * nf + d.y] = acc;
+              if (SSC) ssc_s[fi * nf + d.y] = __fdividef(num, acc);
+              log_s[fi * kRow + d.y] = __logf(acc);
+            }
+            acc = 0.f;
+            num = 0.f;
+          }
         }
         // zero the float4 padding of the log rows (the buffer held FFT data a moment ago)
         if (u < ((nf + 3) & ~3) - nf) log_s[fi * kRow + nf + u] = 0.0f;
@@ -404,57 +424,40 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
       }
     }
 
-    // ---- per-clip CMVN (processing.rs:265-300) on the stashed [T][nc] block ---------------
+    // ---- per-clip CMVN (processing.rs:265-300) on the stashed [T][nc] block.  The stash is
+    // double-buffered so ONE barrier per clip suffices: it both publishes this clip's stash and
+    // proves every warp has finished reading the other buffer (the previous clip's CMVN).
     if (a.fuse_cmvn) {
       __syncthreads();
-      // thread = (row lane r, column c): 10 row lanes x 16 columns; partials combined in a fixed order
-      float* part = stash + a.stash_floats;   // [10][16]
-      float* stat = part + 160;               // [16][2]
+      const float* st = stash;
       const int Ti = (int)T;
-      const int c = threadIdx.x & 15, r = threadIdx.x >> 4;
-      const bool cok = c < nc;
-      float s = 0.f;
-      if (cok) for (int t = r; t < Ti; t += 10) s += stash[t * nc + c];
-      part[r * 16 + c] = s;
-      __syncthreads();
-      float mean = 0.f;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) mean += part[i * 16 + c];
-      mean /= (float)Ti;
-      __syncthreads();
-      if (a.fuse_cmvn == 2) {
-        // std of the mean-subtracted column y, ddof 0: sqrt(mean(y^2) - mean(y)^2), mean(y) ~ 0
-        float s1 = 0.f, s2 = 0.f;
-        if (cok) for (int t = r; t < Ti; t += 10) {
-          const float d = stash[t * nc + c] - mean;
-          s1 += d;
-          s2 = fmaf(d, d, s2);
-        }
-        part[r * 16 + c] = s1;
-        part[160 + 32 + r * 16 + c] = s2;
-        __syncthreads();
-        if (r == 0) {
-          float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 10; ++i) { t1 += part[i * 16 + c]; t2 += part[160 + 32 + i * 16 + c]; }
-          const float my = t1 / (float)Ti;
-          const float var = fmaxf(t2 / (float)Ti - my * my, 0.f);
-          stat[2 * c] = mean;
-          stat[2 * c + 1] = 1.0f / (sqrtf(var) + kCmvnEps);
-        }
-      } else if (r == 0) {
-        stat[2 * c] = mean;
-        stat[2 * c + 1] = 1.0f;
-      }
-      __syncthreads();
       float* dst = p.mfcc + clip * T * nc;
-      const int tot = Ti * nc;
-      for (int i = threadIdx.x, cc = threadIdx.x % nc; i < tot; i += kThreads) {
-        dst[i] = (stash[i] - stat[2 * cc]) * stat[2 * cc + 1];
-        cc += kThreads % nc;   // column of the next element without a division
-        if (cc >= nc) cc -= nc;
+      for (int c = warp; c < nc; c += kWarps) {  // a warp owns whole columns: no further barrier
+        float s0 = 0.f;
+        for (int t = lane; t < Ti; t += 32) s0 += st[t * nc + c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        const float mean = s0 / (float)Ti;
+        float inv = 1.0f;
+        if (a.fuse_cmvn == 2) {
+          // std of the mean-subtracted column y, ddof 0: sqrt(mean(y^2) - mean(y)^2), mean(y) ~ 0
+          float s1 = 0.f, s2 = 0.f;
+          for (int t = lane; t < Ti; t += 32) {
+            const float d = st[t * nc + c] - mean;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          const float my = s1 / (float)Ti;
+          inv = 1.0f / (sqrtf(fmaxf(s2 / (float)Ti - my * my, 0.f)) + kCmvnEps);
+        }
+        for (int t = lane; t < Ti; t += 32) dst[t * nc + c] = (st[t * nc + c] - mean) * inv;
       }
-      __syncthreads();  // the stash is rewritten by the next clip
+      stash = (stash == stash0) ? stash0 + a.stash_floats : stash0;
     }
   }
 }
@@ -464,17 +467,77 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
 struct Fast512Tables {
   float* d_tab = nullptr;
   bool store_hi = true;
+  int nit = 0;  // iterations of the mel program
 };
+
+// The mel program: filters sorted by length and dealt round-robin to 8 lanes; slot s holds
+// filters 8s..8s+7.  A slot runs ceil(span/4) iterations, span = the longest 4-aligned run
+// [start & ~3, start + len) among its filters.
+struct MelProgram {
+  int nit = 0;
+  std::vector<int> desc;     // [nit][8][2]
+  std::vector<float> w, w2;  // [nit][8][4]
+};
+static void build_mel_program(const Derived& d, const MelBank& mb, MelProgram* mp, bool* store_hi_out) {
+  const int nf = d.nf;
+  std::vector<int> order(nf);
+  for (int i = 0; i < nf; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return mb.len[x] > mb.len[y]; });
+  const bool store_hi = mb.max_bin > 128;
+  const int hi_end = store_hi ? 260 : 132;  // the kernel writes bins [0, hi_end) afresh in every quad
+  const float mscale = 0.5f * (1.0f / (float)d.W);  // the kernel keeps 2*n_fft*|X| in shared memory
+  const float r0 = 1.0f, step = d.F > 1 ? ((float)d.cfg.sample_rate / 2.0f - 1.0f) / (float)(d.F - 1) : 0.f;
+  mp->nit = 0;
+  mp->desc.clear(); mp->w.clear(); mp->w2.clear();
+  const int ns = (nf + 7) / 8;
+  for (int s = 0; s < ns; ++s) {
+    int its = 1;
+    int b0[8];
+    for (int l = 0; l < 8; ++l) {
+      b0[l] = 0;
+      if (s * 8 + l >= nf) continue;
+      const int f = order[s * 8 + l];
+      if (mb.len[f] == 0) continue;
+      b0[l] = mb.start[f] & ~3;
+      its = std::max(its, (mb.start[f] + mb.len[f] - b0[l] + 3) / 4);
+    }
+    // keep every (padded) read inside the bins the kernel has freshly written
+    for (int l = 0; l < 8; ++l) b0[l] = std::max(0, std::min(b0[l], hi_end - 4 * its));
+    for (int it = 0; it < its; ++it)
+      for (int l = 0; l < 8; ++l) {
+        const bool used = s * 8 + l < nf;
+        const int f = used ? order[s * 8 + l] : -1;
+        mp->desc.push_back(b0[l] + 4 * it);
+        mp->desc.push_back(it == its - 1 ? (used ? f : -1) : -2);
+        for (int k = 0; k < 4; ++k) {
+          const int bin = b0[l] + 4 * it + k;
+          float w = 0.f;
+          if (used && bin >= mb.start[f] && bin < mb.start[f] + mb.len[f]) w = mb.w[mb.wofs[f] + bin - mb.start[f]];
+          mp->w.push_back(w * mscale);
+          mp->w2.push_back(w * (r0 + step * (float)bin) * mscale);
+        }
+      }
+    mp->nit += its;
+  }
+  *store_hi_out = store_hi;
+}
 
 bool fast512_supported(const Derived& d, const MelBank& mb) {
   if (d.W != 512 || !d.speechpy_ok) return false;
   if (d.nf > kNfMax || d.nc > kNcMax) return false;
-  if ((int)mb.w.size() > kNwMax) return false;
+  MelProgram mp;
+  bool hi;
+  build_mel_program(d, mb, &mp, &hi);
+  if (mp.nit > kMaxIt) return false;
+  if (4 * ((mb.max_len + 6) / 4) > (hi ? 260 : 132)) return false;  // a padded run must fit the written bins
   return true;
 }
 
 int fast512_build_tables(const Derived& d, const MelBank& mb, Fast512Tables** out) {
-  std::vector<float> h(kTabFloats, 0.f);
+  MelProgram mp;
+  bool store_hi;
+  build_mel_program(d, mb, &mp, &store_hi);
+  std::vector<float> h(kTabFixed + (size_t)mp.nit * 8 * 10, 0.f);
   const double pi = 3.14159265358979323846264338327950288;
   for (int u = 0; u < 8; ++u)
     for (int k1 = 0; k1 < 32; ++k1) {
@@ -487,40 +550,21 @@ int fast512_build_tables(const Derived& d, const MelBank& mb, Fast512Tables** ou
     h[kTabTw512 + 2 * k] = (float)std::cos(ang);
     h[kTabTw512 + 2 * k + 1] = (float)std::sin(ang);
   }
-  // the kernel keeps 2*n_fft*|X| in shared memory; 1/(2 n_fft) is folded into the weights
-  const float mscale = 0.5f * (1.0f / (float)d.W);
-  const float r0 = 1.0f, step = d.F > 1 ? ((float)d.cfg.sample_rate / 2.0f - 1.0f) / (float)(d.F - 1) : 0.f;
-  for (int i = 0; i < d.nf; ++i)
-    for (int k = 0; k < mb.len[i]; ++k) {
-      const float w = mb.w[mb.wofs[i] + k];
-      h[kTabFw + mb.wofs[i] + k] = w * mscale;
-      h[kTabFw2 + mb.wofs[i] + k] = w * (r0 + step * (float)(mb.start[i] + k)) * mscale;
-    }
   std::vector<float> dct;
   build_dct(d, &dct);
   for (int c = 0; c < d.nc; ++c)
     for (int n = 0; n < d.nf; ++n) h[kTabDct + c * kRow + n] = dct[(size_t)c * d.nf + n];
-  // filters sorted by length, dealt round-robin: slot s of the 8 lanes holds filters of similar
-  // length, which minimises the sum over slots of the longest loop in the slot
-  std::vector<int> order(d.nf);
-  for (int i = 0; i < d.nf; ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return mb.len[x] > mb.len[y]; });
-  int* sched = reinterpret_cast<int*>(h.data() + kTabSched);
-  int* nslot = reinterpret_cast<int*>(h.data() + kTabNslot);
-  for (int i = 0; i < d.nf; ++i) {
-    const int s = i / 8, l = i % 8, f = order[i];
-    int* e = sched + (s * 8 + l) * 4;
-    e[0] = f;
-    e[1] = mb.start[f];
-    e[2] = mb.len[f];
-    e[3] = mb.wofs[f];
-    nslot[l] = s + 1;
-  }
+  int* desc = reinterpret_cast<int*>(h.data() + kTabFixed);
+  for (size_t i = 0; i < mp.desc.size(); ++i) desc[i] = mp.desc[i];
+  float* w = h.data() + kTabFixed + (size_t)mp.nit * 16;
+  float* w2 = w + (size_t)mp.nit * 32;
+  for (size_t i = 0; i < mp.w.size(); ++i) { w[i] = mp.w[i]; w2[i] = mp.w2[i]; }
   Fast512Tables* t = new Fast512Tables;
-  t->store_hi = mb.max_bin > 128;
-  cudaError_t e = cudaMalloc(&t->d_tab, kTabFloats * sizeof(float));
+  t->store_hi = store_hi;
+  t->nit = mp.nit;
+  cudaError_t e = cudaMalloc(&t->d_tab, h.size() * sizeof(float));
   if (e != cudaSuccess) { delete t; return (int)e; }
-  e = cudaMemcpy(t->d_tab, h.data(), kTabFloats * sizeof(float), cudaMemcpyHostToDevice);
+  e = cudaMemcpy(t->d_tab, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(t->d_tab); delete t; return (int)e; }
   *out = t;
   return 0;
@@ -543,7 +587,7 @@ int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, v
   a.quads_per_clip = (int)qpc;
   // fused per-clip CMVN when the clip's [T][nc] block fits a 24 KB stash
   const size_t stash_bytes = (size_t)p.T * p.nc * sizeof(float);
-  const bool fuse = p.mfcc && p.cmvn_mode && stash_bytes <= 24 * 1024;
+  const bool fuse = p.mfcc && p.cmvn_mode && stash_bytes <= 12 * 1024;
   a.fuse_cmvn = fuse ? p.cmvn_mode : 0;
   a.stash_floats = fuse ? (int)(p.T * p.nc) : 0;
   if (fuse) {
@@ -559,7 +603,9 @@ int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, v
   a.chunks_per_clip = (int)((qpc + a.chunk_quads - 1) / a.chunk_quads);
   a.n_items = p.n_rows * a.chunks_per_clip;
   a.store_hi = t->store_hi ? 1 : 0;
-  const size_t smem = (size_t)(kTabFloats + kWarps * kWarpFloats + a.stash_floats + (fuse ? 160 + 32 + 160 : 0)) * sizeof(float);
+  a.nit = t->nit;
+  a.tab_floats = kTabFixed + t->nit * 8 * (2 + 4 + (p.ssc ? 4 : 0));
+  const size_t smem = (size_t)(a.tab_floats + kWarps * kWarpFloats + 2 * a.stash_floats) * sizeof(float);
   const int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sm_count * SS_FAST_MINB);
   if (grid <= 0) return 0;
   // float2 loads need every frame start 8-byte aligned: even stride / step and an aligned base
