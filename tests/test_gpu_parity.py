@@ -293,3 +293,34 @@ def test_stft_errors():
     with pytest.raises(sb.SpeechsauceError) as ei:
         sb.functions.stft2(np.zeros((1, 4000), np.float32), dflt)
     assert ei.value.code == _lib.SS_ERR_INVALID_ARG
+
+
+def test_cpp_mirror_runs_reference_unit_tests():
+    """builds mfcc-rust_b200/cpp/example.cpp (the reference's lib.rs:41-134 tests on the C++ mirror
+    of the crate API) against the shipped library and runs it on this GPU"""
+    import subprocess
+    from pathlib import Path
+    pkg = Path(sb.LIB_PATH).parent.parent
+    exe = Path("/tmp/ss_cpp_example")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", f"-I{pkg.parent / 'include'}", f"-I{pkg / 'cpp'}",
+                           str(pkg / "cpp" / "example.cpp"), "-o", str(exe), f"-L{pkg / 'lib'}", "-lspeechsauce_cuda",
+                           f"-Wl,-rpath,{pkg / 'lib'}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all reference-shaped tests passed" in out.stdout
+
+
+def test_multi_device_plan_matches_single_device():
+    """clips shard over a plan's devices with no collective; results must not depend on the split"""
+    n = sb.lib.ss_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    x = o.synth_signal(37, 16000, 77)
+    one = sb.feature.features(x, sb.SpeechConfig(**CONFIGS["c1"], devices=[0]), lmfe=True, mfcc=True, cmvn_mode=2)
+    many = sb.feature.features(x, sb.SpeechConfig(**CONFIGS["c1"], devices=list(range(n))), lmfe=True, mfcc=True, cmvn_mode=2)
+    np.testing.assert_array_equal(one["mfcc"], many["mfcc"])
+    np.testing.assert_array_equal(one["lmfe"], many["lmfe"])
+    y = o.synth_signal(9, 8000, 78)
+    a = sb.functions.stft2(y, sb.SpeechConfig(**CONFIGS["c4"], devices=[0]))
+    b = sb.functions.stft2(y, sb.SpeechConfig(**CONFIGS["c4"], devices=list(range(n))))
+    np.testing.assert_array_equal(a, b)
