@@ -1,0 +1,178 @@
+// Compile-time FFT building blocks for register-resident transforms.
+//
+// Everything here is resolved at compile time: loop indices (sfor), twiddle factors (constexpr
+// sin/cos evaluated in double precision and emitted as FFMA immediates) and the data movement of
+// the Stockham stages (pure register renaming after full unrolling).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+namespace ssfft {
+
+template <int I, int E, class F>
+__device__ __forceinline__ void sfor(F&& f) {
+  if constexpr (I < E) {
+    f(std::integral_constant<int, I>{});
+    sfor<I + 1, E>(static_cast<F&&>(f));
+  }
+}
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+// sin / cos on [-pi/4, pi/4] by Taylor series (truncation error < 1e-18)
+constexpr double sin_core(double x) {
+  const double x2 = x * x;
+  double term = x, sum = x;
+  for (int n = 1; n <= 11; ++n) {
+    term *= -x2 / ((2.0 * n) * (2.0 * n + 1.0));
+    sum += term;
+  }
+  return sum;
+}
+constexpr double cos_core(double x) {
+  const double x2 = x * x;
+  double term = 1.0, sum = 1.0;
+  for (int n = 1; n <= 11; ++n) {
+    term *= -x2 / ((2.0 * n - 1.0) * (2.0 * n));
+    sum += term;
+  }
+  return sum;
+}
+// cos / sin of 2 pi m / n.  The octant is found on the integers, so the exact cases
+// (multiples of pi/4) come out exact and everything else is accurate to ~1e-16.
+constexpr double cos2pi(long long m, long long n);
+constexpr double sin2pi(long long m, long long n) { return cos2pi(4 * m - n, 4 * n); }  // sin x = cos(x - pi/2)
+constexpr double cos2pi(long long m, long long n) {
+  m %= n;
+  if (m < 0) m += n;                       // 0 <= m < n
+  if (2 * m > n) m = n - m;                // cos(2pi - x) = cos x        -> 0 <= x <= pi
+  bool neg = false;
+  if (4 * m > n) { m = n - 2 * m; n *= 2; neg = true; if (m < 0) m = -m; }  // cos x = -cos(pi - x), x' = 2pi (n-2m)/(2n)
+  // now 0 <= 2 pi m / n <= pi/2
+  double v = 0.0;
+  if (8 * m <= n) v = cos_core(2.0 * kPi * (double)m / (double)n);
+  else v = sin_core(2.0 * kPi * (double)(n - 4 * m) / (double)(4 * n));   // cos x = sin(pi/2 - x)
+  if (m == 0) v = 1.0;
+  if (4 * m == n) v = 0.0;
+  return neg ? -v : v;
+}
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// radix-2 DIT butterfly with w = e^{-2 pi i M / N}: a' = a + w b, b' = a - w b = 2a - a'
+template <int N, int M>
+__device__ __forceinline__ void bfly2(float2& a, float2& b) {
+  constexpr int m = ((M % N) + N) % N;
+  if constexpr (m == 0) {
+    const float2 t = a;
+    a = make_float2(t.x + b.x, t.y + b.y);
+    b = make_float2(t.x - b.x, t.y - b.y);
+  } else if constexpr (4 * m == N) {  // w = -i : w b = (b.y, -b.x)
+    const float2 t = a, s = b;
+    a = make_float2(t.x + s.y, t.y - s.x);
+    b = make_float2(t.x - s.y, t.y + s.x);
+  } else if constexpr (2 * m == N) {  // w = -1
+    const float2 t = a;
+    a = make_float2(t.x - b.x, t.y - b.y);
+    b = make_float2(t.x + b.x, t.y + b.y);
+  } else if constexpr (4 * m == 3 * N) {  // w = +i : w b = (-b.y, b.x)
+    const float2 t = a, s = b;
+    a = make_float2(t.x - s.y, t.y + s.x);
+    b = make_float2(t.x + s.y, t.y - s.x);
+  } else {
+    constexpr float c = (float)cos2pi(m, N), s = (float)sin2pi(m, N);  // w = c - i s
+    float2 t;
+    t.x = fmaf(c, b.x, a.x);
+    t.x = fmaf(s, b.y, t.x);
+    t.y = fmaf(c, b.y, a.y);
+    t.y = fmaf(-s, b.x, t.y);
+    b = make_float2(fmaf(2.0f, a.x, -t.x), fmaf(2.0f, a.y, -t.y));
+    a = t;
+  }
+}
+
+// multiply by e^{-2 pi i M / N}, compile-time
+template <int N, int M>
+__device__ __forceinline__ float2 twmul(float2 v) {
+  constexpr int m = ((M % N) + N) % N;
+  if constexpr (m == 0) return v;
+  else if constexpr (4 * m == N) return make_float2(v.y, -v.x);
+  else if constexpr (2 * m == N) return make_float2(-v.x, -v.y);
+  else if constexpr (4 * m == 3 * N) return make_float2(-v.y, v.x);
+  else {
+    constexpr float c = (float)cos2pi(m, N), s = (float)sin2pi(m, N);
+    return make_float2(fmaf(c, v.x, s * v.y), fmaf(c, v.y, -s * v.x));
+  }
+}
+
+// 5-point DFT, y_k = sum_n x_n e^{-2 pi i nk/5} (36 FP32 instructions)
+__device__ __forceinline__ void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+  constexpr float c1 = (float)cos2pi(1, 5), c2 = (float)cos2pi(2, 5);
+  constexpr float s1 = (float)sin2pi(1, 5), s2 = (float)sin2pi(2, 5);
+  const float2 t1 = make_float2(x1.x + x4.x, x1.y + x4.y), t2 = make_float2(x2.x + x3.x, x2.y + x3.y);
+  const float2 t3 = make_float2(x1.x - x4.x, x1.y - x4.y), t4 = make_float2(x2.x - x3.x, x2.y - x3.y);
+  const float2 m1 = make_float2(fmaf(c2, t2.x, fmaf(c1, t1.x, x0.x)), fmaf(c2, t2.y, fmaf(c1, t1.y, x0.y)));
+  const float2 m2 = make_float2(fmaf(c1, t2.x, fmaf(c2, t1.x, x0.x)), fmaf(c1, t2.y, fmaf(c2, t1.y, x0.y)));
+  const float2 u1 = make_float2(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y));
+  const float2 u2 = make_float2(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y));
+  x0 = make_float2(x0.x + (t1.x + t2.x), x0.y + (t1.y + t2.y));
+  x1 = make_float2(m1.x + u1.y, m1.y - u1.x);  // m1 - i u1
+  x4 = make_float2(m1.x - u1.y, m1.y + u1.x);
+  x2 = make_float2(m2.x + u2.y, m2.y - u2.x);
+  x3 = make_float2(m2.x - u2.y, m2.y + u2.x);
+}
+
+// One Stockham stage on a register array: N points, radix R (2 or 5), sub-length NS.
+//   out[(j / NS) * NS * R + k + r * NS] = DFT_R( in[j + r * N/R] * W_{NS*R}^{k r} ),  k = j % NS
+template <int N, int R, int NS>
+__device__ __forceinline__ void stockham_stage(const float2 (&in)[N], float2 (&out)[N]) {
+  static_assert(R == 2 || R == 5, "radix 2 or 5");
+  constexpr int NB = N / R;
+  sfor<0, NB>([&](auto jj) {
+    constexpr int j = decltype(jj)::value;
+    constexpr int k = j % NS;
+    constexpr int o = (j / NS) * NS * R + k;
+    if constexpr (R == 2) {
+      float2 a = in[j], b = in[j + NB];
+      bfly2<NS * 2, k>(a, b);
+      out[o] = a;
+      out[o + NS] = b;
+    } else {
+      float2 v0 = in[j];
+      float2 v1 = twmul<NS * 5, k>(in[j + NB]);
+      float2 v2 = twmul<NS * 5, 2 * k>(in[j + 2 * NB]);
+      float2 v3 = twmul<NS * 5, 3 * k>(in[j + 3 * NB]);
+      float2 v4 = twmul<NS * 5, 4 * k>(in[j + 4 * NB]);
+      dft5(v0, v1, v2, v3, v4);
+      out[o] = v0;
+      out[o + NS] = v1;
+      out[o + 2 * NS] = v2;
+      out[o + 3 * NS] = v3;
+      out[o + 4 * NS] = v4;
+    }
+  });
+}
+
+// y[k] = sum_j x[j] e^{-2 pi i jk/N}, natural order in and out, for N in {5, 10, 20, 40}: a radix-5
+// stage without twiddles followed by radix-2 stages with 6-FFMA butterflies.
+template <int N>
+__device__ __forceinline__ void fft_5x2(float2 (&x)[N]) {
+  static_assert(N == 5 || N == 10 || N == 20 || N == 40, "5 * 2^a");
+  float2 t[N];
+  stockham_stage<N, 5, 1>(x, t);
+  if constexpr (N == 5) {
+    sfor<0, N>([&](auto i) { x[decltype(i)::value] = t[decltype(i)::value]; });
+  } else {
+    stockham_stage<N, 2, 5>(t, x);
+    if constexpr (N >= 20) {
+      stockham_stage<N, 2, 10>(x, t);
+      if constexpr (N == 40) stockham_stage<N, 2, 20>(t, x);
+      else sfor<0, N>([&](auto i) { x[decltype(i)::value] = t[decltype(i)::value]; });
+    }
+  }
+}
+
+}  // namespace ssfft

@@ -78,6 +78,7 @@ struct DeviceCtx {
   DevBuf tables;  // one allocation holding every device table
   DevTables tab;
   Fast512Tables* fast512 = nullptr;
+  Stft400Tables* stft400 = nullptr;
   Lane lanes[kLanes];
   DevBuf dev_scratch;  // scratch for the *_dev entry points (cmvn partials)
   std::string err;     // worker-thread error message
@@ -94,6 +95,7 @@ struct ss_plan {
   std::vector<float> analysis_mem;  // [W-H], config.rs:126,162
   std::vector<ss::DeviceCtx> devs;
   bool fast512 = false;
+  bool stft400 = false;
 };
 
 namespace ss {
@@ -138,6 +140,10 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   if (pl->fast512) {
     int e = fast512_build_tables(pl->d, pl->mb, &dc->fast512);
     if (e) return cuda_fail((cudaError_t)e, "fast512_build_tables");
+  }
+  if (pl->stft400) {
+    int e = stft400_build_tables(pl->d, pl->mb, pl->window, &dc->stft400);
+    if (e) return cuda_fail((cudaError_t)e, "stft400_build_tables");
   }
   return SS_OK;
 }
@@ -223,6 +229,15 @@ static void stft_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float*
   p->mode = kModeStft;
   p->wnorm = d.wnorm;
   p->tab = dc->tab;
+}
+
+// mel_spectrogram / stft launch: a size-specialised kernel when one exists, else the generic one
+static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
+  if (pl->stft400 && dc->stft400 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+    const int e = launch_stft400(p, dc->stft400, dc->sm_count, stream);
+    if (e != -1000) return e;
+  }
+  return launch_frames_generic(p, stream);
 }
 
 static int check_speechpy(ss_plan* pl, int64_t clip_len, int64_t row_stride, int64_t* T) {
@@ -395,6 +410,7 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   pl->fft_ok = pl->d.W <= (1 << 20) && build_fft_plan((int)pl->d.W, &pl->fft);
   if (pl->d.stft_ok) pl->analysis_mem.assign((size_t)(pl->d.W - pl->d.H), 0.f);  // config.rs:162
   pl->fast512 = pl->fft_ok && fast512_supported(pl->d, pl->mb);
+  pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
   std::vector<int> devs;
   if (n_devices < 0) {
     int n = ss_device_count();
@@ -444,6 +460,7 @@ void ss_plan_destroy(ss_plan* pl) {
     dc.tables.release();
     dc.dev_scratch.release();
     if (dc.fast512) fast512_free_tables(dc.fast512);
+    if (dc.stft400) stft400_free_tables(dc.stft400);
   }
   if (prev >= 0) cudaSetDevice(prev);
   delete pl;
@@ -463,7 +480,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
   info->fast_path = pl->fast512 && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  info->fast_stft = 0;
+  info->fast_stft = pl->stft400 && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }
 
@@ -637,7 +654,7 @@ static int stft_host(ss_plan* pl, const float* pcm, int64_t ch, int64_t ttd, int
         p.log_mode = log_mode;
         if (out_ri) p.stft_out = static_cast<float2*>(ln.out.p);
         else p.mel_out = static_cast<float*>(ln.out.p);
-        int e = launch_frames_generic(p, ln.stream);
+        int e = launch_stft_any(pl, dc, p, ln.stream);
         if (e) return cuda_fail((cudaError_t)e, "stft kernel launch");
         float* host_out = out_ri ? out_ri + (size_t)a * Tp * d.F * 2 : out_mel + (size_t)a * d.nf * Tp;
         SS_CUDA(cudaMemcpyAsync(host_out, ln.out.p, n * per_row_out, cudaMemcpyDeviceToHost, ln.stream));
@@ -683,7 +700,7 @@ static int stft_dev(ss_plan* pl, int dev_index, void* stream, const float* d_pcm
   p.stft_out = reinterpret_cast<float2*>(d_out_ri);
   p.mel_out = d_out_mel;
   if (ch > 0 && p.Tp > 0) {
-    int e = launch_frames_generic(p, stream);
+    int e = launch_stft_any(pl, &pl->devs[dev_index], p, stream);
     if (e) return cuda_fail((cudaError_t)e, "stft kernel launch");
   }
   int e = launch_stft_mem_update(p, stream);

@@ -118,6 +118,13 @@ int fast512_build_tables(const Derived& d, const MelBank& mb, Fast512Tables** ou
 void fast512_free_tables(Fast512Tables* t);
 int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, void* stream);
 
+// fft_points == 400 register-FFT path for mel_spectrogram (ss_kernels_stft400.cu)
+bool stft400_supported(const Derived& d, const MelBank& mb);
+struct Stft400Tables;
+int stft400_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft400Tables** out);
+void stft400_free_tables(Stft400Tables* t);
+int launch_stft400(const FrameParams& p, const Stft400Tables* t, int sm_count, void* stream);
+
 int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
                        int64_t shift, float cof, void* stream);
 int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,

@@ -148,7 +148,6 @@ struct FastArgs {
   int quads_per_clip, chunk_quads, chunks_per_clip;
   int fuse_cmvn;      // 0 none, 1 mean, 2 mean+var: whole clip in one CTA, stash in smem
   int stash_floats;
-  int store_hi;       // some filter reads a bin above 128: keep the upper half of P in smem
   int nit;            // iterations of the mel program
   int tab_floats;     // kTabFixed + nit * 8 * (2 + 4 + (SSC ? 4 : 0))
 };
@@ -171,6 +170,9 @@ __device__ __forceinline__ float2 rfft_pair_mag(float2 za, float2 zb, float2 w) 
 // JMAX: number of 16-sample column groups that can be non-zero (ceil(L/16));
 // EXACT: L == 16*JMAX and every frame start is 8-byte aligned -> unpredicated float2 loads;
 // SSC: also accumulate the spectral-subband-centroid numerator.
+// Only bins <= 128 are kept in shared memory: with the reference's filterbank formula
+// (feature.rs:69-70, quirk Q8) no filter has a non-zero tap above bin 128 when n_fft = 512;
+// fast512_supported() declines any plan where that does not hold.
 template <int JMAX, bool EXACT, bool SSC>
 #ifndef SS_PREFETCH
 #define SS_PREFETCH 0  // software-pipelined global loads: measured slower (register pressure -> spills)
@@ -209,6 +211,17 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
   float* ssc_s = warp_s + kOffSsc;
   float* log_s = warp_s + kOffLog;
   float* Pf = P_s + fi * kPs;
+  // post-processing addresses as per-thread base pointers + compile-time offsets
+  const int kb = isz ? -112 : u;  // k of slots 4..7 is kb + 32 s (u == 0: 16 + 32 (s - 4))
+  const float2* twA = tw512_s + u;
+  const float2* twB = tw512_s + kb;
+  const float2* twC = tw512_s + k1C;
+  float* pA = Pf + u;
+  float* pC = Pf + k1C;
+  float* pCm = Pf + 256 - k1C;
+  float* plo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) plo[i] = isz ? Pf + 16 + 32 * i : Pf + 256 - u - 32 * (i + 4);
 
   for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int64_t clip = item / a.chunks_per_clip;
@@ -296,33 +309,32 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
         constexpr int s = decltype(ss_)::value;
         {
           float2 za, zb;
-          int k;
           if constexpr (s == 0) {
             za = gA[0];
             zb = isz ? gA[0] : gB[7];
-            k = u;
           } else if constexpr (s < 4) {
             za = gA[s];
             zb = isz ? gA[8 - s] : gB[7 - s];
-            k = u + 32 * s;
           } else {
             za = isz ? gB[s - 4] : gA[s];
             zb = isz ? gB[11 - s] : gB[7 - s];
-            k = isz ? 16 + 32 * (s - 4) : u + 32 * s;
           }
-          const float2 m = rfft_pair_mag(za, zb, tw512_s[k]);
-          // k <= 128 exactly when s < 4 (u == 0: always); the other bin of the pair is >= 128
-          // bins <= 131 are always stored (the mel program reads P in aligned groups of 4 up to
-          // bin 131); the rest of the upper half only when a filter reaches above bin 128
-          if (a.store_hi || k <= 131) Pf[k] = m.x;
-          if (a.store_hi || k >= 125) Pf[256 - k] = m.y;
+          // k = (s < 4 ? u : kb) + 32 s with kb = u, or -112 for u == 0: base pointer + immediate
+          const float2 m = rfft_pair_mag(za, zb, (s < 4 ? twA : twB)[32 * s]);
+          if constexpr (s < 4) {
+            pA[32 * s] = m.x;                    // bin u + 32 s <= 103
+          } else {
+            *plo[s - 4] = isz ? m.x : m.y;       // the bin of the pair that is <= 128
+          }
           esum += m.x + m.y;
         }
         {
-          const int k = k1C + 32 * s;
-          const float2 m = rfft_pair_mag(gC[s], gD[7 - s], tw512_s[k]);
-          if (a.store_hi || k <= 131) Pf[k] = m.x;
-          if (a.store_hi || k >= 125) Pf[256 - k] = m.y;
+          const float2 m = rfft_pair_mag(gC[s], gD[7 - s], twC[32 * s]);
+          if constexpr (s < 4) {
+            pC[32 * s] = m.x;                    // bin k1C + 32 s <= 111
+          } else {
+            pCm[-32 * s] = m.y;                  // bin 256 - k1C - 32 s <= 119
+          }
           esum += m.x + m.y;
         }
       });
@@ -330,7 +342,8 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
         const float m = 2.0f * fast_sqrt(fmaf(gA[4].x, gA[4].x, gA[4].y * gA[4].y));
         Pf[128] = m;
         esum += m;
-        if (a.store_hi) { Pf[257] = 0.f; Pf[258] = 0.f; Pf[259] = 0.f; }  // tail of the last aligned group
+        // tail of the last aligned group of 4 the mel program may read
+        Pf[129] = 0.f; Pf[130] = 0.f; Pf[131] = 0.f;
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
@@ -349,28 +362,31 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
         const int2* desc = reinterpret_cast<const int2*>(tab_s + kTabFixed) + u;
         const float4* pw = reinterpret_cast<const float4*>(tab_s + kTabFixed + a.nit * 16) + u;
         const float4* pw2 = pw + a.nit * 8;
-        float acc = 0.f, num = 0.f;
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f), num4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* melf = mel_s + fi * nf;
+        float* sscf = ssc_s + fi * nf;
+        float* logf_ = log_s + fi * kRow;
 #pragma unroll 1
         for (int it = 0; it < a.nit; ++it) {
           const int2 d = desc[it * 8];
           const float4 w = pw[it * 8];
           const float4 pv = *reinterpret_cast<const float4*>(Pf + d.x);
-          acc = fmaf(w.x, pv.x, acc); acc = fmaf(w.y, pv.y, acc);
-          acc = fmaf(w.z, pv.z, acc); acc = fmaf(w.w, pv.w, acc);
+          acc4.x = fmaf(w.x, pv.x, acc4.x); acc4.y = fmaf(w.y, pv.y, acc4.y);  // four independent chains
+          acc4.z = fmaf(w.z, pv.z, acc4.z); acc4.w = fmaf(w.w, pv.w, acc4.w);
           if (SSC) {
             const float4 w2 = pw2[it * 8];
-            num = fmaf(w2.x, pv.x, num); num = fmaf(w2.y, pv.y, num);
-            num = fmaf(w2.z, pv.z, num); num = fmaf(w2.w, pv.w, num);
+            num4.x = fmaf(w2.x, pv.x, num4.x); num4.y = fmaf(w2.y, pv.y, num4.y);
+            num4.z = fmaf(w2.z, pv.z, num4.z); num4.w = fmaf(w2.w, pv.w, num4.w);
           }
           if (d.y != -2) {  // end of a slot (the same iteration on every lane)
             if (d.y >= 0) {
-              acc = zero_handling(acc);
-              mel_s[fi * nf + d.y] = acc;
-              if (SSC) ssc_s[fi * nf + d.y] = __fdividef(num, acc);
-              log_s[fi * kRow + d.y] = __logf(acc);
+              const float acc = zero_handling((acc4.x + acc4.y) + (acc4.z + acc4.w));
+              melf[d.y] = acc;
+              if (SSC) sscf[d.y] = __fdividef((num4.x + num4.y) + (num4.z + num4.w), acc);
+              logf_[d.y] = __logf(acc);
             }
-            acc = 0.f;
-            num = 0.f;
+            acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            num4 = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         // zero the float4 padding of the log rows (the buffer held FFT data a moment ago)
@@ -400,15 +416,16 @@ __global__ void __launch_bounds__(kThreads, SS_FAST_MINB) k_fast512(const FastAr
         const int c1 = u + 8;
         const float4* d0 = reinterpret_cast<const float4*>(dct_s + u * kRow);
         const float4* d1 = reinterpret_cast<const float4*>(dct_s + (c1 < nc ? c1 : u) * kRow);
-        float acc0 = 0.f, acc1 = 0.f;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
         for (int i = 0; i < n4; ++i) {
           const float4 x = lg[i], da = d0[i], db = d1[i];
-          acc0 = fmaf(da.x, x.x, acc0); acc1 = fmaf(db.x, x.x, acc1);
-          acc0 = fmaf(da.y, x.y, acc0); acc1 = fmaf(db.y, x.y, acc1);
-          acc0 = fmaf(da.z, x.z, acc0); acc1 = fmaf(db.z, x.z, acc1);
-          acc0 = fmaf(da.w, x.w, acc0); acc1 = fmaf(db.w, x.w, acc1);
+          s0.x = fmaf(da.x, x.x, s0.x); s1.x = fmaf(db.x, x.x, s1.x);  // eight independent chains
+          s0.y = fmaf(da.y, x.y, s0.y); s1.y = fmaf(db.y, x.y, s1.y);
+          s0.z = fmaf(da.z, x.z, s0.z); s1.z = fmaf(db.z, x.z, s1.z);
+          s0.w = fmaf(da.w, x.w, s0.w); s1.w = fmaf(db.w, x.w, s1.w);
         }
+        float acc0 = (s0.x + s0.y) + (s0.z + s0.w), acc1 = (s1.x + s1.y) + (s1.z + s1.w);
         if (u == 0) {
           if (p.dc_elim) acc0 = __logf(energy);
           else if (fr == 0) acc0 *= p.scale_00;  // only element [0,0] gets the k=0 scale (feature.rs:128)
@@ -529,7 +546,8 @@ bool fast512_supported(const Derived& d, const MelBank& mb) {
   bool hi;
   build_mel_program(d, mb, &mp, &hi);
   if (mp.nit > kMaxIt) return false;
-  if (4 * ((mb.max_len + 6) / 4) > (hi ? 260 : 132)) return false;  // a padded run must fit the written bins
+  if (hi) return false;                                  // a filter reaches above bin 128: generic kernel
+  if (4 * ((mb.max_len + 6) / 4) > 132) return false;    // a padded run must fit the written bins
   return true;
 }
 
@@ -602,7 +620,6 @@ int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, v
   }
   a.chunks_per_clip = (int)((qpc + a.chunk_quads - 1) / a.chunk_quads);
   a.n_items = p.n_rows * a.chunks_per_clip;
-  a.store_hi = t->store_hi ? 1 : 0;
   a.nit = t->nit;
   a.tab_floats = kTabFixed + t->nit * 8 * (2 + 4 + (p.ssc ? 4 : 0));
   const size_t smem = (size_t)(a.tab_floats + kWarps * kWarpFloats + 2 * a.stash_floats) * sizeof(float);

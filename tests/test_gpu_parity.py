@@ -260,6 +260,32 @@ def test_stft_and_mel_match_oracle(cname, n_clips, ttd):
     assert_spec_close(sb.functions.stft1(x[1], cfg4).real, o.stft1(x[1], oc4).real, what="stft1 after state")
 
 
+@pytest.mark.parametrize("cname,shapes", [("c4", [(5, 32000), (3, 4001), (7, 161), (2, 100), (9, 3200), (1, 48017)])])
+def test_stft_fast_path_matches_generic_and_oracle(cname, shapes):
+    """the size-specialised STFT kernel (fft_points = 400) against the generic kernel and the oracle,
+    including ragged lengths, rows shorter than the overlap memory and row-to-row carry"""
+    kw = CONFIGS[cname]
+    for n, ttd in shapes:
+        x = o.synth_signal(n, ttd, 1000 + ttd)
+        for log in (False, True):
+            fast, gen, oc = sb.SpeechConfig(**kw), sb.SpeechConfig(**kw, flags=GENERIC), o.SpeechConfig(**kw)
+            assert fast.info.fast_stft == 1 and gen.info.fast_stft == 0
+            a = sb.feature.mel_spectrogram2(x, fast, log=log)
+            b = sb.feature.mel_spectrogram2(x, gen, log=log)
+            want = o.log_mel_spectrogram2(x, oc) if log else o.mel_spectrogram2(x, oc)
+            assert a.shape == b.shape == want.shape
+            if log:
+                assert_log_close(a, want, what=f"{cname} fast log-mel {n}x{ttd}")
+                assert_log_close(a, b, what=f"{cname} fast vs generic log-mel {n}x{ttd}")
+            else:
+                assert_spec_close(a, want, what=f"{cname} fast mel {n}x{ttd}")
+                assert_spec_close(a, b, what=f"{cname} fast vs generic mel {n}x{ttd}")
+            # the plan's overlap memory is carried the same way on both paths
+            a2 = sb.feature.mel_spectrogram2(x, fast, log=log)
+            want2 = o.log_mel_spectrogram2(x, oc) if log else o.mel_spectrogram2(x, oc)
+            (assert_log_close if log else assert_spec_close)(a2, want2, what=f"{cname} fast 2nd call {n}x{ttd}")
+
+
 def test_stft_explicit_memory_equals_plan_memory_and_sharding_halo():
     kw = CONFIGS["c4"]
     x = o.synth_signal(8, 3200, 77)
