@@ -175,4 +175,23 @@ __device__ __forceinline__ void fft_5x2(float2 (&x)[N]) {
   }
 }
 
+// y[k] = sum_j x[j] e^{-2 pi i jk/N} for N = 8, 16 or 32: radix-2 Stockham stages in registers
+template <int N>
+__device__ __forceinline__ void fft_pow2(float2 (&x)[N]) {
+  static_assert(N == 8 || N == 16 || N == 32, "8, 16 or 32");
+  float2 t[N];
+  stockham_stage<N, 2, 1>(x, t);
+  stockham_stage<N, 2, 2>(t, x);
+  stockham_stage<N, 2, 4>(x, t);
+  if constexpr (N == 8) {
+    sfor<0, N>([&](auto i) { x[decltype(i)::value] = t[decltype(i)::value]; });
+  } else {
+    stockham_stage<N, 2, 8>(t, x);
+    if constexpr (N == 32) {
+      stockham_stage<N, 2, 16>(x, t);
+      sfor<0, N>([&](auto i) { x[decltype(i)::value] = t[decltype(i)::value]; });
+    }
+  }
+}
+
 }  // namespace ssfft

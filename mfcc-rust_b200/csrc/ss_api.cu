@@ -79,6 +79,7 @@ struct DeviceCtx {
   DevTables tab;
   Fast512Tables* fast512 = nullptr;
   Stft400Tables* stft400 = nullptr;
+  Stft2048Tables* stft2048 = nullptr;
   Lane lanes[kLanes];
   DevBuf dev_scratch;  // scratch for the *_dev entry points (cmvn partials)
   std::string err;     // worker-thread error message
@@ -96,6 +97,7 @@ struct ss_plan {
   std::vector<ss::DeviceCtx> devs;
   bool fast512 = false;
   bool stft400 = false;
+  bool stft2048 = false;
 };
 
 namespace ss {
@@ -144,6 +146,10 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   if (pl->stft400) {
     int e = stft400_build_tables(pl->d, pl->mb, pl->window, &dc->stft400);
     if (e) return cuda_fail((cudaError_t)e, "stft400_build_tables");
+  }
+  if (pl->stft2048) {
+    int e = stft2048_build_tables(pl->d, pl->mb, pl->window, &dc->stft2048);
+    if (e) return cuda_fail((cudaError_t)e, "stft2048_build_tables");
   }
   return SS_OK;
 }
@@ -235,6 +241,10 @@ static void stft_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float*
 static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
   if (pl->stft400 && dc->stft400 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400(p, dc->stft400, dc->sm_count, stream);
+    if (e != -1000) return e;
+  }
+  if (pl->stft2048 && dc->stft2048 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+    const int e = launch_stft2048(p, dc->stft2048, dc->sm_count, stream);
     if (e != -1000) return e;
   }
   return launch_frames_generic(p, stream);
@@ -411,6 +421,7 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   if (pl->d.stft_ok) pl->analysis_mem.assign((size_t)(pl->d.W - pl->d.H), 0.f);  // config.rs:162
   pl->fast512 = pl->fft_ok && fast512_supported(pl->d, pl->mb);
   pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
+  pl->stft2048 = pl->fft_ok && stft2048_supported(pl->d, pl->mb);
   std::vector<int> devs;
   if (n_devices < 0) {
     int n = ss_device_count();
@@ -461,6 +472,7 @@ void ss_plan_destroy(ss_plan* pl) {
     dc.dev_scratch.release();
     if (dc.fast512) fast512_free_tables(dc.fast512);
     if (dc.stft400) stft400_free_tables(dc.stft400);
+    if (dc.stft2048) stft2048_free_tables(dc.stft2048);
   }
   if (prev >= 0) cudaSetDevice(prev);
   delete pl;
@@ -480,7 +492,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
   info->fast_path = pl->fast512 && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  info->fast_stft = pl->stft400 && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
+  info->fast_stft = (pl->stft400 || pl->stft2048) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }
 

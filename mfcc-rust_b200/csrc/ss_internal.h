@@ -125,6 +125,13 @@ int stft400_build_tables(const Derived& d, const MelBank& mb, const std::vector<
 void stft400_free_tables(Stft400Tables* t);
 int launch_stft400(const FrameParams& p, const Stft400Tables* t, int sm_count, void* stream);
 
+// fft_points == 2048 register-FFT path for mel_spectrogram (ss_kernels_stft2048.cu)
+bool stft2048_supported(const Derived& d, const MelBank& mb);
+struct Stft2048Tables;
+int stft2048_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft2048Tables** out);
+void stft2048_free_tables(Stft2048Tables* t);
+int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count, void* stream);
+
 int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
                        int64_t shift, float cof, void* stream);
 int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,

@@ -260,9 +260,10 @@ def test_stft_and_mel_match_oracle(cname, n_clips, ttd):
     assert_spec_close(sb.functions.stft1(x[1], cfg4).real, o.stft1(x[1], oc4).real, what="stft1 after state")
 
 
-@pytest.mark.parametrize("cname,shapes", [("c4", [(5, 32000), (3, 4001), (7, 161), (2, 100), (9, 3200), (1, 48017)])])
+@pytest.mark.parametrize("cname,shapes", [("c4", [(5, 32000), (3, 4001), (7, 161), (2, 100), (9, 3200), (1, 48017)]),
+                                          ("c3", [(3, 22050), (2, 5001), (4, 2048), (2, 700), (1, 110250), (37, 16896)])])
 def test_stft_fast_path_matches_generic_and_oracle(cname, shapes):
-    """the size-specialised STFT kernel (fft_points = 400) against the generic kernel and the oracle,
+    """the size-specialised STFT kernels (fft_points = 400 / 2048) against the generic kernel and the oracle,
     including ragged lengths, rows shorter than the overlap memory and row-to-row carry"""
     kw = CONFIGS[cname]
     for n, ttd in shapes:
