@@ -132,7 +132,8 @@ def run_reference(args, w):
         return
     import oracle_c
     import speechsauce_oracle as o
-    cores = oracle_c.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed to
+    cores = len(os.sched_getaffinity(0))
     cfg = oracle_c.make_config(**w["cfg"])
     if w["kind"] == "speechpy":
         sample = min(w["n"], 512 * cores) if w["length"] <= 10**6 else cores
@@ -145,9 +146,9 @@ def run_reference(args, w):
     def step():
         if w["kind"] == "speechpy":
             kw = {k: True for k in w["outs"] if k != "ssc"}
-            oracle_c.features(x, cfg, cmvn_mode=w["cmvn"], **kw)
+            oracle_c.features(x, cfg, cmvn_mode=w["cmvn"], n_threads=cores, **kw)
         else:
-            oracle_c.mel_spectrogram2(x, cfg, log=bool(w["log"]))
+            oracle_c.mel_spectrogram2(x, cfg, log=bool(w["log"]), n_threads=cores)
 
     for _ in range(args.warmup):
         step()
@@ -310,21 +311,21 @@ def main():
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
         import oracle_c
         import speechsauce_oracle as orc
-        cores = oracle_c.max_threads()
+        cores = len(os.sched_getaffinity(0))
         ccfg = oracle_c.make_config(**w["cfg"])
         if w["kind"] == "speechpy":
             cs = min(n, 2048 * cores) if length <= 10**6 else cores
             cl = min(length, 16000 * 600)
             xs = orc.synth_signal(cs, cl, 1)
             kw = {k: True for k in w["outs"] if k != "ssc"}
-            oracle_c.features(xs[: max(1, cs // 8)], ccfg, cmvn_mode=w["cmvn"], **kw)
+            oracle_c.features(xs[: max(1, cs // 8)], ccfg, cmvn_mode=w["cmvn"], n_threads=cores, **kw)
             t0 = time.perf_counter()
-            oracle_c.features(xs, ccfg, cmvn_mode=w["cmvn"], **kw)
+            oracle_c.features(xs, ccfg, cmvn_mode=w["cmvn"], n_threads=cores, **kw)
         else:
             cs, cl = 8 * cores, length
             xs = orc.synth_signal(cs, cl, 1)
             t0 = time.perf_counter()
-            oracle_c.mel_spectrogram2(xs, ccfg, log=bool(w["log"]))
+            oracle_c.mel_spectrogram2(xs, ccfg, log=bool(w["log"]), n_threads=cores)
         dt = time.perf_counter() - t0
         cpu = {"value": cs * cl / w["cfg"]["sample_rate"] / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                "sample": f"{cs} clips x {cl / w['cfg']['sample_rate']:.0f} s, {dt:.1f} s wall; restated CPU reference "
