@@ -127,7 +127,8 @@ __device__ __forceinline__ void dft5(float2& x0, float2& x1, float2& x2, float2&
 
 // One Stockham stage on a register array: N points, radix R (2 or 5), sub-length NS.
 //   out[(j / NS) * NS * R + k + r * NS] = DFT_R( in[j + r * N/R] * W_{NS*R}^{k r} ),  k = j % NS
-template <int N, int R, int NS>
+// JNZ: in[j] is a structural zero for j >= JNZ (zero padding); only used by the first stage.
+template <int N, int R, int NS, int JNZ = N>
 __device__ __forceinline__ void stockham_stage(const float2 (&in)[N], float2 (&out)[N]) {
   static_assert(R == 2 || R == 5, "radix 2 or 5");
   constexpr int NB = N / R;
@@ -135,7 +136,10 @@ __device__ __forceinline__ void stockham_stage(const float2 (&in)[N], float2 (&o
     constexpr int j = decltype(jj)::value;
     constexpr int k = j % NS;
     constexpr int o = (j / NS) * NS * R + k;
-    if constexpr (R == 2) {
+    if constexpr (R == 2 && NS == 1 && j + NB >= JNZ) {
+      out[o] = in[j];  // a + 0, a - 0
+      out[o + NS] = in[j];
+    } else if constexpr (R == 2) {
       float2 a = in[j], b = in[j + NB];
       bfly2<NS * 2, k>(a, b);
       out[o] = a;
@@ -176,11 +180,11 @@ __device__ __forceinline__ void fft_5x2(float2 (&x)[N]) {
 }
 
 // y[k] = sum_j x[j] e^{-2 pi i jk/N} for N = 8, 16 or 32: radix-2 Stockham stages in registers
-template <int N>
+template <int N, int JNZ = N>
 __device__ __forceinline__ void fft_pow2(float2 (&x)[N]) {
   static_assert(N == 8 || N == 16 || N == 32, "8, 16 or 32");
   float2 t[N];
-  stockham_stage<N, 2, 1>(x, t);
+  stockham_stage<N, 2, 1, JNZ>(x, t);
   stockham_stage<N, 2, 2>(t, x);
   stockham_stage<N, 2, 4>(x, t);
   if constexpr (N == 8) {

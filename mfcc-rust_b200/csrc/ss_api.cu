@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -78,6 +79,7 @@ struct DeviceCtx {
   DevBuf tables;  // one allocation holding every device table
   DevTables tab;
   Fast512Tables* fast512 = nullptr;
+  Fast512bTables* fast512b = nullptr;
   Stft400Tables* stft400 = nullptr;
   Stft2048Tables* stft2048 = nullptr;
   Lane lanes[kLanes];
@@ -96,6 +98,7 @@ struct ss_plan {
   std::vector<float> analysis_mem;  // [W-H], config.rs:126,162
   std::vector<ss::DeviceCtx> devs;
   bool fast512 = false;
+  bool fast512b = false;
   bool stft400 = false;
   bool stft2048 = false;
 };
@@ -142,6 +145,10 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   if (pl->fast512) {
     int e = fast512_build_tables(pl->d, pl->mb, &dc->fast512);
     if (e) return cuda_fail((cudaError_t)e, "fast512_build_tables");
+  }
+  if (pl->fast512b) {
+    int e = fast512b_build_tables(pl->d, pl->mb, &dc->fast512b);
+    if (e) return cuda_fail((cudaError_t)e, "fast512b_build_tables");
   }
   if (pl->stft400) {
     int e = stft400_build_tables(pl->d, pl->mb, pl->window, &dc->stft400);
@@ -190,9 +197,12 @@ static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const f
   p.tab = dc->tab;
   bool cmvn_done = false;
   int e;
-  const bool use_fast = pl->fast512 && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  const bool use_fast = (pl->fast512 || pl->fast512b) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  // SS_FAST512_GEN1=1 selects the first-generation kernel (8 lanes x 32 points) for A/B measurements
+  static const bool gen1 = getenv("SS_FAST512_GEN1") != nullptr;
   if (use_fast) {
-    e = launch_fast512(p, dc->fast512, dc->sm_count, stream);
+    if (pl->fast512b && !(gen1 && pl->fast512)) e = launch_fast512b(p, dc->fast512b, dc->sm_count, stream);
+    else e = launch_fast512(p, dc->fast512, dc->sm_count, stream);
     cmvn_done = true;  // the fast path normalises in-kernel or enqueues its own cmvn pass
     if (e == -1000) {  // the fast path declined this shape; fall through to the generic kernel
       cmvn_done = false;
@@ -420,6 +430,7 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   pl->fft_ok = pl->d.W <= (1 << 20) && build_fft_plan((int)pl->d.W, &pl->fft);
   if (pl->d.stft_ok) pl->analysis_mem.assign((size_t)(pl->d.W - pl->d.H), 0.f);  // config.rs:162
   pl->fast512 = pl->fft_ok && fast512_supported(pl->d, pl->mb);
+  pl->fast512b = pl->fft_ok && fast512b_supported(pl->d, pl->mb);
   pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
   pl->stft2048 = pl->fft_ok && stft2048_supported(pl->d, pl->mb);
   std::vector<int> devs;
@@ -471,6 +482,7 @@ void ss_plan_destroy(ss_plan* pl) {
     dc.tables.release();
     dc.dev_scratch.release();
     if (dc.fast512) fast512_free_tables(dc.fast512);
+    if (dc.fast512b) fast512b_free_tables(dc.fast512b);
     if (dc.stft400) stft400_free_tables(dc.stft400);
     if (dc.stft2048) stft2048_free_tables(dc.stft2048);
   }
@@ -491,7 +503,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->num_cepstral = d.nc;
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
-  info->fast_path = pl->fast512 && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  info->fast_path = (pl->fast512 || pl->fast512b) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
   info->fast_stft = (pl->stft400 || pl->stft2048) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }

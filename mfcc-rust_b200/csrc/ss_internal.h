@@ -118,6 +118,13 @@ int fast512_build_tables(const Derived& d, const MelBank& mb, Fast512Tables** ou
 void fast512_free_tables(Fast512Tables* t);
 int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, void* stream);
 
+// second-generation n_fft == 512 kernel: 16 lanes x 16 points per frame (ss_kernels_fast512b.cu)
+bool fast512b_supported(const Derived& d, const MelBank& mb);
+struct Fast512bTables;
+int fast512b_build_tables(const Derived& d, const MelBank& mb, Fast512bTables** out);
+void fast512b_free_tables(Fast512bTables* t);
+int launch_fast512b(const FrameParams& p, const Fast512bTables* t, int sm_count, void* stream);
+
 // fft_points == 400 register-FFT path for mel_spectrogram (ss_kernels_stft400.cu)
 bool stft400_supported(const Derived& d, const MelBank& mb);
 struct Stft400Tables;

@@ -1,0 +1,37 @@
+"""Small invocation of every kernel for compute-sanitizer (memcheck / racecheck / initcheck):
+    compute-sanitizer --tool memcheck python tests/sanitize_small.py
+Not a pytest file; shapes are tiny so the instrumented run finishes in seconds."""
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT / "mfcc-rust_b200"), str(ROOT / "oracle")]
+import numpy as np  # noqa: E402
+import speechsauce_b200 as sb  # noqa: E402
+import speechsauce_oracle as o  # noqa: E402
+from speechsauce_b200 import _lib  # noqa: E402
+
+C1 = dict(sample_rate=16000, fft_points=512, frame_length=0.025, frame_stride=0.01, num_cepstral=13, num_filters=40,
+          low_frequency=0.0, high_frequency=8000.0)
+C3 = dict(sample_rate=22050, fft_points=2048, frame_length=512 / 22050, frame_stride=0.01, num_cepstral=13,
+          num_filters=128, low_frequency=0.0, high_frequency=11025.0)
+C4 = dict(sample_rate=16000, fft_points=400, frame_length=0.01, frame_stride=0.01, num_cepstral=13, num_filters=80,
+          low_frequency=0.0, high_frequency=8000.0)
+x = o.synth_signal(5, 16000, 1)
+for flags in (0, _lib.SS_FLAG_FORCE_GENERIC):
+    cfg = sb.SpeechConfig(**C1, devices=[0], flags=flags)
+    sb.feature.features(x, cfg, mfe=True, energy=True, lmfe=True, ssc=True, mfcc=True, cmvn_mode=2)
+    sb.feature.features(x[:, :5003], cfg, lmfe=True, mfcc=True, cmvn_mode=0)
+    sb.feature.features(o.synth_signal(2, 200_000, 2), cfg, mfcc=True, cmvn_mode=2)  # too long for the fused stash
+    for c, n, ttd in ((C4, 3, 4001), (C4, 2, 100), (C3, 2, 9000), (C3, 2, 700)):
+        k = sb.SpeechConfig(**c, devices=[0], flags=flags)
+        y = o.synth_signal(n, ttd, 3)
+        sb.feature.mel_spectrogram2(y, k, log=True)
+        sb.functions.stft2(y, k)
+sb.processing.preemphasis(x[0]); sb.processing.preemphasis(x)
+sb.processing.stack_frames(x[0], 16000, 0.025, 0.01, None, True)
+sb.processing.power_spectrum(o.synth_signal(9, 400, 4), 512)
+sb.processing.cmvn(o.synth_signal(300, 13, 5), True)
+sb.processing.cmvn(o.synth_signal(4, 97 * 13, 6).reshape(4, 97, 13), True)
+print("sanitize_small: all kernels ran")
