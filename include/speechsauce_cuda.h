@@ -160,6 +160,21 @@ int ss_cmvn(const float* in, int64_t rows, int64_t cols, int variance_normalizat
 int ss_cmvn_batch(const float* in, int64_t n_mats, int64_t rows, int64_t cols,
                   int variance_normalization, float* out);
 
+/* ---- "next" rows: delta features and sliding-window CMVN.  The reference's util::pad
+ *      symmetric / edge modes are degenerate as written, so these follow the speechpy behaviour the
+ *      Rust code transliterates (numpy 'edge' / 'symmetric' padding); see DESIGN.md. --------------- */
+/* processing::derivative_extraction (processing.rs:222-254): in/out [rows][cols], edge-padded along features */
+int ss_derivative_extraction(const float* in, int64_t rows, int64_t cols, int delta_windows, float* out);
+/* feature::extract_derivative_feature (feature.rs:253-269): out [rows][cols][3] = static, delta, delta-delta */
+int ss_extract_derivative_feature(const float* in, int64_t rows, int64_t cols, float* out_cube);
+/* processing::cmvnw (processing.rs:315-371): sliding window (odd win_size), symmetric padding along time */
+int ss_cmvnw(const float* in, int64_t rows, int64_t cols, int64_t win_size, int variance_normalization, float* out);
+int ss_derivative_extraction_dev(void* cuda_stream, const float* d_in, int64_t rows, int64_t cols, int delta_windows,
+                                 float* d_out);
+int ss_extract_derivative_feature_dev(void* cuda_stream, const float* d_in, int64_t rows, int64_t cols, float* d_out_cube);
+int ss_cmvnw_dev(void* cuda_stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols, int64_t win_size,
+                 int variance_normalization, float* d_out);
+
 /* ---- device-resident variants: device pointers on plan device `dev_index`, enqueued on
  *      `cuda_stream` (a cudaStream_t; NULL = legacy default stream), no synchronisation.
  *      Used by the throughput harness and by callers that already hold data in HBM. ------- */

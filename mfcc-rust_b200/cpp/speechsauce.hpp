@@ -182,6 +182,12 @@ inline Array2 mel_spectrogram1(View1 signal, const SpeechConfig& cfg) {
   check(ss_mel_spectrogram(cfg.plan(), signal.data, 1, (int64_t)signal.len, (int64_t)signal.len, out.v.data(), nullptr, 0));
   return out;
 }
+// feature.rs:253 -> [T][C][3] = static, delta, delta-delta
+inline Array3 extract_derivative_feature(View2 feat) {
+  Array3 out(feat.rows, feat.cols, 3);
+  check(ss_extract_derivative_feature(feat.data, (int64_t)feat.rows, (int64_t)feat.cols, out.v.data()));
+  return out;
+}
 }  // namespace feature
 
 namespace processing {
@@ -211,6 +217,18 @@ inline Array2 power_spectrum(View2 frames, size_t fft_points) {
 inline Array2 cmvn(View2 vec, bool variance_normalization) {
   Array2 out(vec.rows, vec.cols);
   check(ss_cmvn(vec.data, (int64_t)vec.rows, (int64_t)vec.cols, variance_normalization, out.v.data()));
+  return out;
+}
+// processing.rs:222 (numpy 'edge' padding along the feature axis)
+inline Array2 derivative_extraction(View2 feat, int delta_windows = 2) {
+  Array2 out(feat.rows, feat.cols);
+  check(ss_derivative_extraction(feat.data, (int64_t)feat.rows, (int64_t)feat.cols, delta_windows, out.v.data()));
+  return out;
+}
+// processing.rs:315 (numpy 'symmetric' padding along time)
+inline Array2 cmvnw(View2 vec, size_t win_size = 301, bool variance_normalization = false) {
+  Array2 out(vec.rows, vec.cols);
+  check(ss_cmvnw(vec.data, (int64_t)vec.rows, (int64_t)vec.cols, (int64_t)win_size, variance_normalization, out.v.data()));
   return out;
 }
 }  // namespace processing

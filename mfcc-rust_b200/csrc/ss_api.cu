@@ -380,6 +380,21 @@ static int default_ctx(DefaultCtx** out) {
   return SS_OK;
 }
 
+// host buffers -> device -> fn -> host buffers on the default context
+template <class Fn>
+static int host_unary(const float* in, size_t in_floats, float* out, size_t out_floats, Fn fn) {
+  if (!in || !out) return fail(SS_ERR_INVALID_ARG, "null argument");
+  DefaultCtx* c;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  if ((rc = c->a.reserve(std::max<size_t>(16, in_floats * 4)))) return rc;
+  if ((rc = c->b.reserve(std::max<size_t>(16, out_floats * 4)))) return rc;
+  if (in_floats) SS_CUDA(cudaMemcpyAsync(c->a.p, in, in_floats * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = fn(c->stream, static_cast<float*>(c->a.p), static_cast<float*>(c->b.p)))) return rc;
+  if (out_floats) SS_CUDA(cudaMemcpyAsync(out, c->b.p, out_floats * 4, cudaMemcpyDeviceToHost, c->stream));
+  SS_CUDA(cudaStreamSynchronize(c->stream));
+  return SS_OK;
+}
 }  // namespace ss
 
 using namespace ss;
@@ -929,6 +944,58 @@ int ss_cmvn_batch(const float* in, int64_t n_mats, int64_t rows, int64_t cols, i
 }
 int ss_cmvn(const float* in, int64_t rows, int64_t cols, int varnorm, float* out) {
   return ss_cmvn_batch(in, 1, rows, cols, varnorm, out);
+}
+
+// ------------------------------------------------------------ "next" rows: deltas, cmvnw
+int ss_derivative_extraction_dev(void* stream, const float* d_in, int64_t rows, int64_t cols, int dw, float* d_out) {
+  if (!d_in || !d_out) return fail(SS_ERR_INVALID_ARG, "null argument");
+  if (rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  if (dw < 1) return fail(SS_ERR_INVALID_ARG, "delta_windows must be >= 1 (zero scale in the reference, processing.rs:253)");
+  if (d_in == d_out) return fail(SS_ERR_INVALID_ARG, "derivative_extraction cannot run in place");
+  int e = launch_derivative(d_in, rows, cols, dw, d_out, stream);
+  if (e) return cuda_fail((cudaError_t)e, "derivative launch");
+  return SS_OK;
+}
+int ss_extract_derivative_feature_dev(void* stream, const float* d_in, int64_t rows, int64_t cols, float* d_out) {
+  if (!d_in || !d_out) return fail(SS_ERR_INVALID_ARG, "null argument");
+  if (rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  int e = launch_derivative_cube(d_in, rows, cols, d_out, stream);
+  if (e) return cuda_fail((cudaError_t)e, "derivative cube launch");
+  return SS_OK;
+}
+static thread_local DevBuf g_cmvnw_scratch;
+int ss_cmvnw_dev(void* stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols, int64_t win, int varnorm,
+                 float* d_out) {
+  if (!d_in || !d_out) return fail(SS_ERR_INVALID_ARG, "null argument");
+  if (n_mats < 0 || rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  if (win < 1 || win % 2 != 1) return fail(SS_ERR_INVALID_ARG, "Windows size must be odd! (processing.rs:327)");
+  if (cols > 256 || n_mats > 65535 || win > (1 << 24)) return fail(SS_ERR_UNSUPPORTED, "cmvnw: shape outside this build's limits");
+  if (n_mats == 0 || rows == 0 || cols == 0) return SS_OK;
+  float* scratch = nullptr;
+  if (varnorm) {
+    int rc = g_cmvnw_scratch.reserve((size_t)n_mats * rows * cols * sizeof(float));
+    if (rc) return rc;
+    scratch = static_cast<float*>(g_cmvnw_scratch.p);
+  }
+  int e = launch_cmvnw(d_in, n_mats, rows, cols, (int)win, varnorm, d_out, scratch, stream);
+  if (e) return cuda_fail((cudaError_t)e, "cmvnw launch");
+  return SS_OK;
+}
+
+int ss_derivative_extraction(const float* in, int64_t rows, int64_t cols, int dw, float* out) {
+  if (rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  return host_unary(in, (size_t)rows * cols, out, (size_t)rows * cols,
+                    [&](cudaStream_t s, float* a, float* b) { return ss_derivative_extraction_dev(s, a, rows, cols, dw, b); });
+}
+int ss_extract_derivative_feature(const float* in, int64_t rows, int64_t cols, float* out) {
+  if (rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  return host_unary(in, (size_t)rows * cols, out, (size_t)rows * cols * 3,
+                    [&](cudaStream_t s, float* a, float* b) { return ss_extract_derivative_feature_dev(s, a, rows, cols, b); });
+}
+int ss_cmvnw(const float* in, int64_t rows, int64_t cols, int64_t win, int varnorm, float* out) {
+  if (rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  return host_unary(in, (size_t)rows * cols, out, (size_t)rows * cols,
+                    [&](cudaStream_t s, float* a, float* b) { return ss_cmvnw_dev(s, a, 1, rows, cols, win, varnorm, b); });
 }
 
 }  // extern "C"

@@ -7,6 +7,8 @@
 // statistics.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "ss_internal.h"
 
 namespace ss {
@@ -162,6 +164,101 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
   }
 }
 
+// ------------------------------------------------------------------ derivative features
+// processing::derivative_extraction (processing.rs:222-254) with numpy 'edge' padding along the
+// FEATURE axis (the reference's util::pad edge mode is degenerate):
+//   out[r][c] = (sum_{q=1..dw} (F[r][clamp(c+q)] * q - F[r][clamp(c-q)])) / (2 sum q^2)
+// Unfused multiplies / adds in the reference's order, so results are bit-identical to it.
+__device__ __forceinline__ float delta_at(const float* __restrict__ row, int cols, int c, int dw, float scale) {
+  float dif = 0.f;
+  for (int q = 1; q <= dw; ++q) {
+    const float a = __ldg(row + min(c + q, cols - 1)), b = __ldg(row + max(c - q, 0));
+    dif = __fadd_rn(dif, __fsub_rn(__fmul_rn(a, (float)q), b));
+  }
+  return __fdiv_rn(dif, scale);
+}
+
+__global__ void __launch_bounds__(256) k_derivative(const float* __restrict__ in, float* __restrict__ out,
+                                                    int64_t rows, int cols, int dw, float scale) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    out[i] = delta_at(in + r * cols, cols, c, dw, scale);
+  }
+}
+
+// feature::extract_derivative_feature (feature.rs:253-269): [rows][cols] -> [rows][cols][3] =
+// (static, delta, delta-delta) with DeltaWindows = 2; delta-delta is the delta of the delta row.
+__global__ void __launch_bounds__(256) k_derivative_cube(const float* __restrict__ in, float* __restrict__ out,
+                                                         int64_t rows, int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float* row = in + r * cols;
+    float d[5];  // delta at clamp(c-2) .. clamp(c+2)
+#pragma unroll
+    for (int k = -2; k <= 2; ++k) d[k + 2] = delta_at(row, cols, min(max(c + k, 0), cols - 1), 2, 10.0f);
+    float dd = 0.f;
+    dd = __fadd_rn(dd, __fsub_rn(__fmul_rn(d[3], 1.0f), d[1]));
+    dd = __fadd_rn(dd, __fsub_rn(__fmul_rn(d[4], 2.0f), d[0]));
+    out[i * 3] = __ldg(row + c);
+    out[i * 3 + 1] = d[2];
+    out[i * 3 + 2] = __fdiv_rn(dd, 10.0f);
+  }
+}
+
+// ------------------------------------------------------------------------- cmvnw
+// processing::cmvnw (processing.rs:315-371) with numpy 'symmetric' padding along time.  One thread
+// owns (column, chunk of rows): it sums its first window directly, then slides.  Sums are kept in
+// double so the result does not depend on the chunking.  Pass 1: y = x - window mean; pass 2
+// (variance normalisation): y / (window std of the symmetric-padded y + 2^-30).
+__device__ __forceinline__ int64_t reflect_sym(int64_t i, int64_t n) {
+  const int64_t p = 2 * n;
+  i %= p;
+  if (i < 0) i += p;
+  return i < n ? i : p - 1 - i;
+}
+
+template <bool VAR>
+__global__ void __launch_bounds__(256) k_cmvnw(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
+                                               int cols, int win, int chunk) {
+  const int64_t mat = blockIdx.y;
+  const int colsp = blockDim.x >= 32 ? 1 : 1;
+  (void)colsp;
+  const int c = threadIdx.x % cols;          // threads beyond a multiple of cols idle
+  const int lane = threadIdx.x / cols;
+  const int lanes = blockDim.x / cols;
+  if (lane >= lanes) return;
+  const float* x = in + mat * rows * cols;
+  float* y = out + mat * rows * cols;
+  const int64_t r0 = ((int64_t)blockIdx.x * lanes + lane) * chunk;
+  if (r0 >= rows) return;
+  const int64_t r1 = min(rows, r0 + chunk);
+  const int p = (win - 1) / 2;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t j = r0 - p; j <= r0 + p; ++j) {
+    const double v = (double)__ldg(x + reflect_sym(j, rows) * cols + c);
+    s1 += v;
+    if (VAR) s2 += v * v;
+  }
+  for (int64_t r = r0; r < r1; ++r) {
+    const float v = __ldg(x + r * cols + c);
+    if (!VAR) {
+      y[r * cols + c] = v - (float)(s1 / (double)win);
+    } else {
+      const double m = s1 / (double)win;
+      const double var = fmax(s2 / (double)win - m * m, 0.0);
+      y[r * cols + c] = v / ((float)sqrt(var) + kCmvnEps);
+    }
+    const double a = (double)__ldg(x + reflect_sym(r + p + 1, rows) * cols + c);
+    const double b = (double)__ldg(x + reflect_sym(r - p, rows) * cols + c);
+    s1 += a - b;
+    if (VAR) s2 += a * a - b * b;
+  }
+}
+
 inline int64_t cmvn_rows_per_blk(int64_t n_mats, int64_t rows) {
   // enough blocks to fill the chip a few times over, at least 64 rows per block
   const int64_t want_blocks = 8 * kSmCountGuess;
@@ -199,6 +296,43 @@ int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_
   int64_t blocks = (T * L + 255) / 256;
   if (blocks > 16LL * kSmCountGuess) blocks = 16LL * kSmCountGuess;
   k_stack_frames<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, L, S, T, flags);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_derivative(const float* in, int64_t rows, int64_t cols, int dw, float* out, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  float scale = 0.f;
+  for (int q = 1; q <= dw; ++q) scale += 2.0f * (float)(q * q);  // processing.rs:249
+  int64_t blocks = std::min<int64_t>((rows * cols + 255) / 256, 16LL * kSmCountGuess);
+  k_derivative<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, rows, (int)cols, dw, scale);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_derivative_cube(const float* in, int64_t rows, int64_t cols, float* out, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  int64_t blocks = std::min<int64_t>((rows * cols + 255) / 256, 16LL * kSmCountGuess);
+  k_derivative_cube<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, rows, (int)cols);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// scratch: n_mats * rows * cols floats when variance_normalization (the mean-subtracted matrix)
+int launch_cmvnw(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int win, int varnorm, float* out,
+                 float* scratch, void* stream) {
+  if (n_mats <= 0 || rows <= 0 || cols <= 0) return 0;
+  if (cols > 256 || n_mats > 65535) return (int)cudaErrorInvalidValue;
+  const int lanes = 256 / (int)cols;
+  const int chunk = 256;
+  const int64_t nchunks = (rows + chunk - 1) / chunk;
+  dim3 grid((unsigned)((nchunks + lanes - 1) / lanes), (unsigned)n_mats);
+  float* y = varnorm ? scratch : out;
+  k_cmvnw<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, y, rows, (int)cols, win, chunk);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !varnorm) return (int)e;
+  k_cmvnw<true><<<grid, 256, 0, (cudaStream_t)stream>>>(y, out, rows, (int)cols, win, chunk);
   count_launch();
   return (int)cudaGetLastError();
 }

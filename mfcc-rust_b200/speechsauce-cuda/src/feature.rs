@@ -77,3 +77,12 @@ pub fn mel_spectrogram1(signal: ArrayView1<f32>, cfg: &SpeechConfig) -> Array2<f
     unsafe { check(ffi::ss_mel_spectrogram(cfg.plan, x.as_ptr(), 1, ttd as i64, ttd as i64, out.as_mut_ptr(), ptr::null_mut(), 0)) };
     out
 }
+
+/// feature.rs:253 (private in the reference) — [T, C] -> [T, C, 3] = static, delta, delta-delta
+pub fn extract_derivative_feature(feature: Array2<f32>) -> Array3<f32> {
+    let x = feature.as_standard_layout();
+    let (rows, cols) = x.dim();
+    let mut out = Array3::<f32>::zeros((rows, cols, 3));
+    unsafe { check(ffi::ss_extract_derivative_feature(x.as_ptr(), rows as i64, cols as i64, out.as_mut_ptr())) };
+    out
+}

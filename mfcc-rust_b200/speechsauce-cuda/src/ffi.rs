@@ -104,6 +104,15 @@ extern "C" {
                                  d_out: *mut f32) -> c_int;
     pub fn ss_cmvn_dev(cuda_stream: *mut c_void, d_in: *const f32, n_mats: i64, rows: i64, cols: i64,
                        variance_normalization: c_int, d_out: *mut f32) -> c_int;
+    pub fn ss_derivative_extraction(input: *const f32, rows: i64, cols: i64, delta_windows: c_int, out: *mut f32) -> c_int;
+    pub fn ss_extract_derivative_feature(input: *const f32, rows: i64, cols: i64, out_cube: *mut f32) -> c_int;
+    pub fn ss_cmvnw(input: *const f32, rows: i64, cols: i64, win_size: i64, variance_normalization: c_int, out: *mut f32) -> c_int;
+    pub fn ss_derivative_extraction_dev(cuda_stream: *mut c_void, d_in: *const f32, rows: i64, cols: i64, delta_windows: c_int,
+                                        d_out: *mut f32) -> c_int;
+    pub fn ss_extract_derivative_feature_dev(cuda_stream: *mut c_void, d_in: *const f32, rows: i64, cols: i64,
+                                             d_out_cube: *mut f32) -> c_int;
+    pub fn ss_cmvnw_dev(cuda_stream: *mut c_void, d_in: *const f32, n_mats: i64, rows: i64, cols: i64, win_size: i64,
+                        variance_normalization: c_int, d_out: *mut f32) -> c_int;
     pub fn ss_debug_filterbank(plan: *const ss_plan, out_nf_by_f: *mut f32) -> c_int;
     pub fn ss_debug_window(plan: *const ss_plan, out_w: *mut f32) -> c_int;
     pub fn ss_kernel_launch_count() -> i64;

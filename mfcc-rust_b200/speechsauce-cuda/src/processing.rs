@@ -43,3 +43,21 @@ pub fn cmvn(vec: ArrayView2<f32>, variance_normalization: bool) -> Array2<f32> {
     unsafe { check(ffi::ss_cmvn(v.as_ptr(), rows as i64, cols as i64, variance_normalization as i32, out.as_mut_ptr())) };
     out
 }
+
+/// processing.rs:222 — delta features along the feature axis (numpy 'edge' padding)
+pub fn derivative_extraction(feat: &Array2<f32>, delta_windows: usize) -> Array2<f32> {
+    let f = feat.as_standard_layout();
+    let (rows, cols) = f.dim();
+    let mut out = Array2::<f32>::zeros((rows, cols));
+    unsafe { check(ffi::ss_derivative_extraction(f.as_ptr(), rows as i64, cols as i64, delta_windows as i32, out.as_mut_ptr())) };
+    out
+}
+
+/// processing.rs:315 — sliding-window CMVN (numpy 'symmetric' padding along time)
+pub fn cmvnw(vec: Array2<f32>, win_size: usize, variance_normalization: bool) -> Array2<f32> {
+    let v = vec.as_standard_layout();
+    let (rows, cols) = v.dim();
+    let mut out = Array2::<f32>::zeros((rows, cols));
+    unsafe { check(ffi::ss_cmvnw(v.as_ptr(), rows as i64, cols as i64, win_size as i64, variance_normalization as i32, out.as_mut_ptr())) };
+    out
+}

@@ -91,6 +91,12 @@ SYMBOLS = {
     "ss_stack_frames_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, C.c_uint32, _fp, _i64]),
     "ss_power_spectrum_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, _fp]),
     "ss_cmvn_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, _fp]),
+    "ss_derivative_extraction": (C.c_int, [_fp, _i64, _i64, C.c_int, _fp]),
+    "ss_extract_derivative_feature": (C.c_int, [_fp, _i64, _i64, _fp]),
+    "ss_cmvnw": (C.c_int, [_fp, _i64, _i64, _i64, C.c_int, _fp]),
+    "ss_derivative_extraction_dev": (C.c_int, [_vp, _fp, _i64, _i64, C.c_int, _fp]),
+    "ss_extract_derivative_feature_dev": (C.c_int, [_vp, _fp, _i64, _i64, _fp]),
+    "ss_cmvnw_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, _i64, C.c_int, _fp]),
     "ss_debug_filterbank": (C.c_int, [_vp, _fp]),
     "ss_debug_window": (C.c_int, [_vp, _fp]),
     "ss_kernel_launch_count": (_i64, []),

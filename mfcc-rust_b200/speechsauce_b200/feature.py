@@ -87,3 +87,14 @@ def mel_spectrogram1(signal, cfg, **kw):
     if x.ndim != 1:
         raise ValueError("mel_spectrogram1 takes a 1-D signal")
     return mel_spectrogram2(x[None, :], cfg, **kw)[0]
+
+
+def extract_derivative_feature(feat):
+    """feature::extract_derivative_feature (feature.rs:253-269, private in the reference):
+    [T, C] -> [T, C, 3] = (static, delta, delta-delta)."""
+    x = np.ascontiguousarray(feat, np.float32)
+    if x.ndim != 2:
+        raise ValueError("feature must be 2-D")
+    out = np.empty(x.shape + (3,), np.float32)
+    check(lib.ss_extract_derivative_feature(_lib.fptr(x), x.shape[0], x.shape[1], _lib.fptr(out)))
+    return out

@@ -70,3 +70,19 @@ def cmvn(vec, variance_normalization=False):
     else:
         raise ValueError("vec must be 2-D or 3-D")
     return out
+
+
+def derivative_extraction(feat, delta_windows=2):
+    """processing::derivative_extraction (processing.rs:222-254), numpy 'edge' padding along features."""
+    f = _f32(feat, 2)
+    out = np.empty_like(f)
+    check(lib.ss_derivative_extraction(_lib.fptr(f), f.shape[0], f.shape[1], int(delta_windows), _lib.fptr(out)))
+    return out
+
+
+def cmvnw(vec, win_size=301, variance_normalization=False):
+    """processing::cmvnw (processing.rs:315-371), numpy 'symmetric' padding along time."""
+    v = _f32(vec, 2)
+    out = np.empty_like(v)
+    check(lib.ss_cmvnw(_lib.fptr(v), v.shape[0], v.shape[1], int(win_size), int(bool(variance_normalization)), _lib.fptr(out)))
+    return out

@@ -385,3 +385,73 @@ def synth_signal(n_clips, clip_len, seed=0x5EED0000):
     """N(0, 0.1^2) f32 clips, the reference fixture's distribution (lib.rs:18-22)."""
     rng = np.random.Generator(np.random.Philox(seed))
     return (rng.standard_normal((n_clips, clip_len), dtype=np.float32) * np.float32(0.1))
+
+
+# ------------------------------------------------- "next" rows of SURVEY 8(f): deltas, cmvnw
+#
+# The reference's util::pad symmetric / edge modes are degenerate as written (util.rs:75-369:
+# `pad` copies the input into the top-left corner and `edge_pad` then overwrites the centre with
+# the last row; `symmetric_pad` / `set_edge` assign mismatched shapes), so these two functions
+# follow the documented speechpy behaviour the Rust code transliterates: numpy's 'edge' and
+# 'symmetric' padding.  The arithmetic (including the `Range * A - B` precedence shared by
+# speechpy and processing.rs:244-247) is literal.
+
+
+def derivative_extraction(feat, delta_windows=2, dtype=F32):
+    """processing.rs:222-254: edge-pad along the FEATURE axis, sum_r (r * F[:, c+r] - F[:, c-r]) / (2 sum r^2)."""
+    f = np.asarray(feat, dtype)
+    cols = f.shape[1]
+    dw = int(delta_windows)
+    if dw < 1:
+        raise ValueError("delta_windows must be >= 1 (division by zero scale in the reference)")
+    F = np.pad(f, ((0, 0), (dw, dw)), mode="edge")
+    dif = np.zeros_like(f)
+    scale = dtype(0.0)
+    for i in range(dw):
+        r = i + 1
+        dif = dif + (F[:, dw + r:dw + r + cols] * dtype(r) - F[:, dw - r:dw - r + cols])
+        scale = scale + dtype(2.0) * dtype(r) ** 2
+    return (dif / scale).astype(dtype)
+
+
+def extract_derivative_feature(feat, dtype=F32):
+    """feature.rs:253-269: [T, C] -> [T, C, 3] = (static, delta, delta-delta), DeltaWindows = 2."""
+    f = np.asarray(feat, dtype)
+    d1 = derivative_extraction(f, 2, dtype)
+    d2 = derivative_extraction(d1, 2, dtype)
+    return np.stack([f, d1, d2], axis=2)
+
+
+def cmvnw(vec, win_size=301, variance_normalization=False, dtype=F32):
+    """processing.rs:315-371: sliding-window CMVN, symmetric padding along time, eps = 2^-30, ddof 0."""
+    x = np.asarray(vec, dtype)
+    if win_size % 2 != 1:
+        raise ValueError("Windows size must be odd!")
+    rows = x.shape[0]
+    p = (win_size - 1) // 2
+    xp = np.pad(x, ((p, p), (0, 0)), mode="symmetric")
+    cs = np.concatenate([np.zeros((1, x.shape[1]), np.float64), np.cumsum(xp.astype(np.float64), axis=0)])
+    mean = ((cs[win_size:win_size + rows] - cs[:rows]) / win_size).astype(dtype)
+    y = (x - mean).astype(dtype)
+    if not variance_normalization:
+        return y
+    yp = np.pad(y, ((p, p), (0, 0)), mode="symmetric").astype(np.float64)
+    c1 = np.concatenate([np.zeros((1, x.shape[1])), np.cumsum(yp, axis=0)])
+    c2 = np.concatenate([np.zeros((1, x.shape[1])), np.cumsum(yp * yp, axis=0)])
+    m = (c1[win_size:win_size + rows] - c1[:rows]) / win_size
+    v = np.maximum((c2[win_size:win_size + rows] - c2[:rows]) / win_size - m * m, 0.0)
+    return (y / (np.sqrt(v).astype(dtype) + dtype(CMVN_EPS))).astype(dtype)
+
+
+def cmvnw_direct(vec, win_size=301, variance_normalization=False, dtype=F32):
+    """the same function written exactly like the reference loops (O(T * win)); used to pin the
+    prefix-sum version above on small inputs"""
+    x = np.asarray(vec, dtype)
+    rows = x.shape[0]
+    p = (win_size - 1) // 2
+    xp = np.pad(x, ((p, p), (0, 0)), mode="symmetric")
+    y = np.stack([x[i] - xp[i:i + win_size].mean(axis=0, dtype=dtype) for i in range(rows)]).astype(dtype)
+    if not variance_normalization:
+        return y
+    yp = np.pad(y, ((p, p), (0, 0)), mode="symmetric")
+    return np.stack([y[i] / (yp[i:i + win_size].std(axis=0, dtype=dtype) + dtype(CMVN_EPS)) for i in range(rows)]).astype(dtype)

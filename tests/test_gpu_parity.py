@@ -351,3 +351,30 @@ def test_multi_device_plan_matches_single_device():
     a = sb.functions.stft2(y, sb.SpeechConfig(**CONFIGS["c4"], devices=[0]))
     b = sb.functions.stft2(y, sb.SpeechConfig(**CONFIGS["c4"], devices=list(range(n))))
     np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------ "next" rows: deltas, cmvnw
+
+
+def test_derivative_features_bit_exact():
+    rng = np.random.default_rng(11)
+    for shape in [(97, 13), (1, 40), (359, 5), (1000, 1), (64, 3)]:
+        f = rng.standard_normal(shape).astype(np.float32)
+        for dw in (1, 2, 3):
+            np.testing.assert_array_equal(sb.processing.derivative_extraction(f, dw), o.derivative_extraction(f, dw))
+        np.testing.assert_array_equal(sb.feature.extract_derivative_feature(f), o.extract_derivative_feature(f))
+    with pytest.raises(sb.SpeechsauceError):
+        sb.processing.derivative_extraction(np.zeros((4, 4), np.float32), 0)
+
+
+def test_cmvnw_matches_oracle():
+    rng = np.random.default_rng(12)
+    for rows, cols, win in [(1000, 13, 301), (50, 13, 301), (97, 40, 51), (20000, 13, 301), (7, 3, 1), (300, 1, 299)]:
+        x = (rng.standard_normal((rows, cols)) * 3 + 5).astype(np.float32)
+        for vn in (False, True):
+            got = sb.processing.cmvnw(x, win, vn)
+            np.testing.assert_allclose(got, o.cmvnw(x, win, vn), atol=2e-5, rtol=2e-5)
+            if rows <= 1000:
+                np.testing.assert_allclose(got, o.cmvnw_direct(x, win, vn), atol=5e-5, rtol=5e-5)
+    with pytest.raises(sb.SpeechsauceError, match="odd"):
+        sb.processing.cmvnw(np.zeros((10, 3), np.float32), 300, False)   # processing.rs:327

@@ -195,3 +195,22 @@ def test_golden_fixtures_match_oracle():
             np.testing.assert_allclose(np.stack([o.mfe(c, cfg)[0] for c in x]), z["mfe"], rtol=2e-6)
         else:
             np.testing.assert_allclose(o.mel_spectrogram2(x, cfg), z["mel"], rtol=1e-5, atol=1e-12)
+
+
+def test_next_rows_deltas_and_cmvnw():
+    """closed forms for the delta features and the sliding-window CMVN"""
+    f = np.arange(12, dtype=np.float32).reshape(2, 6) ** 2
+    d = o.derivative_extraction(f, 2)
+    F = np.pad(f, ((0, 0), (2, 2)), mode="edge")
+    want = ((F[:, 3:9] * 1 - F[:, 1:7]) + (F[:, 4:10] * 2 - F[:, 0:6])) / 10.0   # Range * A - B precedence
+    np.testing.assert_allclose(d, want, rtol=1e-6)
+    cube = o.extract_derivative_feature(f)
+    assert cube.shape == (2, 6, 3)
+    np.testing.assert_array_equal(cube[:, :, 0], f)
+    np.testing.assert_array_equal(cube[:, :, 2], o.derivative_extraction(cube[:, :, 1], 2))
+    x = o.synth_signal(400, 5, 8) * 4 + 1
+    for vn in (False, True):
+        np.testing.assert_allclose(o.cmvnw(x, 301, vn), o.cmvnw_direct(x, 301, vn), atol=2e-5)
+    np.testing.assert_allclose(o.cmvnw(np.full((40, 3), 2.5, np.float32), 11, False), 0, atol=1e-6)
+    with pytest.raises(ValueError):
+        o.cmvnw(x, 300, False)
