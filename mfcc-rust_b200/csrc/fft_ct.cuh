@@ -58,8 +58,35 @@ constexpr double cos2pi(long long m, long long n) {
   return neg ? -v : v;
 }
 
+// ---- packed complex arithmetic --------------------------------------------------------------
+// sm_100 executes two FP32 operations per lane in one instruction on a 64-bit register pair
+// (FADD2 / FMUL2 / FFMA2; PTX add/mul/fma.rn.f32x2), with per-operand swap (.LO_HI), broadcast and
+// sign-pattern modifiers that ptxas folds in.  A complex number is exactly such a pair, so every
+// butterfly below is written on whole float2 values: a complex add is one instruction, a twiddled
+// radix-2 butterfly is three.  Each half is an ordinary IEEE fused multiply-add / add, so results
+// are bit-identical to the scalar formulation.
+__device__ __forceinline__ float2 cneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, cneg(b)); }
+// a - i b and a + i b
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }
+__device__ __forceinline__ float2 cadd_pi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }
+// a + (c - i s) b
+__device__ __forceinline__ float2 cfma_tw(float c, float s, float2 b, float2 a) {
+  // the sign pattern sits on the data operand so that c and s both stay broadcast immediates
+  const float2 t = __ffma2_rn(make_float2(c, c), b, a);
+  return __ffma2_rn(make_float2(s, s), make_float2(b.y, -b.x), t);
+}
+// (c - i s) v
+__device__ __forceinline__ float2 cmul_tw(float c, float s, float2 v) {
+  const float2 r = __fmul2_rn(make_float2(s, s), make_float2(v.y, -v.x));
+  return __ffma2_rn(make_float2(c, c), v, r);
+}
+// a b for two run-time complex numbers
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  // b.x a + b.y (i a): the broadcast operands carry no sign, the swap / sign pattern sits on the pair a
+  const float2 r = __fmul2_rn(make_float2(b.x, b.x), a);
+  return __ffma2_rn(make_float2(b.y, b.y), make_float2(-a.y, a.x), r);
 }
 
 // radix-2 DIT butterfly with w = e^{-2 pi i M / N}: a' = a + w b, b' = a - w b = 2a - a'
@@ -68,28 +95,24 @@ __device__ __forceinline__ void bfly2(float2& a, float2& b) {
   constexpr int m = ((M % N) + N) % N;
   if constexpr (m == 0) {
     const float2 t = a;
-    a = make_float2(t.x + b.x, t.y + b.y);
-    b = make_float2(t.x - b.x, t.y - b.y);
+    a = cadd(t, b);
+    b = csub(t, b);
   } else if constexpr (4 * m == N) {  // w = -i : w b = (b.y, -b.x)
     const float2 t = a, s = b;
-    a = make_float2(t.x + s.y, t.y - s.x);
-    b = make_float2(t.x - s.y, t.y + s.x);
+    a = cadd_mi(t, s);
+    b = cadd_pi(t, s);
   } else if constexpr (2 * m == N) {  // w = -1
     const float2 t = a;
-    a = make_float2(t.x - b.x, t.y - b.y);
-    b = make_float2(t.x + b.x, t.y + b.y);
+    a = csub(t, b);
+    b = cadd(t, b);
   } else if constexpr (4 * m == 3 * N) {  // w = +i : w b = (-b.y, b.x)
     const float2 t = a, s = b;
-    a = make_float2(t.x - s.y, t.y + s.x);
-    b = make_float2(t.x + s.y, t.y - s.x);
+    a = cadd_pi(t, s);
+    b = cadd_mi(t, s);
   } else {
     constexpr float c = (float)cos2pi(m, N), s = (float)sin2pi(m, N);  // w = c - i s
-    float2 t;
-    t.x = fmaf(c, b.x, a.x);
-    t.x = fmaf(s, b.y, t.x);
-    t.y = fmaf(c, b.y, a.y);
-    t.y = fmaf(-s, b.x, t.y);
-    b = make_float2(fmaf(2.0f, a.x, -t.x), fmaf(2.0f, a.y, -t.y));
+    const float2 t = cfma_tw(c, s, b, a);
+    b = __ffma2_rn(make_float2(2.0f, 2.0f), a, cneg(t));
     a = t;
   }
 }
@@ -104,25 +127,25 @@ __device__ __forceinline__ float2 twmul(float2 v) {
   else if constexpr (4 * m == 3 * N) return make_float2(-v.y, v.x);
   else {
     constexpr float c = (float)cos2pi(m, N), s = (float)sin2pi(m, N);
-    return make_float2(fmaf(c, v.x, s * v.y), fmaf(c, v.y, -s * v.x));
+    return cmul_tw(c, s, v);
   }
 }
 
-// 5-point DFT, y_k = sum_n x_n e^{-2 pi i nk/5} (36 FP32 instructions)
+// 5-point DFT, y_k = sum_n x_n e^{-2 pi i nk/5} (18 packed FP32 instructions)
 __device__ __forceinline__ void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
   constexpr float c1 = (float)cos2pi(1, 5), c2 = (float)cos2pi(2, 5);
   constexpr float s1 = (float)sin2pi(1, 5), s2 = (float)sin2pi(2, 5);
-  const float2 t1 = make_float2(x1.x + x4.x, x1.y + x4.y), t2 = make_float2(x2.x + x3.x, x2.y + x3.y);
-  const float2 t3 = make_float2(x1.x - x4.x, x1.y - x4.y), t4 = make_float2(x2.x - x3.x, x2.y - x3.y);
-  const float2 m1 = make_float2(fmaf(c2, t2.x, fmaf(c1, t1.x, x0.x)), fmaf(c2, t2.y, fmaf(c1, t1.y, x0.y)));
-  const float2 m2 = make_float2(fmaf(c1, t2.x, fmaf(c2, t1.x, x0.x)), fmaf(c1, t2.y, fmaf(c2, t1.y, x0.y)));
-  const float2 u1 = make_float2(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y));
-  const float2 u2 = make_float2(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y));
-  x0 = make_float2(x0.x + (t1.x + t2.x), x0.y + (t1.y + t2.y));
-  x1 = make_float2(m1.x + u1.y, m1.y - u1.x);  // m1 - i u1
-  x4 = make_float2(m1.x - u1.y, m1.y + u1.x);
-  x2 = make_float2(m2.x + u2.y, m2.y - u2.x);
-  x3 = make_float2(m2.x - u2.y, m2.y + u2.x);
+  const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3);
+  const float2 t3 = csub(x1, x4), t4 = csub(x2, x3);
+  const float2 m1 = __ffma2_rn(make_float2(c2, c2), t2, __ffma2_rn(make_float2(c1, c1), t1, x0));
+  const float2 m2 = __ffma2_rn(make_float2(c1, c1), t2, __ffma2_rn(make_float2(c2, c2), t1, x0));
+  const float2 u1 = __ffma2_rn(make_float2(s2, s2), t4, __fmul2_rn(make_float2(s1, s1), t3));
+  const float2 u2 = __ffma2_rn(make_float2(-s1, -s1), t4, __fmul2_rn(make_float2(s2, s2), t3));
+  x0 = cadd(x0, cadd(t1, t2));
+  x1 = cadd_mi(m1, u1);  // m1 - i u1
+  x4 = cadd_pi(m1, u1);
+  x2 = cadd_mi(m2, u2);
+  x3 = cadd_pi(m2, u2);
 }
 
 // One Stockham stage on a register array: N points, radix R (2 or 5), sub-length NS.

@@ -80,6 +80,7 @@ struct DeviceCtx {
   DevTables tab;
   Fast512Tables* fast512 = nullptr;
   Fast512bTables* fast512b = nullptr;
+  Fast512cTables* fast512c = nullptr;
   Stft400Tables* stft400 = nullptr;
   Stft2048Tables* stft2048 = nullptr;
   Lane lanes[kLanes];
@@ -99,6 +100,7 @@ struct ss_plan {
   std::vector<ss::DeviceCtx> devs;
   bool fast512 = false;
   bool fast512b = false;
+  bool fast512c = false;
   bool stft400 = false;
   bool stft2048 = false;
 };
@@ -150,6 +152,10 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
     int e = fast512b_build_tables(pl->d, pl->mb, &dc->fast512b);
     if (e) return cuda_fail((cudaError_t)e, "fast512b_build_tables");
   }
+  if (pl->fast512c) {
+    int e = fast512c_build_tables(pl->d, pl->mb, &dc->fast512c);
+    if (e) return cuda_fail((cudaError_t)e, "fast512c_build_tables");
+  }
   if (pl->stft400) {
     int e = stft400_build_tables(pl->d, pl->mb, pl->window, &dc->stft400);
     if (e) return cuda_fail((cudaError_t)e, "stft400_build_tables");
@@ -197,11 +203,15 @@ static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const f
   p.tab = dc->tab;
   bool cmvn_done = false;
   int e;
-  const bool use_fast = (pl->fast512 || pl->fast512b) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  // SS_FAST512_GEN1=1 selects the first-generation kernel (8 lanes x 32 points) for A/B measurements
-  static const bool gen1 = getenv("SS_FAST512_GEN1") != nullptr;
+  const bool use_fast = (pl->fast512 || pl->fast512b || pl->fast512c) &&
+                        !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  // SS_FAST512_GEN=1|2 selects an older generation of the n_fft = 512 kernel for A/B measurements
+  // (1: 8 lanes x 32 points, CUDA-core epilogue; 2: 16 lanes x 16 points, CUDA-core epilogue;
+  // default 3: 16 lanes x 16 points, tensor-core mel + DCT)
+  static const int gen = getenv("SS_FAST512_GEN") ? atoi(getenv("SS_FAST512_GEN")) : 3;
   if (use_fast) {
-    if (pl->fast512b && !(gen1 && pl->fast512)) e = launch_fast512b(p, dc->fast512b, dc->sm_count, stream);
+    if (pl->fast512c && (gen >= 3 || !(pl->fast512 || pl->fast512b))) e = launch_fast512c(p, dc->fast512c, dc->sm_count, stream);
+    else if (pl->fast512b && (gen == 2 || !pl->fast512)) e = launch_fast512b(p, dc->fast512b, dc->sm_count, stream);
     else e = launch_fast512(p, dc->fast512, dc->sm_count, stream);
     cmvn_done = true;  // the fast path normalises in-kernel or enqueues its own cmvn pass
     if (e == -1000) {  // the fast path declined this shape; fall through to the generic kernel
@@ -446,6 +456,7 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   if (pl->d.stft_ok) pl->analysis_mem.assign((size_t)(pl->d.W - pl->d.H), 0.f);  // config.rs:162
   pl->fast512 = pl->fft_ok && fast512_supported(pl->d, pl->mb);
   pl->fast512b = pl->fft_ok && fast512b_supported(pl->d, pl->mb);
+  pl->fast512c = pl->fft_ok && fast512c_supported(pl->d, pl->mb);
   pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
   pl->stft2048 = pl->fft_ok && stft2048_supported(pl->d, pl->mb);
   std::vector<int> devs;
@@ -498,6 +509,7 @@ void ss_plan_destroy(ss_plan* pl) {
     dc.dev_scratch.release();
     if (dc.fast512) fast512_free_tables(dc.fast512);
     if (dc.fast512b) fast512b_free_tables(dc.fast512b);
+    if (dc.fast512c) fast512c_free_tables(dc.fast512c);
     if (dc.stft400) stft400_free_tables(dc.stft400);
     if (dc.stft2048) stft2048_free_tables(dc.stft2048);
   }
@@ -518,7 +530,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->num_cepstral = d.nc;
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
-  info->fast_path = (pl->fast512 || pl->fast512b) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  info->fast_path = (pl->fast512 || pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
   info->fast_stft = (pl->stft400 || pl->stft2048) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }

@@ -125,6 +125,13 @@ int fast512b_build_tables(const Derived& d, const MelBank& mb, Fast512bTables** 
 void fast512b_free_tables(Fast512bTables* t);
 int launch_fast512b(const FrameParams& p, const Fast512bTables* t, int sm_count, void* stream);
 
+// third-generation n_fft == 512 kernel: FFT as in the second, mel + DCT on mma.sync TF32x3 (ss_kernels_fast512c.cu)
+bool fast512c_supported(const Derived& d, const MelBank& mb);
+struct Fast512cTables;
+int fast512c_build_tables(const Derived& d, const MelBank& mb, Fast512cTables** out);
+void fast512c_free_tables(Fast512cTables* t);
+int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count, void* stream);
+
 // fft_points == 400 register-FFT path for mel_spectrogram (ss_kernels_stft400.cu)
 bool stft400_supported(const Derived& d, const MelBank& mb);
 struct Stft400Tables;

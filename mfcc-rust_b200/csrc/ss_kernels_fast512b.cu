@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_fast512b(const FastArgs a) {
         constexpr int k1 = 2 * decltype(kk)::value;
         const float4 w = twrow[k1 / 2];
         float2 y0 = v[k1], y1 = v[k1 + 1];
-        if constexpr (k1 > 0) y0 = make_float2(y0.x * w.x - y0.y * w.y, y0.x * w.y + y0.y * w.x);
-        y1 = make_float2(y1.x * w.z - y1.y * w.w, y1.x * w.w + y1.y * w.z);
+        if constexpr (k1 > 0) y0 = ssfft::cmulf(y0, make_float2(w.x, w.y));
+        y1 = ssfft::cmulf(y1, make_float2(w.z, w.w));
         xch[k1 * kXs + u] = y0;
         xch[(k1 + 1) * kXs + u] = y1;
       });
@@ -187,12 +187,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_fast512b(const FastArgs a) {
         zb.y = __shfl_sync(0xffffffffu, g[15 - k2].y, partner);
         if (isz) zb = g[(16 - k2) & 15];
         const float2 za = g[k2];
-        const float ex = za.x + zb.x, ey = za.y - zb.y;
-        const float2 o = ssfft::twmul<32, k2>(make_float2(za.y + zb.y, zb.x - za.x));  // O' * W32^{k2}
-        const float tx = o.x * wu.x - o.y * wu.y, ty = o.x * wu.y + o.y * wu.x;         // ... * W512^u
-        const float ax = ex + tx, ay = ey + ty, bx = ex - tx, by = ey - ty;
-        const float ma = fast_sqrt(fmaf(ax, ax, ay * ay));  // 2 n_fft |X[k]| (scale folded into the weights)
-        const float mb = fast_sqrt(fmaf(bx, bx, by * by));  // 2 n_fft |X[256-k]|
+        const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));                         // E' = za + conj zb
+        const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));   // O' = (za - conj zb) / i
+        const float2 tt = ssfft::cmulf(ssfft::twmul<32, k2>(od), wu);                      // O' W32^{k2} W512^u
+        const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
+        const float ma = fast_sqrt(fmaf(xa.x, xa.x, xa.y * xa.y));  // 2 n_fft |X[k]| (scale folded into the weights)
+        const float mb = fast_sqrt(fmaf(xb.x, xb.x, xb.y * xb.y));  // 2 n_fft |X[256-k]|
         pA[16 * k2] = ma;
         esum += ma + mb;
       });

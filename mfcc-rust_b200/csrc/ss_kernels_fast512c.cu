@@ -1,0 +1,583 @@
+// Fused speechpy-framing feature kernel for n_fft = 512, third generation (c1 / c2 / c5):
+//   framing -> zero-pad -> real FFT -> |X|/N -> frame energy -> mel filterbank -> ln -> DCT-II
+//   (+ SSC, + per-clip CMVN) in one pass; every intermediate in registers / shared memory.
+// Replaces feature::{mfe, lmfe, mfcc} (feature.rs:99-245) + processing::{stack_frames,
+// power_spectrum, cmvn} (processing.rs:65-181,265-300) for this FFT size.
+//
+// FFT stage as in the second generation (ss_kernels_fast512b.cu): 16 lanes x 16 points per frame,
+// 256 = 16 x 16 four-step complex FFT in registers, mirror bin by warp shuffle, two frames per warp.
+// New here: everything after the magnitudes runs on the tensor cores with warp-level
+// mma.sync.m16n8k8 TF32, split 3-way (A_hi B_hi + A_lo B_hi + A_hi B_lo, ~2^-21 relative) so the
+// f32 tolerances hold:
+//   * a warp collects |X| of 8 consecutive frames (4 FFT pairs) in a private [8][136] tile and
+//     multiplies it by the banded filterbank, 8 bins x 8 filters per MMA, visiting only the blocks
+//     the band touches (28 of 85 for the 40-filter bank).  The profile of the second generation had
+//     the per-pair CUDA-core mel program at 23 % and the DCT at 11 % of all issued instructions;
+//   * the accumulator fragment of the mel product (frame g, filters 2t, 2t+1) *is* the A fragment of
+//     the DCT product once the contraction index is permuted (the DCT matrix fragments are
+//     permuted on the host instead), so ln -> DCT needs no data movement at all;
+//   * rows 8..15 of the MMA tile carry P[k] * R[k] when the spectral subband centroids are
+//     requested, so the SSC numerator costs no extra MMA;
+//   * the cepstra stay in the accumulator fragments through the c0 / scale step and the per-clip
+//     CMVN (column statistics reduced by shuffles, merged across warps with Chan's formula through
+//     96 floats of shared memory, one barrier per clip), so no [T][nc] stash exists any more.
+// Fragment tables are read through the L1 (one copy per SM, shared by the resident CTAs).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "fft_ct.cuh"
+#include "ss_internal.h"
+
+namespace ss {
+
+namespace {
+
+using ssfft::sfor;
+
+#ifndef SS_F512C_WARPS
+#define SS_F512C_WARPS 8
+#endif
+#ifndef SS_F512C_CTAS
+#define SS_F512C_CTAS 3
+#endif
+constexpr int kWarps = SS_F512C_WARPS, kThreads = kWarps * 32;
+constexpr int kCtasPerSm = SS_F512C_CTAS;
+constexpr int kXs = 18;                       // transpose row stride in float2 (144 B: conflict-free LDS.128)
+constexpr int kXchFrame = 16 * kXs;           // 288 float2 per frame
+constexpr int kXchFloats = 2 * kXchFrame * 2; // 1152 floats per warp (2 frames)
+constexpr int kTileRows = 8;                  // frames per MMA tile
+constexpr int kPs = 136;                      // P row stride: 17 k-steps of 8 bins; 136 % 32 == 8 -> conflict-free LDS.64 A fragments
+constexpr int kKs = kPs / 8;                  // 17 k-steps
+constexpr int kKsTab = kKs + 1;               // + one zero block: bands are padded to an even number of k-steps
+constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows;  // + 8 frame energies
+static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
+constexpr int kTwRow = 36;                    // floats per lane row of the W256 table (16 float2 + pad)
+constexpr int kTabTw = 16 * kTwRow;           // CTA-shared twiddle table
+constexpr int kNtMax = 8, kNcMax = 16;        // nf <= 64, nc <= 16
+
+__device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// ln x = log2 x * ln 2 with the MUFU approximation (as __logf, minus its denormal-input fix-up:
+// the arguments here are zero_handling()-ed mel energies)
+__device__ __forceinline__ float fast_ln(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.693147180559945309f;
+}
+// x = hi + lo with hi = x truncated to TF32 (10 mantissa bits); lo is exact in f32 (|lo| < 2^-10 |x|)
+// and the tensor core drops its low 13 mantissa bits, i.e. 2^-20 |x| in the worst case
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// D += A(16x8, row) * B(8x8, col), TF32 inputs, f32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+struct FastArgsC {
+  FrameParams p;
+  const float* tw;         // [16][kTwRow] W256^{u k1}
+  const float4* mel_frag;  // [NT][kKs][32] = b0_hi, b1_hi, b0_lo, b1_lo
+  const float4* dct_frag;  // [NT][2][32]
+  int64_t n_items;         // clips * chunks_per_clip; one item per warp at a time
+  int chunks_per_clip;
+  int fpi;                 // frames per item (a multiple of the tile height, or >= T)
+  int fuse_cmvn;           // 0 none, 1 mean, 2 mean+var: one warp takes the whole clip and normalises it in place
+  int vec2;                // every frame start is 8-byte aligned
+  int nf_even;             // nf is even: float2 stores of the mel rows
+  int ks_lo[kNtMax], ks_n2[kNtMax];  // first k-step (8 bins each) and number of k-step pairs of the band, per n-tile of 8 filters
+};
+
+// JMAX: column groups (32 samples each) that can be non-zero; EXACT: JMAX == ceil(L / 32), so only
+// the last group needs a bounds check; SSC: also the centroid numerator; NT: n-tiles of 8 filters
+template <int JMAX, bool EXACT, bool SSC, int NT>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_fast512c(const FastArgsC a) {
+  extern __shared__ __align__(16) float smem[];
+  float* tw_s = smem;
+  float* warp_s = smem + kTabTw + (threadIdx.x >> 5) * kWarpFloats;
+  const FrameParams& p = a.p;
+  for (int i = threadIdx.x; i < kTabTw; i += kThreads) tw_s[i] = __ldg(a.tw + i);
+  // the tile's pad columns (bins 132..135) are never written again and must be finite
+  for (int i = (threadIdx.x & 31); i < kTileRows * kPs + kTileRows; i += 32) warp_s[kXchFloats + i] = 0.0f;
+  __syncthreads();  // the only block-wide barrier: from here on the warps are independent
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fi = lane >> 4, u = lane & 15;   // FFT stage: frame of the pair, lane within the frame
+  const int g = lane >> 2, t = lane & 3;     // MMA stage: fragment row group, thread in group
+  const bool isz = (u == 0);
+  const int partner = (lane & 16) | ((16 - u) & 15);
+  const int nf = p.nf, nc = p.nc, L = p.L;
+  const int T = (int)p.T;
+  const float mscale = 0.5f * p.mag_scale;  // the 1/2 of E, O and 1/n_fft (processing.rs:180)
+
+  const float4* twrow = reinterpret_cast<const float4*>(tw_s + u * kTwRow);
+  // W512^{u + 16 k2} = W512^u * W32^{k2}: one per-lane register pair times a compile-time constant
+  float2 wu;
+  sincospif(-(float)u / 256.0f, &wu.y, &wu.x);
+
+  float2* xch = reinterpret_cast<float2*>(warp_s) + fi * kXchFrame;
+  float* Pt = warp_s + kXchFloats;            // [kTileRows][kPs]
+  float* e_s = Pt + kTileRows * kPs;          // [kTileRows] frame energies
+  // tile frame j <-> tile row r: the two frames of a pair sit two rows apart (bank-disjoint stores)
+  const int j_of_g = 4 * (g >> 2) + 2 * (g & 1) + ((g >> 1) & 1);
+  // does this lane's last column group (j = JMAX - 1) lie inside the frame?
+  const bool last0 = 2 * u + 32 * (JMAX - 1) < L, last1 = 2 * u + 32 * (JMAX - 1) + 1 < L;
+  for (int64_t item = (int64_t)blockIdx.x * kWarps + warp; item < a.n_items; item += (int64_t)gridDim.x * kWarps) {
+    const int64_t clip = item / a.chunks_per_clip;
+    const int chunk = (int)(item - clip * a.chunks_per_clip);
+    const float* rowp = p.pcm + clip * p.row_stride + 2 * u;
+    const int64_t obase = clip * T;  // first output row of the clip
+    const int fbeg = chunk * a.fpi;
+    const int fend = min(T, fbeg + a.fpi);
+
+#pragma unroll 1
+    for (int tile_f0 = fbeg; tile_f0 < fend; tile_f0 += kTileRows) {
+      const int npairs = min(kTileRows / 2, (fend - tile_f0 + 1) >> 1);
+#pragma unroll 1
+      for (int pr = 0; pr < npairs; ++pr) {
+        const int fr = tile_f0 + 2 * pr + fi;
+        const bool valid = fr < fend;
+        const int row = 4 * (pr >> 1) + (pr & 1) + 2 * fi;
+
+        // ---- framing: v[j] = x[2m] + i x[2m+1], m = u + 16 j; zero beyond L (processing.rs:147-156).
+        // An out-of-range frame of the last pair re-reads frame T-1 (in bounds); it is never stored.
+        float2 v[16];
+        {
+          const float* px = rowp + (int64_t)(valid ? fr : T - 1) * p.S;
+          // pull the samples of the next pair into the L1 while this one is transformed (one 128-byte
+          // line per lane; the 60 % that overlaps the current pair is already there)
+          if (tile_f0 + 2 * pr + 3 < fend) {
+            const float* nx = rowp - 2 * u + (int64_t)(tile_f0 + 2 * pr + 2) * p.S + 32 * lane;
+            if (32 * lane < p.S + L) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+          }
+          sfor<0, 16>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            if constexpr (j >= JMAX) {
+              v[j] = make_float2(0.0f, 0.0f);
+            } else if constexpr (!EXACT) {
+              v[j].x = (2 * u + 32 * j < L) ? __ldg(px + 32 * j) : 0.0f;
+              v[j].y = (2 * u + 32 * j + 1 < L) ? __ldg(px + 32 * j + 1) : 0.0f;
+            } else if constexpr (j == JMAX - 1) {
+              v[j].x = last0 ? __ldg(px + 32 * j) : 0.0f;
+              v[j].y = last1 ? __ldg(px + 32 * j + 1) : 0.0f;
+            } else {
+              if (a.vec2) v[j] = __ldg(reinterpret_cast<const float2*>(px + 32 * j));
+              else v[j] = make_float2(__ldg(px + 32 * j), __ldg(px + 32 * j + 1));
+            }
+          });
+        }
+        // ---- stage 1: 16-point FFT over j
+        ssfft::fft_pow2<16, JMAX>(v);
+        // ---- twiddle W256^{u k1} and transpose
+        sfor<0, 8>([&](auto kk) {
+          constexpr int k1 = 2 * decltype(kk)::value;
+          const float4 w = twrow[k1 / 2];
+          float2 y0 = v[k1], y1 = v[k1 + 1];
+          if constexpr (k1 > 0) y0 = ssfft::cmulf(y0, make_float2(w.x, w.y));
+          y1 = ssfft::cmulf(y1, make_float2(w.z, w.w));
+          xch[k1 * kXs + u] = y0;
+          xch[(k1 + 1) * kXs + u] = y1;
+        });
+        __syncwarp();
+        float2 gg[16];
+        {
+          const float4* r4 = reinterpret_cast<const float4*>(xch + u * kXs);
+          sfor<0, 8>([&](auto tt) {
+            constexpr int i = decltype(tt)::value;
+            const float4 x = r4[i];
+            gg[2 * i] = make_float2(x.x, x.y);
+            gg[2 * i + 1] = make_float2(x.z, x.w);
+          });
+        }
+        __syncwarp();  // the transpose tile is rewritten by the next pair
+        // ---- stage 2: 16-point FFT over the lane index.  gg[k2] = Z[u + 16 k2]
+        ssfft::fft_pow2<16>(gg);
+
+        // ---- real-FFT split for k = u + 16 k2 <= 127 (k2 < 8): Z[256 - k] is gg[15 - k2] of lane
+        // 16 - u (lane 0: its own gg[16 - k2]).  Each pair yields |X[k]| and |X[256 - k]|; both go
+        // into the frame energy, only the bins a filter can reach (<= 128) into the tile.
+        float* Prow = Pt + row * kPs;
+        float* pA = Prow + u;
+        float esum = 0.f;
+        sfor<0, 8>([&](auto kk) {
+          constexpr int k2 = decltype(kk)::value;
+          float2 zb;
+          zb.x = __shfl_sync(0xffffffffu, gg[15 - k2].x, partner);
+          zb.y = __shfl_sync(0xffffffffu, gg[15 - k2].y, partner);
+          if (isz) zb = gg[(16 - k2) & 15];
+          const float2 za = gg[k2];
+          const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));                         // E' = za + conj zb
+          const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));   // O' = (za - conj zb) / i
+          const float2 tt = ssfft::cmulf(ssfft::twmul<32, k2>(od), wu);                      // O' W32^{k2} W512^u
+          const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
+          const float ma = fast_sqrt(fmaf(xa.x, xa.x, xa.y * xa.y));  // 2 n_fft |X[k]| (scale folded into the weights)
+          const float mb = fast_sqrt(fmaf(xb.x, xb.x, xb.y * xb.y));  // 2 n_fft |X[256-k]|
+          pA[16 * k2] = ma;
+          esum += ma + mb;
+        });
+        if (isz) {  // bin 128 (self-mirrored): X[128] = conj Z[128]; x2 to match the pairs
+          const float m = 2.0f * fast_sqrt(fmaf(gg[8].x, gg[8].x, gg[8].y * gg[8].y));
+          *reinterpret_cast<float4*>(Prow + 128) = make_float4(m, 0.f, 0.f, 0.f);
+          esum += m;
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+        if (isz) {
+          const float energy = zero_handling(mscale * esum);  // feature.rs:216-219
+          e_s[row] = energy;
+          if (p.energy && valid) p.energy[obase + fr] = energy;
+        }
+      }
+      __syncwarp();
+
+      // ---- mel filterbank on the tensor cores (feature.rs:229-230): [8 frames][136 bins] x banded
+      // [136][8 NT], one n-tile of 8 filters at a time over the k-steps its band touches.
+      // Contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1, so a lane's two A
+      // values are one 8-byte load.  Rows 8..15: P * R for the SSC numerator, else zero.
+      // Then zero_handling -> stores -> ln (feature.rs:216-230, 242-245) on the accumulator
+      // fragment: lane (g, t) holds filters 8 nt + 2t, + 1 of tile row g.
+      const int frg = tile_f0 + j_of_g;
+      const bool validr = frg < fend;
+      const int64_t orow = (obase + frg) * nf + 2 * t;
+      float* const mfe_p = p.mfe ? p.mfe + orow : nullptr;
+      float* const lmfe_p = p.lmfe ? p.lmfe + orow : nullptr;
+      float* const ssc_p = (SSC && p.ssc) ? p.ssc + orow : nullptr;
+      float lg[NT][2];
+      {
+        const float* prow = Pt + g * kPs + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float accB[4] = {0.f, 0.f, 0.f, 0.f}, accS[4] = {0.f, 0.f, 0.f, 0.f}, accT[4] = {0.f, 0.f, 0.f, 0.f};
+          const int k0 = a.ks_lo[nt];
+          const float* pp = prow + 8 * k0;
+          const float4* bp = a.mel_frag + (nt * kKsTab + k0) * 32 + lane;
+          float rb = SSC ? fmaf(p.ssc_step, (float)(8 * k0 + 2 * t), p.ssc_r0) : 0.f;
+          // two k-steps per iteration (the band is padded to an even count with zero-weight blocks;
+          // the tile columns those read are other rows' finite values)
+#pragma unroll 1
+          for (int n2 = a.ks_n2[nt]; n2 > 0; --n2) {
+            const float2 pv0 = *reinterpret_cast<const float2*>(pp);
+            const float2 pv1 = *reinterpret_cast<const float2*>(pp + 8);
+            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 32);
+            pp += 16;
+            bp += 64;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float2 pv = h ? pv1 : pv0;
+              const float4 b = h ? b1 : b0;
+              uint32_t ah[4], al[4];
+              split_tf32(pv.x, ah[0], al[0]);
+              split_tf32(pv.y, ah[2], al[2]);
+              if (SSC) {
+                split_tf32(pv.x * rb, ah[1], al[1]);
+                split_tf32(pv.y * (rb + p.ssc_step), ah[3], al[3]);
+                rb = fmaf(8.0f, p.ssc_step, rb);
+              } else {
+                ah[1] = ah[3] = al[1] = al[3] = 0u;
+              }
+              mma_tf32(accB, ah, b.x, b.y);  // hi x hi
+              mma_tf32(accS, al, b.x, b.y);  // lo x hi
+              mma_tf32(accT, ah, b.z, b.w);  // hi x lo
+            }
+          }
+          const float m0 = zero_handling(accB[0] + (accS[0] + accT[0]));
+          const float m1 = zero_handling(accB[1] + (accS[1] + accT[1]));
+          lg[nt][0] = fast_ln(m0);
+          lg[nt][1] = fast_ln(m1);
+          if (validr) {
+            float s0 = 0.f, s1 = 0.f;
+            if (SSC) {
+              s0 = __fdividef(accB[2] + (accS[2] + accT[2]), m0);
+              s1 = __fdividef(accB[3] + (accS[3] + accT[3]), m1);
+            }
+            if (a.nf_even && 8 * nt + 2 * t + 1 < nf) {
+              if (mfe_p) *reinterpret_cast<float2*>(mfe_p + 8 * nt) = make_float2(m0, m1);
+              if (lmfe_p) *reinterpret_cast<float2*>(lmfe_p + 8 * nt) = make_float2(lg[nt][0], lg[nt][1]);
+              if (SSC && ssc_p) *reinterpret_cast<float2*>(ssc_p + 8 * nt) = make_float2(s0, s1);
+            } else if (8 * nt + 2 * t < nf) {
+              const bool two = 8 * nt + 2 * t + 1 < nf;
+              if (mfe_p) { mfe_p[8 * nt] = m0; if (two) mfe_p[8 * nt + 1] = m1; }
+              if (lmfe_p) { lmfe_p[8 * nt] = lg[nt][0]; if (two) lmfe_p[8 * nt + 1] = lg[nt][1]; }
+              if (SSC && ssc_p) { ssc_p[8 * nt] = s0; if (two) ssc_p[8 * nt + 1] = s1; }
+            }
+          }
+        }
+      }
+
+      // ---- DCT-II on the tensor cores (feature.rs:120-123): the mel accumulator fragment is the A
+      // fragment of k-step nt (slot t <-> filter 8 nt + 2t, slot t + 4 <-> filter 8 nt + 2t + 1)
+      if (p.mfcc) {
+        float dB[2][4], dS[2][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 2; ++n2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { dB[n2][i] = 0.f; dS[n2][i] = 0.f; }
+        }
+        const float4* dt = a.dct_frag + lane;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t ah[4], al[4];
+          split_tf32(lg[nt][0], ah[0], al[0]);
+          split_tf32(lg[nt][1], ah[2], al[2]);
+          ah[1] = ah[3] = al[1] = al[3] = 0u;
+#pragma unroll
+          for (int n2 = 0; n2 < 2; ++n2) {
+            if (n2 == 0 || nc > 8) {
+              const float4 b = __ldg(dt + (nt * 2 + n2) * 32);
+              mma_tf32(dB[n2], ah, b.x, b.y);
+              mma_tf32(dS[n2], al, b.x, b.y);
+              mma_tf32(dS[n2], ah, b.z, b.w);
+            }
+          }
+        }
+        // scale (feature.rs:126-131) and c0 <- ln(energy) (feature.rs:137-146)
+        float cv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 8 * (k >> 1) + 2 * t + (k & 1);
+          float x = dB[k >> 1][k & 1] + dS[k >> 1][k & 1];
+          if (c == 0) {
+            if (p.dc_elim) x = fast_ln(e_s[g]);
+            else if (frg == 0) x *= p.scale_00;  // only element [0,0] gets the k=0 scale (feature.rs:128)
+          } else {
+            x *= p.scale_rest;
+          }
+          cv[k] = x;
+        }
+        if (validr) {  // with a fused CMVN these are normalised in place below
+          float* dst = p.mfcc + (obase + frg) * nc;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = 8 * (k >> 1) + 2 * t + (k & 1);
+            if (c < nc) dst[c] = cv[k];
+          }
+        }
+      }
+      __syncwarp();  // the tile and the energies are rewritten by the next tile's pairs
+    }
+
+    // ---- per-clip CMVN (processing.rs:265-300): the warp re-reads the [T][nc] block it has just
+    // written (L2-resident), lane = (row parity, column), eight rows in flight per lane: column mean
+    // and variance of the column (shifted by its first row: a one-sweep, cancellation-safe form of the
+    // reference's mean-subtract-then-std), then normalise in place.
+    if (a.fuse_cmvn) {
+      __syncwarp();
+      float* blk = p.mfcc + obase * nc;
+      const int c = lane & 15, r0 = lane >> 4;
+      const bool act = c < nc;
+      const float* col = blk + (act ? c : 0);
+      const float K = __ldcg(col);  // row 0 of the column
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int rb = r0; rb < T; rb += 16) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (rb + 2 * j < T) ? __ldcg(col + (rb + 2 * j) * nc) : K;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = x[j] - K;
+          s1 += d;
+          s2 = fmaf(d, d, s2);
+        }
+      }
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+      const float invT = 1.0f / (float)T;
+      const float mean = fmaf(s1, invT, K);
+      float inv = 1.0f;  // std with ddof 0, divide by (std + 2^-30) (processing.rs:283-292)
+      if (a.fuse_cmvn == 2) inv = 1.0f / (sqrtf(fmaxf(s2 - s1 * s1 * invT, 0.f) * invT) + kCmvnEps);
+      if (act) {
+#pragma unroll 1
+        for (int rb = r0; rb < T; rb += 16) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (rb + 2 * j < T) ? __ldcg(col + (rb + 2 * j) * nc) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (rb + 2 * j < T) blk[(rb + 2 * j) * nc + c] = (x[j] - mean) * inv;
+        }
+      }
+    }
+  }
+}
+
+// round-to-nearest (ties away) conversion f32 -> TF32, as cvt.rna.tf32.f32
+static float tf32_rna(float x) {
+  uint32_t b;
+  std::memcpy(&b, &x, 4);
+  b = (b + 0x1000u) & 0xffffe000u;  // the weights are finite and far from overflow
+  float r;
+  std::memcpy(&r, &b, 4);
+  return r;
+}
+
+struct FragTables {
+  int NT = 0;
+  int ks_lo[kNtMax] = {0}, ks_hi[kNtMax] = {0};
+  std::vector<float> mel, dct;  // [NT][kKsTab][32][4], [NT][2][32][4]
+};
+
+static bool build_frags(const Derived& d, const MelBank& mb, FragTables* ft) {
+  const int nf = d.nf;
+  if (mb.max_bin > 128) return false;  // only bins <= 128 are kept (always true for the reference's bank at n_fft 512)
+  if (nf > 8 * kNtMax || d.nc > kNcMax || nf < 1) return false;
+  const int NT = nf <= 40 ? 5 : 8;
+  ft->NT = NT;
+  const float mscale = 0.5f * (1.0f / (float)d.W);  // the kernel keeps 2 n_fft |X| in the tile
+  std::vector<float> dense((size_t)8 * NT * kPs, 0.f);  // [filter][bin]
+  for (int f = 0; f < nf; ++f)
+    for (int i = 0; i < mb.len[f]; ++i) dense[(size_t)f * kPs + mb.start[f] + i] = mb.w[mb.wofs[f] + i] * mscale;
+  ft->mel.assign((size_t)kKsTab * NT * 32 * 4, 0.f);
+  for (int nt = 0; nt < kNtMax; ++nt) { ft->ks_lo[nt] = kKs; ft->ks_hi[nt] = 0; }
+  for (int nt = 0; nt < NT; ++nt) {
+    for (int ks = 0; ks < kKs; ++ks) {
+      bool any = false;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        const float b0 = dense[(size_t)(8 * nt + g) * kPs + 8 * ks + 2 * t];
+        const float b1 = dense[(size_t)(8 * nt + g) * kPs + 8 * ks + 2 * t + 1];
+        float* o = &ft->mel[(((size_t)nt * kKsTab + ks) * 32 + lane) * 4];
+        o[0] = tf32_rna(b0);
+        o[1] = tf32_rna(b1);
+        o[2] = b0 - o[0];
+        o[3] = b1 - o[1];
+        any = any || b0 != 0.f || b1 != 0.f;
+      }
+      if (any) { ft->ks_lo[nt] = std::min(ft->ks_lo[nt], ks); ft->ks_hi[nt] = std::max(ft->ks_hi[nt], ks + 1); }
+    }
+    if (ft->ks_hi[nt] == 0) ft->ks_lo[nt] = 0;  // an n-tile of empty filters: no k-steps
+  }
+  std::vector<float> dct;
+  build_dct(d, &dct);  // [nc][nf]
+  ft->dct.assign((size_t)NT * 2 * 32 * 4, 0.f);
+  for (int nt = 0; nt < NT; ++nt)
+    for (int n2 = 0; n2 < 2; ++n2)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        const int c = 8 * n2 + g, f0 = 8 * nt + 2 * t;
+        const float b0 = (c < d.nc && f0 < nf) ? dct[(size_t)c * nf + f0] : 0.f;
+        const float b1 = (c < d.nc && f0 + 1 < nf) ? dct[(size_t)c * nf + f0 + 1] : 0.f;
+        float* o = &ft->dct[(((size_t)nt * 2 + n2) * 32 + lane) * 4];
+        o[0] = tf32_rna(b0);
+        o[1] = tf32_rna(b1);
+        o[2] = b0 - o[0];
+        o[3] = b1 - o[1];
+      }
+  return true;
+}
+
+}  // namespace
+
+struct Fast512cTables {
+  float* d_tab = nullptr;  // tw | mel fragments | dct fragments
+  size_t o_mel = 0, o_dct = 0;
+  int NT = 0;
+  int ks_lo[kNtMax] = {0}, ks_hi[kNtMax] = {0};
+};
+
+bool fast512c_supported(const Derived& d, const MelBank& mb) {
+  if (d.W != 512 || !d.speechpy_ok) return false;
+  FragTables ft;
+  return build_frags(d, mb, &ft);
+}
+
+int fast512c_build_tables(const Derived& d, const MelBank& mb, Fast512cTables** out) {
+  FragTables ft;
+  if (!build_frags(d, mb, &ft)) return (int)cudaErrorInvalidValue;
+  std::vector<float> h(kTabTw, 0.f);
+  const double pi = 3.14159265358979323846264338327950288;
+  for (int u = 0; u < 16; ++u)
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const double ang = -2.0 * pi * (double)(u * k1) / 256.0;
+      h[u * kTwRow + 2 * k1] = (float)std::cos(ang);
+      h[u * kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
+    }
+  Fast512cTables* t = new Fast512cTables;
+  t->NT = ft.NT;
+  for (int i = 0; i < kNtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_hi[i] = ft.ks_hi[i]; }
+  t->o_mel = h.size();
+  h.insert(h.end(), ft.mel.begin(), ft.mel.end());
+  t->o_dct = h.size();
+  h.insert(h.end(), ft.dct.begin(), ft.dct.end());
+  cudaError_t e = cudaMalloc(&t->d_tab, h.size() * sizeof(float));
+  if (e != cudaSuccess) { delete t; return (int)e; }
+  e = cudaMemcpy(t->d_tab, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(t->d_tab); delete t; return (int)e; }
+  *out = t;
+  return 0;
+}
+
+void fast512c_free_tables(Fast512cTables* t) {
+  if (!t) return;
+  if (t->d_tab) cudaFree(t->d_tab);
+  delete t;
+}
+
+// returns 0 (done, including any requested cmvn), -1000 (shape declined), -1001 (features
+// written, cmvn left to the caller) or a cudaError_t
+int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count, void* stream) {
+  if (p.N != 512 || p.L > 512 || p.T < 1 || p.T > (1LL << 31) - 64) return -1000;
+  FastArgsC a;
+  a.p = p;
+  a.tw = t->d_tab;
+  a.mel_frag = reinterpret_cast<const float4*>(t->d_tab + t->o_mel);
+  a.dct_frag = reinterpret_cast<const float4*>(t->d_tab + t->o_dct);
+  for (int i = 0; i < kNtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = (t->ks_hi[i] - t->ks_lo[i] + 1) / 2; }
+  const int64_t warps_resident = (int64_t)sm_count * kCtasPerSm * kWarps;
+  // a fused CMVN needs the whole clip in one warp; worth it while there are enough clips to fill the GPU
+  const bool fuse = p.mfcc && p.cmvn_mode && p.T <= 4096 && p.n_rows >= warps_resident;
+  a.fuse_cmvn = fuse ? p.cmvn_mode : 0;
+  if (fuse) {
+    a.fpi = (int)p.T;
+    a.chunks_per_clip = 1;
+  } else {
+    // chunks of whole tiles, small enough that every resident warp gets a few items
+    int64_t fpi = 32 * kTileRows;
+    auto items = [&](int64_t f) { return p.n_rows * ((p.T + f - 1) / f); };
+    while (fpi > kTileRows && items(fpi) < 4 * warps_resident) fpi /= 2;
+    a.fpi = (int)fpi;
+    a.chunks_per_clip = (int)((p.T + fpi - 1) / fpi);
+  }
+  a.n_items = p.n_rows * a.chunks_per_clip;
+  a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
+  auto al8 = [](const float* q) { return reinterpret_cast<uintptr_t>(q) % 8 == 0; };
+  a.nf_even = (p.nf % 2 == 0) && al8(p.mfe) && al8(p.lmfe) && al8(p.ssc);
+  const bool ssc = p.ssc != nullptr;
+  const size_t smem = (size_t)(kTabTw + kWarps * kWarpFloats) * sizeof(float);
+  const int64_t grid = std::min<int64_t>((a.n_items + kWarps - 1) / kWarps, (int64_t)sm_count * kCtasPerSm);
+  if (grid <= 0) return 0;
+  const int jn = (p.L + 31) / 32;
+  cudaError_t e;
+#define SS_LAUNCH_FASTC(J, X, C, N)                                                                            \
+  do {                                                                                                         \
+    e = cudaFuncSetAttribute(k_fast512c<J, X, C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e != cudaSuccess) return (int)e;                                                                       \
+    k_fast512c<J, X, C, N><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);                       \
+  } while (0)
+#define SS_LAUNCH_FASTC_N(J, X, C)                                          \
+  do {                                                                      \
+    if (t->NT == 5) SS_LAUNCH_FASTC(J, X, C, 5); else SS_LAUNCH_FASTC(J, X, C, 8); \
+  } while (0)
+  if (jn == 10) { if (ssc) SS_LAUNCH_FASTC_N(10, true, true); else SS_LAUNCH_FASTC_N(10, true, false); }        // L = 289..320
+  else if (jn == 13) { if (ssc) SS_LAUNCH_FASTC_N(13, true, true); else SS_LAUNCH_FASTC_N(13, true, false); }   // L = 385..416
+  else { if (ssc) SS_LAUNCH_FASTC_N(16, false, true); else SS_LAUNCH_FASTC_N(16, false, false); }
+#undef SS_LAUNCH_FASTC_N
+#undef SS_LAUNCH_FASTC
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  return (p.cmvn_mode && !fuse) ? -1001 : 0;
+}
+
+}  // namespace ss

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
             constexpr int j = decltype(jj)::value;
             const float2 x = __ldg(reinterpret_cast<const float2*>(px + 64 * j));
             const float2 w = win2[32 * j];
-            v[j] = make_float2(x.x * w.x, x.y * w.y);
+            v[j] = __fmul2_rn(x, w);
           });
         } else {
           const int64_t q0 = memlen + row * span + o0 + 2 * u;
@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
         constexpr int k1 = 2 * decltype(kk)::value;
         const float4 w = twrow[k1 / 2];
         float2 y0 = v[k1], y1 = v[k1 + 1];
-        if constexpr (k1 > 0) y0 = make_float2(y0.x * w.x - y0.y * w.y, y0.x * w.y + y0.y * w.x);
-        y1 = make_float2(y1.x * w.z - y1.y * w.w, y1.x * w.w + y1.y * w.z);
+        if constexpr (k1 > 0) y0 = ssfft::cmulf(y0, make_float2(w.x, w.y));
+        y1 = ssfft::cmulf(y1, make_float2(w.z, w.w));
         xch[k1 * kXs + u] = y0;
         xch[(k1 + 1) * kXs + u] = y1;
       });
@@ -166,11 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
         if (isz) zb = g[(32 - k2) & 31];
         const float2 za = g[k2];
         const float2 w = twk[32 * k2];
-        const float ex = za.x + zb.x, ey = za.y - zb.y;
-        const float ox = za.y + zb.y, oy = zb.x - za.x;
-        const float tx = ox * w.x - oy * w.y, ty = ox * w.y + oy * w.x;
-        const float ax = ex + tx, ay = ey + ty;
-        pA[32 * k2] = fmaf(ax, ax, ay * ay);
+        const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
+        const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
+        const float2 xa = ssfft::cadd(e, ssfft::cmulf(od, w));
+        pA[32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
       });
       if (isz) {
         Pf[512] = 4.0f * fmaf(g[16].x, g[16].x, g[16].y * g[16].y);  // X[512] = conj Z[512]

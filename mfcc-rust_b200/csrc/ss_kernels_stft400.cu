@@ -74,11 +74,11 @@ __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
 
 __device__ __forceinline__ float2 pair_power(float2 za, float2 zb, float2 w) {
   // E' = za + conj zb, O' = (za - conj zb)/i, T' = W400^k O'; returns |E'+T'|^2, |E'-T'|^2
-  const float ex = za.x + zb.x, ey = za.y - zb.y;
-  const float ox = za.y + zb.y, oy = zb.x - za.x;
-  const float tx = ox * w.x - oy * w.y, ty = ox * w.y + oy * w.x;
-  const float ax = ex + tx, ay = ey + ty, bx = ex - tx, by = ey - ty;
-  return make_float2(fmaf(ax, ax, ay * ay), fmaf(bx, bx, by * by));
+  const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
+  const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
+  const float2 tt = ssfft::cmulf(od, w);
+  const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
+  return make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
 }
 
 #ifndef SS_STFT400_MINB
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, SS_STFT400_MINB) k_stft400(const Stf
             constexpr int j = decltype(jj)::value;
             const float2 x = __ldg(reinterpret_cast<const float2*>(px + 20 * j));
             const float2 w = win2[10 * j];
-            v[j] = make_float2(x.x * w.x, x.y * w.y);
+            v[j] = __fmul2_rn(x, w);
           });
         } else {
           sfor<0, kR1>([&](auto jj) {
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kThreads, SS_STFT400_MINB) k_stft400(const Stf
       constexpr int k1 = 2 * decltype(kk)::value;
       const float4 w = twrow[k1 / 2];
       float2 y0 = v[k1], y1 = v[k1 + 1];
-      if constexpr (k1 > 0) y0 = make_float2(y0.x * w.x - y0.y * w.y, y0.x * w.y + y0.y * w.x);
-      y1 = make_float2(y1.x * w.z - y1.y * w.w, y1.x * w.w + y1.y * w.z);
+      if constexpr (k1 > 0) y0 = ssfft::cmulf(y0, make_float2(w.x, w.y));
+      y1 = ssfft::cmulf(y1, make_float2(w.z, w.w));
       xch[k1 * kT + u] = y0;
       xch[(k1 + 1) * kT + u] = y1;
     });
