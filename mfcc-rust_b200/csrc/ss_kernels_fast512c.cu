@@ -38,13 +38,12 @@ namespace {
 using ssfft::sfor;
 
 #ifndef SS_F512C_WARPS
-#define SS_F512C_WARPS 8
+#define SS_F512C_WARPS 20
 #endif
-#ifndef SS_F512C_CTAS
-#define SS_F512C_CTAS 3
-#endif
-constexpr int kWarps = SS_F512C_WARPS, kThreads = kWarps * 32;
-constexpr int kCtasPerSm = SS_F512C_CTAS;
+// One persistent CTA per SM: the warps are independent after the table load, and a single CTA
+// needs only one shared-memory copy of the fragment tables (27 KB for the 40-filter bank).
+constexpr int kMaxWarps = SS_F512C_WARPS, kMaxThreads = kMaxWarps * 32;
+constexpr int kSmemBudget = 226 * 1024;       // of the 227 KB an sm_100 CTA may use
 constexpr int kXs = 18;                       // transpose row stride in float2 (144 B: conflict-free LDS.128)
 constexpr int kXchFrame = 16 * kXs;           // 288 float2 per frame
 constexpr int kXchFloats = 2 * kXchFrame * 2; // 1152 floats per warp (2 frames)
@@ -56,7 +55,8 @@ constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows;  // + 8 fr
 static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 constexpr int kTwRow = 36;                    // floats per lane row of the W256 table (16 float2 + pad)
 constexpr int kTabTw = 16 * kTwRow;           // CTA-shared twiddle table
-constexpr int kNtMax = 8, kNcMax = 16;        // nf <= 64, nc <= 16
+constexpr int kNtMax = 8, kMtMax = 4, kNcMax = 16;  // nf <= 64, nc <= 16
+constexpr int kLgRow = 72;                    // log-mel tile row stride: >= 64 filters, 72 % 32 == 8 -> conflict-free LDS.64 B fragments
 
 __device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
 __device__ __forceinline__ float fast_sqrt(float x) {
@@ -78,38 +78,48 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // D += A(16x8, row) * B(8x8, col), TF32 inputs, f32 accumulate
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], float b0, float b1) {
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float4& a, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+      : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+        "r"(b0), "r"(b1));
 }
 
 struct FastArgsC {
   FrameParams p;
   const float* tw;         // [16][kTwRow] W256^{u k1}
-  const float4* mel_frag;  // [NT][kKs][32] = b0_hi, b1_hi, b0_lo, b1_lo
-  const float4* dct_frag;  // [NT][2][32]
+  const float* tab;        // fragment tables, copied to shared memory once per CTA:
+                           //   mel [blocks][hi, lo][32] float4: A fragments of the filterbank (16 filters x 8 bins),
+                           //   only the k-steps inside each 16-filter group's band, then
+                           //   dct [NT][hi, lo][32] float4: A fragments of the DCT matrix (16 cepstra x 8 filters)
+  int tab_floats;          // size of the two tables
+  int dct_ofs;             // float offset of the dct table inside tab
+  int mel_base[kMtMax];    // first block of m-tile mt inside the mel table
   int64_t n_items;         // clips * chunks_per_clip; one item per warp at a time
   int chunks_per_clip;
   int fpi;                 // frames per item (a multiple of the tile height, or >= T)
   int fuse_cmvn;           // 0 none, 1 mean, 2 mean+var: one warp takes the whole clip and normalises it in place
   int vec2;                // every frame start is 8-byte aligned
   int nf_even;             // nf is even: float2 stores of the mel rows
-  int ks_lo[kNtMax], ks_n2[kNtMax];  // first k-step (8 bins each) and number of k-step pairs of the band, per n-tile of 8 filters
+  int ks_lo[kMtMax], ks_n2[kMtMax];  // first k-step (8 bins each) and number of k-step pairs of the band, per m-tile of 16 filters
 };
 
 // JMAX: column groups (32 samples each) that can be non-zero; EXACT: JMAX == ceil(L / 32), so only
 // the last group needs a bounds check; SSC: also the centroid numerator; NT: n-tiles of 8 filters
-template <int JMAX, bool EXACT, bool SSC, int NT>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_fast512c(const FastArgsC a) {
+template <int JMAX, bool EXACT, bool SSC, int NT>  // MT = (NT + 1) / 2 m-tiles of 16 filters
+__global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) {
   extern __shared__ __align__(16) float smem[];
   float* tw_s = smem;
-  float* warp_s = smem + kTabTw + (threadIdx.x >> 5) * kWarpFloats;
+  float* tab_s = smem + kTabTw;
+  float* warp_s = tab_s + a.tab_floats + (threadIdx.x >> 5) * kWarpFloats;
   const FrameParams& p = a.p;
-  for (int i = threadIdx.x; i < kTabTw; i += kThreads) tw_s[i] = __ldg(a.tw + i);
+  constexpr int MT = (NT + 1) / 2;
+  for (int i = threadIdx.x; i < kTabTw; i += blockDim.x) tw_s[i] = __ldg(a.tw + i);
+  for (int i = threadIdx.x; i < a.tab_floats / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(a.tab) + i);
   // the tile's pad columns (bins 132..135) are never written again and must be finite
-  for (int i = (threadIdx.x & 31); i < kTileRows * kPs + kTileRows; i += 32) warp_s[kXchFloats + i] = 0.0f;
+  for (int i = (threadIdx.x & 31); i < kWarpFloats; i += 32) warp_s[i] = 0.0f;
   __syncthreads();  // the only block-wide barrier: from here on the warps are independent
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,11 +139,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_fast512c(const FastArg
   float2* xch = reinterpret_cast<float2*>(warp_s) + fi * kXchFrame;
   float* Pt = warp_s + kXchFloats;            // [kTileRows][kPs]
   float* e_s = Pt + kTileRows * kPs;          // [kTileRows] frame energies
-  // tile frame j <-> tile row r: the two frames of a pair sit two rows apart (bank-disjoint stores)
-  const int j_of_g = 4 * (g >> 2) + 2 * (g & 1) + ((g >> 1) & 1);
   // does this lane's last column group (j = JMAX - 1) lie inside the frame?
   const bool last0 = 2 * u + 32 * (JMAX - 1) < L, last1 = 2 * u + 32 * (JMAX - 1) + 1 < L;
-  for (int64_t item = (int64_t)blockIdx.x * kWarps + warp; item < a.n_items; item += (int64_t)gridDim.x * kWarps) {
+  const int n_warps = blockDim.x >> 5;
+  for (int64_t item = (int64_t)blockIdx.x * n_warps + warp; item < a.n_items; item += (int64_t)gridDim.x * n_warps) {
     const int64_t clip = item / a.chunks_per_clip;
     const int chunk = (int)(item - clip * a.chunks_per_clip);
     const float* rowp = p.pcm + clip * p.row_stride + 2 * u;
@@ -235,133 +244,113 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_fast512c(const FastArg
         for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
         if (isz) {
           const float energy = zero_handling(mscale * esum);  // feature.rs:216-219
-          e_s[row] = energy;
+          e_s[2 * pr + fi] = energy;
           if (p.energy && valid) p.energy[obase + fr] = energy;
         }
       }
       __syncwarp();
 
-      // ---- mel filterbank on the tensor cores (feature.rs:229-230): [8 frames][136 bins] x banded
-      // [136][8 NT], one n-tile of 8 filters at a time over the k-steps its band touches.
-      // Contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1, so a lane's two A
-      // values are one 8-byte load.  Rows 8..15: P * R for the SSC numerator, else zero.
-      // Then zero_handling -> stores -> ln (feature.rs:216-230, 242-245) on the accumulator
-      // fragment: lane (g, t) holds filters 8 nt + 2t, + 1 of tile row g.
-      const int frg = tile_f0 + j_of_g;
-      const bool validr = frg < fend;
-      const int64_t orow = (obase + frg) * nf + 2 * t;
-      float* const mfe_p = p.mfe ? p.mfe + orow : nullptr;
-      float* const lmfe_p = p.lmfe ? p.lmfe + orow : nullptr;
-      float* const ssc_p = (SSC && p.ssc) ? p.ssc + orow : nullptr;
-      float lg[NT][2];
+      // ---- mel filterbank on the tensor cores (feature.rs:229-230), transposed:
+      //   mel^T [16 MT filters][8 frames] = W [16 MT][136 bins] (banded, pre-split on the host) x P^T.
+      // M = 16 filters, N = the 8 frames of the tile, K = 8 bins per MMA, so every row of the MMA is
+      // used; only the k-steps a 16-filter group's band touches are visited (22 of 54 blocks for the
+      // 40-filter bank).  Contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1, so a
+      // lane's two P values are one 8-byte load.  The accumulator fragment holds
+      // (filter 16 mt + g [+ 8], tile row 2t [+ 1]); zero_handling -> stores -> ln follow
+      // (feature.rs:216-230, 242-245) and the log-mel values go to a [frame][filter] tile for the DCT.
+      float* lgT = warp_s;  // overlays the transpose tile, dead until the next pair
+      const int j0 = (t & 1) + 4 * (t >> 1);  // frame (within the tile) of tile row 2t; row 2t + 1 is frame j0 + 2
       {
+        const int fr_a = tile_f0 + j0, fr_b = fr_a + 2;
+        const bool va = fr_a < fend, vb = fr_b < fend;
+        const int64_t oa = (obase + fr_a) * nf, ob = oa + 2 * nf;
         const float* prow = Pt + g * kPs + 2 * t;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
+        for (int mt = 0; mt < MT; ++mt) {
           float accB[4] = {0.f, 0.f, 0.f, 0.f}, accS[4] = {0.f, 0.f, 0.f, 0.f}, accT[4] = {0.f, 0.f, 0.f, 0.f};
-          const int k0 = a.ks_lo[nt];
+          float numB[4] = {0.f, 0.f, 0.f, 0.f}, numS[4] = {0.f, 0.f, 0.f, 0.f}, numT[4] = {0.f, 0.f, 0.f, 0.f};
+          const int k0 = a.ks_lo[mt];
           const float* pp = prow + 8 * k0;
-          const float4* bp = a.mel_frag + (nt * kKsTab + k0) * 32 + lane;
-          float rb = SSC ? fmaf(p.ssc_step, (float)(8 * k0 + 2 * t), p.ssc_r0) : 0.f;
+          const float4* ap = reinterpret_cast<const float4*>(tab_s) + a.mel_base[mt] * 64 + lane;
+          float rb = SSC ? fmaf(p.ssc_step, (float)(8 * k0 + 2 * t), p.ssc_r0) : 0.f;  // R[k] of this lane's first bin
           // two k-steps per iteration (the band is padded to an even count with zero-weight blocks;
           // the tile columns those read are other rows' finite values)
 #pragma unroll 1
-          for (int n2 = a.ks_n2[nt]; n2 > 0; --n2) {
+          for (int n2 = a.ks_n2[mt]; n2 > 0; --n2) {
             const float2 pv0 = *reinterpret_cast<const float2*>(pp);
             const float2 pv1 = *reinterpret_cast<const float2*>(pp + 8);
-            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 32);
+            const float4 h0 = ap[0], l0 = ap[32], h1 = ap[64], l1 = ap[96];
             pp += 16;
-            bp += 64;
+            ap += 128;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float2 pv = h ? pv1 : pv0;
-              const float4 b = h ? b1 : b0;
-              uint32_t ah[4], al[4];
-              split_tf32(pv.x, ah[0], al[0]);
-              split_tf32(pv.y, ah[2], al[2]);
-              if (SSC) {
-                split_tf32(pv.x * rb, ah[1], al[1]);
-                split_tf32(pv.y * (rb + p.ssc_step), ah[3], al[3]);
+              const float4 wh = h ? h1 : h0, wl = h ? l1 : l0;
+              uint32_t bh0, bl0, bh1, bl1;
+              split_tf32(pv.x, bh0, bl0);
+              split_tf32(pv.y, bh1, bl1);
+              mma_tf32(accB, wh, bh0, bh1);  // hi x hi
+              mma_tf32(accS, wl, bh0, bh1);  // lo x hi
+              mma_tf32(accT, wh, bl0, bl1);  // hi x lo
+              if (SSC) {  // numerator: the same weights against P[k] R[k]
+                split_tf32(pv.x * rb, bh0, bl0);
+                split_tf32(pv.y * (rb + p.ssc_step), bh1, bl1);
                 rb = fmaf(8.0f, p.ssc_step, rb);
-              } else {
-                ah[1] = ah[3] = al[1] = al[3] = 0u;
+                mma_tf32(numB, wh, bh0, bh1);
+                mma_tf32(numS, wl, bh0, bh1);
+                mma_tf32(numT, wh, bl0, bl1);
               }
-              mma_tf32(accB, ah, b.x, b.y);  // hi x hi
-              mma_tf32(accS, al, b.x, b.y);  // lo x hi
-              mma_tf32(accT, ah, b.z, b.w);  // hi x lo
             }
           }
-          const float m0 = zero_handling(accB[0] + (accS[0] + accT[0]));
-          const float m1 = zero_handling(accB[1] + (accS[1] + accT[1]));
-          lg[nt][0] = fast_ln(m0);
-          lg[nt][1] = fast_ln(m1);
-          if (validr) {
-            float s0 = 0.f, s1 = 0.f;
-            if (SSC) {
-              s0 = __fdividef(accB[2] + (accS[2] + accT[2]), m0);
-              s1 = __fdividef(accB[3] + (accS[3] + accT[3]), m1);
-            }
-            if (a.nf_even && 8 * nt + 2 * t + 1 < nf) {
-              if (mfe_p) *reinterpret_cast<float2*>(mfe_p + 8 * nt) = make_float2(m0, m1);
-              if (lmfe_p) *reinterpret_cast<float2*>(lmfe_p + 8 * nt) = make_float2(lg[nt][0], lg[nt][1]);
-              if (SSC && ssc_p) *reinterpret_cast<float2*>(ssc_p + 8 * nt) = make_float2(s0, s1);
-            } else if (8 * nt + 2 * t < nf) {
-              const bool two = 8 * nt + 2 * t + 1 < nf;
-              if (mfe_p) { mfe_p[8 * nt] = m0; if (two) mfe_p[8 * nt + 1] = m1; }
-              if (lmfe_p) { lmfe_p[8 * nt] = lg[nt][0]; if (two) lmfe_p[8 * nt + 1] = lg[nt][1]; }
-              if (SSC && ssc_p) { ssc_p[8 * nt] = s0; if (two) ssc_p[8 * nt + 1] = s1; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int f = 16 * mt + g + 8 * (i >> 1);  // filter; i & 1: tile row 2t / 2t + 1 = frame j0 / j0 + 2
+            const float m = zero_handling(accB[i] + (accS[i] + accT[i]));
+            const float lgv = fast_ln(m);
+            if (f < kLgRow) lgT[(j0 + 2 * (i & 1)) * kLgRow + f] = lgv;
+            if (((i & 1) ? vb : va) && f < nf) {
+              const int64_t o = ((i & 1) ? ob : oa) + f;
+              if (p.mfe) p.mfe[o] = m;
+              if (p.lmfe) p.lmfe[o] = lgv;
+              if (SSC && p.ssc) p.ssc[o] = __fdividef(numB[i] + (numS[i] + numT[i]), m);
             }
           }
         }
       }
 
-      // ---- DCT-II on the tensor cores (feature.rs:120-123): the mel accumulator fragment is the A
-      // fragment of k-step nt (slot t <-> filter 8 nt + 2t, slot t + 4 <-> filter 8 nt + 2t + 1)
+      // ---- DCT-II on the tensor cores (feature.rs:120-123), transposed as well:
+      //   ceps^T [16][8 frames] = D [16][8 NT filters] (pre-split on the host) x logmel^T.
+      // One m-tile covers all (<= 16) cepstra; the accumulator holds (cepstrum g [+ 8], frame 2t [+ 1]).
       if (p.mfcc) {
-        float dB[2][4], dS[2][4];
-#pragma unroll
-        for (int n2 = 0; n2 < 2; ++n2) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { dB[n2][i] = 0.f; dS[n2][i] = 0.f; }
-        }
-        const float4* dt = a.dct_frag + lane;
+        __syncwarp();
+        float dB[4] = {0.f, 0.f, 0.f, 0.f}, dS[4] = {0.f, 0.f, 0.f, 0.f}, dT[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* lrow = lgT + g * kLgRow + 2 * t;
+        const float4* dp = reinterpret_cast<const float4*>(tab_s + a.dct_ofs) + lane;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          uint32_t ah[4], al[4];
-          split_tf32(lg[nt][0], ah[0], al[0]);
-          split_tf32(lg[nt][1], ah[2], al[2]);
-          ah[1] = ah[3] = al[1] = al[3] = 0u;
-#pragma unroll
-          for (int n2 = 0; n2 < 2; ++n2) {
-            if (n2 == 0 || nc > 8) {
-              const float4 b = __ldg(dt + (nt * 2 + n2) * 32);
-              mma_tf32(dB[n2], ah, b.x, b.y);
-              mma_tf32(dS[n2], al, b.x, b.y);
-              mma_tf32(dS[n2], ah, b.z, b.w);
-            }
-          }
+          const float2 lv = *reinterpret_cast<const float2*>(lrow + 8 * nt);
+          const float4 wh = dp[(2 * nt) * 32], wl = dp[(2 * nt + 1) * 32];
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32(lv.x, bh0, bl0);
+          split_tf32(lv.y, bh1, bl1);
+          mma_tf32(dB, wh, bh0, bh1);
+          mma_tf32(dS, wl, bh0, bh1);
+          mma_tf32(dT, wh, bl0, bl1);
         }
-        // scale (feature.rs:126-131) and c0 <- ln(energy) (feature.rs:137-146)
-        float cv[4];
+        // scale (feature.rs:126-131), c0 <- ln(energy) (feature.rs:137-146) and stores; with a
+        // fused CMVN the block is normalised in place below
+        const int fr_a = tile_f0 + 2 * t;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = 8 * (k >> 1) + 2 * t + (k & 1);
-          float x = dB[k >> 1][k & 1] + dS[k >> 1][k & 1];
+        for (int i = 0; i < 4; ++i) {
+          const int c = g + 8 * (i >> 1), fr = fr_a + (i & 1);
+          float x = dB[i] + (dS[i] + dT[i]);
           if (c == 0) {
-            if (p.dc_elim) x = fast_ln(e_s[g]);
-            else if (frg == 0) x *= p.scale_00;  // only element [0,0] gets the k=0 scale (feature.rs:128)
+            if (p.dc_elim) x = fast_ln(e_s[2 * t + (i & 1)]);
+            else if (fr == 0) x *= p.scale_00;  // only element [0,0] gets the k=0 scale (feature.rs:128)
           } else {
             x *= p.scale_rest;
           }
-          cv[k] = x;
-        }
-        if (validr) {  // with a fused CMVN these are normalised in place below
-          float* dst = p.mfcc + (obase + frg) * nc;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = 8 * (k >> 1) + 2 * t + (k & 1);
-            if (c < nc) dst[c] = cv[k];
-          }
+          if (fr < fend && c < nc) p.mfcc[(obase + fr) * nc + c] = x;
         }
       }
       __syncwarp();  // the tile and the energies are rewritten by the next tile's pairs
@@ -423,57 +412,72 @@ static float tf32_rna(float x) {
 }
 
 struct FragTables {
-  int NT = 0;
-  int ks_lo[kNtMax] = {0}, ks_hi[kNtMax] = {0};
-  std::vector<float> mel, dct;  // [NT][kKsTab][32][4], [NT][2][32][4]
+  int NT = 0, MT = 0;
+  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
+  std::vector<float> mel, dct;  // [blocks][2][32][4], [NT][2][32][4]
 };
+
+// A fragment of mma.m16n8k8 (row-major 16 x 8) for lane (g, t): rows g, g + 8; contraction slots t, t + 4.
+// `at(row, slot)` returns the matrix element; the fragment is stored pre-split as a TF32 hi quad and
+// the f32 remainder quad.
+template <class F>
+static void put_a_frag(float* hi, float* lo, int lane, F at) {
+  const int g = lane >> 2, t = lane & 3;
+  const float v[4] = {at(g, t), at(g + 8, t), at(g, t + 4), at(g + 8, t + 4)};
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = tf32_rna(v[i]);
+    lo[i] = v[i] - hi[i];
+  }
+}
 
 static bool build_frags(const Derived& d, const MelBank& mb, FragTables* ft) {
   const int nf = d.nf;
   if (mb.max_bin > 128) return false;  // only bins <= 128 are kept (always true for the reference's bank at n_fft 512)
   if (nf > 8 * kNtMax || d.nc > kNcMax || nf < 1) return false;
-  const int NT = nf <= 40 ? 5 : 8;
+  const int NT = nf <= 40 ? 5 : 8, MT = (NT + 1) / 2;
   ft->NT = NT;
+  ft->MT = MT;
   const float mscale = 0.5f * (1.0f / (float)d.W);  // the kernel keeps 2 n_fft |X| in the tile
-  std::vector<float> dense((size_t)8 * NT * kPs, 0.f);  // [filter][bin]
+  const int ncol = 8 * kKsTab;
+  std::vector<float> dense((size_t)16 * MT * ncol, 0.f);  // [filter][bin]
   for (int f = 0; f < nf; ++f)
-    for (int i = 0; i < mb.len[f]; ++i) dense[(size_t)f * kPs + mb.start[f] + i] = mb.w[mb.wofs[f] + i] * mscale;
-  ft->mel.assign((size_t)kKsTab * NT * 32 * 4, 0.f);
-  for (int nt = 0; nt < kNtMax; ++nt) { ft->ks_lo[nt] = kKs; ft->ks_hi[nt] = 0; }
-  for (int nt = 0; nt < NT; ++nt) {
+    for (int i = 0; i < mb.len[f]; ++i) dense[(size_t)f * ncol + mb.start[f] + i] = mb.w[mb.wofs[f] + i] * mscale;
+  ft->mel.clear();
+  for (int mt = 0; mt < kMtMax; ++mt) { ft->ks_lo[mt] = 0; ft->ks_n2[mt] = 0; ft->mel_base[mt] = 0; }
+  int n_blocks = 0;
+  for (int mt = 0; mt < MT; ++mt) {
+    int lo = kKs, hi = 0;
     for (int ks = 0; ks < kKs; ++ks) {
       bool any = false;
-      for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, t = lane & 3;
-        const float b0 = dense[(size_t)(8 * nt + g) * kPs + 8 * ks + 2 * t];
-        const float b1 = dense[(size_t)(8 * nt + g) * kPs + 8 * ks + 2 * t + 1];
-        float* o = &ft->mel[(((size_t)nt * kKsTab + ks) * 32 + lane) * 4];
-        o[0] = tf32_rna(b0);
-        o[1] = tf32_rna(b1);
-        o[2] = b0 - o[0];
-        o[3] = b1 - o[1];
-        any = any || b0 != 0.f || b1 != 0.f;
-      }
-      if (any) { ft->ks_lo[nt] = std::min(ft->ks_lo[nt], ks); ft->ks_hi[nt] = std::max(ft->ks_hi[nt], ks + 1); }
+      for (int r = 0; r < 16; ++r)
+        for (int c = 0; c < 8; ++c) any = any || dense[(size_t)(16 * mt + r) * ncol + 8 * ks + c] != 0.f;
+      if (any) { lo = std::min(lo, ks); hi = std::max(hi, ks + 1); }
     }
-    if (ft->ks_hi[nt] == 0) ft->ks_lo[nt] = 0;  // an n-tile of empty filters: no k-steps
+    if (hi <= lo) continue;  // 16 empty filters: no k-steps
+    const int n2 = (hi - lo + 1) / 2;  // k-step pairs; an odd band gets one zero-weight block (ks <= 17 < kKsTab)
+    ft->ks_lo[mt] = lo;
+    ft->ks_n2[mt] = n2;
+    ft->mel_base[mt] = n_blocks;
+    for (int ks = lo; ks < lo + 2 * n2; ++ks, ++n_blocks) {
+      // contraction slot s <-> bin 8 ks + 2 (s % 4) + s / 4 (the kernel loads bins 2t, 2t + 1 as one float2)
+      const size_t o = ft->mel.size();
+      ft->mel.resize(o + 2 * 32 * 4, 0.f);
+      for (int lane = 0; lane < 32; ++lane)
+        put_a_frag(&ft->mel[o + lane * 4], &ft->mel[o + (32 + lane) * 4], lane,
+                   [&](int r, int s) { return dense[(size_t)(16 * mt + r) * ncol + 8 * ks + 2 * (s & 3) + (s >> 2)]; });
+    }
   }
   std::vector<float> dct;
   build_dct(d, &dct);  // [nc][nf]
   ft->dct.assign((size_t)NT * 2 * 32 * 4, 0.f);
   for (int nt = 0; nt < NT; ++nt)
-    for (int n2 = 0; n2 < 2; ++n2)
-      for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, t = lane & 3;
-        const int c = 8 * n2 + g, f0 = 8 * nt + 2 * t;
-        const float b0 = (c < d.nc && f0 < nf) ? dct[(size_t)c * nf + f0] : 0.f;
-        const float b1 = (c < d.nc && f0 + 1 < nf) ? dct[(size_t)c * nf + f0 + 1] : 0.f;
-        float* o = &ft->dct[(((size_t)nt * 2 + n2) * 32 + lane) * 4];
-        o[0] = tf32_rna(b0);
-        o[1] = tf32_rna(b1);
-        o[2] = b0 - o[0];
-        o[3] = b1 - o[1];
-      }
+    for (int lane = 0; lane < 32; ++lane) {
+      const size_t o = (((size_t)nt * 2) * 32 + lane) * 4;
+      put_a_frag(&ft->dct[o], &ft->dct[o + 32 * 4], lane, [&](int r, int s) {
+        const int f = 8 * nt + 2 * (s & 3) + (s >> 2);
+        return (r < d.nc && f < nf) ? dct[(size_t)r * nf + f] : 0.f;
+      });
+    }
   return true;
 }
 
@@ -481,9 +485,9 @@ static bool build_frags(const Derived& d, const MelBank& mb, FragTables* ft) {
 
 struct Fast512cTables {
   float* d_tab = nullptr;  // tw | mel fragments | dct fragments
-  size_t o_mel = 0, o_dct = 0;
+  int tab_floats = 0, dct_ofs = 0;
   int NT = 0;
-  int ks_lo[kNtMax] = {0}, ks_hi[kNtMax] = {0};
+  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
 };
 
 bool fast512c_supported(const Derived& d, const MelBank& mb) {
@@ -505,11 +509,11 @@ int fast512c_build_tables(const Derived& d, const MelBank& mb, Fast512cTables** 
     }
   Fast512cTables* t = new Fast512cTables;
   t->NT = ft.NT;
-  for (int i = 0; i < kNtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_hi[i] = ft.ks_hi[i]; }
-  t->o_mel = h.size();
+  for (int i = 0; i < kMtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_n2[i] = ft.ks_n2[i]; t->mel_base[i] = ft.mel_base[i]; }
   h.insert(h.end(), ft.mel.begin(), ft.mel.end());
-  t->o_dct = h.size();
+  t->dct_ofs = (int)ft.mel.size();
   h.insert(h.end(), ft.dct.begin(), ft.dct.end());
+  t->tab_floats = (int)(ft.mel.size() + ft.dct.size());
   cudaError_t e = cudaMalloc(&t->d_tab, h.size() * sizeof(float));
   if (e != cudaSuccess) { delete t; return (int)e; }
   e = cudaMemcpy(t->d_tab, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -531,10 +535,15 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   FastArgsC a;
   a.p = p;
   a.tw = t->d_tab;
-  a.mel_frag = reinterpret_cast<const float4*>(t->d_tab + t->o_mel);
-  a.dct_frag = reinterpret_cast<const float4*>(t->d_tab + t->o_dct);
-  for (int i = 0; i < kNtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = (t->ks_hi[i] - t->ks_lo[i] + 1) / 2; }
-  const int64_t warps_resident = (int64_t)sm_count * kCtasPerSm * kWarps;
+  a.tab = t->d_tab + kTabTw;
+  a.tab_floats = t->tab_floats;
+  a.dct_ofs = t->dct_ofs;
+  for (int i = 0; i < kMtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
+  // as many warps as the shared memory left by the tables allows (21 for the 40-filter bank)
+  const size_t fixed = (size_t)(kTabTw + t->tab_floats) * sizeof(float);
+  const int n_warps = (int)std::min<size_t>(kMaxWarps, (kSmemBudget - fixed) / (kWarpFloats * sizeof(float)));
+  if (n_warps < 4) return -1000;
+  const int64_t warps_resident = (int64_t)sm_count * n_warps;
   // a fused CMVN needs the whole clip in one warp; worth it while there are enough clips to fill the GPU
   const bool fuse = p.mfcc && p.cmvn_mode && p.T <= 4096 && p.n_rows >= warps_resident;
   a.fuse_cmvn = fuse ? p.cmvn_mode : 0;
@@ -554,8 +563,8 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   auto al8 = [](const float* q) { return reinterpret_cast<uintptr_t>(q) % 8 == 0; };
   a.nf_even = (p.nf % 2 == 0) && al8(p.mfe) && al8(p.lmfe) && al8(p.ssc);
   const bool ssc = p.ssc != nullptr;
-  const size_t smem = (size_t)(kTabTw + kWarps * kWarpFloats) * sizeof(float);
-  const int64_t grid = std::min<int64_t>((a.n_items + kWarps - 1) / kWarps, (int64_t)sm_count * kCtasPerSm);
+  const size_t smem = fixed + (size_t)n_warps * kWarpFloats * sizeof(float);
+  const int64_t grid = std::min<int64_t>((a.n_items + n_warps - 1) / n_warps, (int64_t)sm_count);
   if (grid <= 0) return 0;
   const int jn = (p.L + 31) / 32;
   cudaError_t e;
@@ -563,7 +572,7 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   do {                                                                                                         \
     e = cudaFuncSetAttribute(k_fast512c<J, X, C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     if (e != cudaSuccess) return (int)e;                                                                       \
-    k_fast512c<J, X, C, N><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);                       \
+    k_fast512c<J, X, C, N><<<(unsigned)grid, n_warps * 32, smem, (cudaStream_t)stream>>>(a);                       \
   } while (0)
 #define SS_LAUNCH_FASTC_N(J, X, C)                                          \
   do {                                                                      \
