@@ -334,18 +334,23 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         achieved = alg["bytes"] / (ms_step * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel and workload from one
+        # `ncu --set full` capture (profiles/ncu_traffic.json, per launch); null when there is none
+        traffic, traffic_src = None, None
+        tf = ROOT / "profiles" / "ncu_traffic.json"
+        if tf.exists():
+            t = json.loads(tf.read_text()).get(args.config)
+            if t and t.get("clips") == n and t.get("kernel") == sb.lib.ss_last_kernel_name().decode():
+                traffic, traffic_src = float(t["dram_bytes"]), t.get("source")
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "frames_per_s": frames_s,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "clips_per_gpu": n, "samples_per_clip": length, "frames_per_clip": T,
                        "l2": "inputs larger than L2" if n * length * 4 > (126 << 20) else "input fits in L2",
-                       "kernel": ("k_fast512" if (w["kind"] == "speechpy" and cfg.info.fast_path and not args.generic) else
-                                  "k_stft400" if (w["kind"] == "stft" and cfg.info.fast_stft and cfg.window_size == 400 and not args.generic) else
-                                  "k_stft2048" if (w["kind"] == "stft" and cfg.info.fast_stft and cfg.window_size == 2048 and not args.generic) else
-                                  "k_frames_generic")},
+                       "kernel": sb.lib.ss_last_kernel_name().decode()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg["bytes"],
                          "fp32": {"achieved_tflops": alg["flops"] / (ms_step * 1e-3) / 1e12,
                                   "peak_tflops_at_max_clock": FP32_PEAK_TFLOPS_AT_MAX_CLOCK,

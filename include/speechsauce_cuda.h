@@ -204,6 +204,9 @@ int ss_debug_filterbank(const ss_plan* plan, float* out_nf_by_F);
 int ss_debug_window(const ss_plan* plan, float* out_W);
 /* number of kernels this library has launched from the calling process since load */
 int64_t ss_kernel_launch_count(void);
+/* name of the fused frame kernel the calling thread launched last ("k_fast512c", "k_stft400", ...; "" before the
+   first launch); valid until the next call on the thread */
+const char* ss_last_kernel_name(void);
 
 #ifdef __cplusplus
 }

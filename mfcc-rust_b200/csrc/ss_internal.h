@@ -159,5 +159,6 @@ int launch_cmvnw(const float* in, int64_t n_mats, int64_t rows, int64_t cols, in
                  float* scratch, void* stream);
 
 void count_launch(int n = 1);
+void note_kernel(const char* name);  // name of the fused frame kernel just launched (ss_last_kernel_name)
 
 }  // namespace ss

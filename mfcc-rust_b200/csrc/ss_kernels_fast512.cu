@@ -640,6 +640,7 @@ int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, v
   else { if (ssc) SS_LAUNCH_FAST(32, false, true); else SS_LAUNCH_FAST(32, false, false); }
 #undef SS_LAUNCH_FAST
   count_launch();
+  note_kernel("k_fast512");
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   return (p.cmvn_mode && !fuse) ? -1001 : 0;

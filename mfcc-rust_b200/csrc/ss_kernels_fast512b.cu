@@ -494,6 +494,7 @@ int launch_fast512b(const FrameParams& p, const Fast512bTables* t, int sm_count,
   else { if (ssc) SS_LAUNCH_FASTB(16, false, true); else SS_LAUNCH_FASTB(16, false, false); }
 #undef SS_LAUNCH_FASTB
   count_launch();
+  note_kernel("k_fast512b");
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   return (p.cmvn_mode && !fuse) ? -1001 : 0;

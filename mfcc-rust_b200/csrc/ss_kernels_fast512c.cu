@@ -584,6 +584,7 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
 #undef SS_LAUNCH_FASTC_N
 #undef SS_LAUNCH_FASTC
   count_launch();
+  note_kernel("k_fast512c");
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   return (p.cmvn_mode && !fuse) ? -1001 : 0;

@@ -330,6 +330,7 @@ int launch_frames_generic(const FrameParams& p, void* stream) {
   if (e != cudaSuccess) return (int)e;
   k_frames_generic<<<(unsigned)nblocks, 256, smem, (cudaStream_t)stream>>>(p, fpc, tpg, tiles_per_row);
   count_launch();
+  note_kernel("k_frames_generic");
   return (int)cudaGetLastError();
 }
 

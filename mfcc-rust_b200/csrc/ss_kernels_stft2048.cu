@@ -327,6 +327,7 @@ int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count,
   if (e != cudaSuccess) return (int)e;
   k_stft2048<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
   count_launch();
+  note_kernel("k_stft2048");
   return (int)cudaGetLastError();
 }
 

@@ -376,6 +376,7 @@ int launch_stft400(const FrameParams& p, const Stft400Tables* t, int sm_count, v
   if (e != cudaSuccess) return (int)e;
   k_stft400<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
   count_launch();
+  note_kernel("k_stft400");
   return (int)cudaGetLastError();
 }
 

@@ -116,4 +116,5 @@ extern "C" {
     pub fn ss_debug_filterbank(plan: *const ss_plan, out_nf_by_f: *mut f32) -> c_int;
     pub fn ss_debug_window(plan: *const ss_plan, out_w: *mut f32) -> c_int;
     pub fn ss_kernel_launch_count() -> i64;
+    pub fn ss_last_kernel_name() -> *const c_char;
 }

@@ -100,6 +100,7 @@ SYMBOLS = {
     "ss_debug_filterbank": (C.c_int, [_vp, _fp]),
     "ss_debug_window": (C.c_int, [_vp, _fp]),
     "ss_kernel_launch_count": (_i64, []),
+    "ss_last_kernel_name": (C.c_char_p, []),
 }
 for _name, (_res, _args) in SYMBOLS.items():
     _fn = getattr(lib, _name)

@@ -137,6 +137,83 @@ def test_fast_and_generic_paths_agree_on_ragged_shapes():
         assert_log_close(ra["mfcc"][3], o.mfcc(x[3], oc), what="fast mfcc vs oracle")
 
 
+@pytest.mark.parametrize("nf,nc,dc", [(26, 13, True), (40, 16, True), (41, 8, False), (64, 13, True), (17, 12, True)])
+def test_fast512_filterbank_and_cepstrum_variants(nf, nc, dc):
+    """The n_fft = 512 tensor-core epilogue for other bank / cepstrum sizes than the headline's 40 / 13:
+    partial 16-filter m-tiles, an odd filter count, a fourth m-tile (nf > 48), 16 cepstra, c0 scaling."""
+    kw = dict(CONFIGS["c1"], num_filters=nf, num_cepstral=nc, dc_elimination=dc, frame_length=0.02)
+    cfg = sb.SpeechConfig(**kw)
+    oc = o.SpeechConfig(**kw)
+    assert cfg.info.fast_path == 1
+    clips = special_clips(16000)
+    x = np.stack([clips["noise"], clips["sine"], clips["impulse"]])
+    r = sb.feature.features(x, cfg, mfe=True, energy=True, lmfe=True, ssc=True, mfcc=True)
+    assert sb.lib.ss_last_kernel_name() == b"k_fast512c"
+    for i, name in enumerate(("noise", "sine", "impulse")):
+        f, e = o.mfe(x[i], oc)
+        assert_spec_close(r["mfe"][i], f, what=f"nf {nf} {name} mfe")
+        assert_spec_close(r["energy"][i], e, what=f"nf {nf} {name} energy")
+        assert_log_close(r["lmfe"][i], np.log(f), what=f"nf {nf} {name} lmfe")
+        assert_spec_close(r["ssc"][i], o.ssc(x[i], oc), rtol=2e-4, what=f"nf {nf} {name} ssc")
+        want = o.mfcc(x[i], oc)
+        if dc:
+            assert_log_close(r["mfcc"][i], want, what=f"nf {nf} nc {nc} {name} mfcc")
+        else:  # column 0 is unscaled (|c0| ~ 1e3): relative tolerance there
+            assert_log_close(r["mfcc"][i][:, 1:], want[:, 1:], what=f"nf {nf} nc {nc} {name} mfcc cols 1..")
+            np.testing.assert_allclose(r["mfcc"][i][:, 0], want[:, 0], rtol=2e-6, atol=1e-3)
+
+
+def test_fast512_fused_cmvn_on_a_full_grid():
+    """With at least one clip per resident warp the n_fft = 512 kernel normalises each clip in place
+    (one warp per clip, no separate cmvn launch): 3,200 device-resident clips of config c2, both cmvn
+    modes, through the *_dev entry point the throughput bench uses."""
+    import ctypes as C
+
+    import torch
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], devices=[0])
+    oc = o.SpeechConfig(**CONFIGS["c1"])
+    x = o.synth_signal(3200, 16000, 0x5EED0102)
+    x[5, :6000] = 0.0      # a clip that starts with digital silence
+    x[6] *= np.float32(30.0)
+    dx = torch.from_numpy(x).cuda()
+    lm = torch.empty((3200, 97, 40), dtype=torch.float32, device="cuda")
+    mf = torch.empty((3200, 97, 13), dtype=torch.float32, device="cuda")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for mode in (1, 2):
+        outs = _lib.ss_feature_outputs(None, None, C.c_void_p(lm.data_ptr()), None, C.c_void_p(mf.data_ptr()), mode, 0)
+        n0 = sb.lib.ss_kernel_launch_count()
+        _lib.check(sb.lib.ss_features_dev(cfg.plan, 0, sp, C.c_void_p(dx.data_ptr()), 3200, 16000, 16000, C.byref(outs)))
+        torch.cuda.synchronize()
+        assert sb.lib.ss_kernel_launch_count() - n0 == 1, "cmvn must be fused into the feature kernel"
+        assert sb.lib.ss_last_kernel_name() == b"k_fast512c"
+        lmfe, mfcc = lm.cpu().numpy(), mf.cpu().numpy()
+        for i in (0, 5, 6, 1599, 3199):
+            assert_log_close(lmfe[i], o.lmfe(x[i], oc), what=f"lmfe clip {i}")
+            assert_log_close(mfcc[i], o.cmvn(o.mfcc(x[i], oc), mode == 2), what=f"cmvn(mfcc) clip {i} mode {mode}")
+        np.testing.assert_allclose(mfcc.mean(1), 0, atol=2e-5 if mode == 2 else 1e-5)
+        if mode == 2:
+            np.testing.assert_allclose(mfcc.std(1), 1, atol=1e-4)
+
+
+def test_fast512_long_stream_chunks():
+    """Config c5's shape in small: two 90 s streams are cut into chunks of whole tiles, one per warp."""
+    cfg = sb.SpeechConfig(**CONFIGS["c1"])
+    gen = sb.SpeechConfig(**CONFIGS["c1"], flags=GENERIC)
+    oc = o.SpeechConfig(**CONFIGS["c1"])
+    x = o.synth_signal(2, 16000 * 90 + 77, 0x5EED0105)
+    r = sb.feature.features(x, cfg, mfe=True, energy=True, ssc=True, mfcc=True)
+    g = sb.feature.features(x, gen, mfe=True, energy=True, ssc=True, mfcc=True)
+    T = o.num_frames(x.shape[1], 400, 160, False)
+    assert r["mfe"].shape == (2, T, 40) and r["mfcc"].shape == (2, T, 13)
+    assert_spec_close(r["mfe"], g["mfe"], what="long stream mfe vs generic")
+    assert_spec_close(r["energy"], g["energy"], what="long stream energy vs generic")
+    assert_spec_close(r["ssc"], g["ssc"], rtol=2e-4, what="long stream ssc vs generic")
+    assert_log_close(r["mfcc"], g["mfcc"], what="long stream mfcc vs generic")
+    f, e = o.mfe(x[1], oc)
+    assert_spec_close(r["mfe"][1], f, what="long stream mfe vs oracle")
+    assert_log_close(r["mfcc"][1], o.mfcc(x[1], oc), what="long stream mfcc vs oracle")
+
+
 def test_reference_shape_tests_1M_samples():
     """speechsauce/src/lib.rs:94-134 re-expressed: default config, 1e6 samples -> (6248, 13), no NaN."""
     sig = o.synth_signal(1, 1_000_000, 7)[0]
