@@ -84,6 +84,7 @@ struct DeviceCtx {
   Fast512bTables* fast512b = nullptr;
   Fast512cTables* fast512c = nullptr;
   Stft400Tables* stft400 = nullptr;
+  Stft400mTables* stft400m = nullptr;
   Stft2048Tables* stft2048 = nullptr;
   Lane lanes[kLanes];
   DevBuf dev_scratch;  // scratch for the *_dev entry points (cmvn partials)
@@ -104,6 +105,7 @@ struct ss_plan {
   bool fast512b = false;
   bool fast512c = false;
   bool stft400 = false;
+  bool stft400m = false;
   bool stft2048 = false;
 };
 
@@ -161,6 +163,10 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   if (pl->stft400) {
     int e = stft400_build_tables(pl->d, pl->mb, pl->window, &dc->stft400);
     if (e) return cuda_fail((cudaError_t)e, "stft400_build_tables");
+  }
+  if (pl->stft400m) {
+    int e = stft400m_build_tables(pl->d, pl->mb, pl->window, &dc->stft400m);
+    if (e) return cuda_fail((cudaError_t)e, "stft400m_build_tables");
   }
   if (pl->stft2048) {
     int e = stft2048_build_tables(pl->d, pl->mb, pl->window, &dc->stft2048);
@@ -261,6 +267,12 @@ static void stft_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float*
 
 // mel_spectrogram / stft launch: a size-specialised kernel when one exists, else the generic one
 static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
+  // SS_STFT400_GEN=1 selects the first-generation fft_points = 400 kernel for A/B measurements
+  static const int gen400 = getenv("SS_STFT400_GEN") ? atoi(getenv("SS_STFT400_GEN")) : 2;
+  if (pl->stft400m && dc->stft400m && gen400 >= 2 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+    const int e = launch_stft400m(p, dc->stft400m, dc->sm_count, stream);
+    if (e != -1000) return e;
+  }
   if (pl->stft400 && dc->stft400 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400(p, dc->stft400, dc->sm_count, stream);
     if (e != -1000) return e;
@@ -461,6 +473,7 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   pl->fast512b = pl->fft_ok && fast512b_supported(pl->d, pl->mb);
   pl->fast512c = pl->fft_ok && fast512c_supported(pl->d, pl->mb);
   pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
+  pl->stft400m = pl->fft_ok && stft400m_supported(pl->d, pl->mb);
   pl->stft2048 = pl->fft_ok && stft2048_supported(pl->d, pl->mb);
   std::vector<int> devs;
   if (n_devices < 0) {
@@ -514,6 +527,7 @@ void ss_plan_destroy(ss_plan* pl) {
     if (dc.fast512b) fast512b_free_tables(dc.fast512b);
     if (dc.fast512c) fast512c_free_tables(dc.fast512c);
     if (dc.stft400) stft400_free_tables(dc.stft400);
+    if (dc.stft400m) stft400m_free_tables(dc.stft400m);
     if (dc.stft2048) stft2048_free_tables(dc.stft2048);
   }
   if (prev >= 0) cudaSetDevice(prev);
@@ -534,7 +548,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
   info->fast_path = (pl->fast512 || pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  info->fast_stft = (pl->stft400 || pl->stft2048) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
+  info->fast_stft = (pl->stft400 || pl->stft400m || pl->stft2048) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }
 

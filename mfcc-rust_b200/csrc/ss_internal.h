@@ -139,6 +139,13 @@ int stft400_build_tables(const Derived& d, const MelBank& mb, const std::vector<
 void stft400_free_tables(Stft400Tables* t);
 int launch_stft400(const FrameParams& p, const Stft400Tables* t, int sm_count, void* stream);
 
+// second-generation fft_points == 400 kernel: warp-independent tiles, mel on mma.sync TF32x3 (ss_kernels_stft400m.cu)
+bool stft400m_supported(const Derived& d, const MelBank& mb);
+struct Stft400mTables;
+int stft400m_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft400mTables** out);
+void stft400m_free_tables(Stft400mTables* t);
+int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count, void* stream);
+
 // fft_points == 2048 register-FFT path for mel_spectrogram (ss_kernels_stft2048.cu)
 bool stft2048_supported(const Derived& d, const MelBank& mb);
 struct Stft2048Tables;

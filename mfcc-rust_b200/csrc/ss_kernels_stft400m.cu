@@ -1,0 +1,523 @@
+// Fused mel-spectrogram kernel for the STFT path with fft_points = 400, second generation
+// (config c4, the Whisper-shaped log-mel: 16 kHz, hop 160, 80 mels):
+//   stream framing (functions.rs:86-160) -> Vorbis window -> real FFT(400) -> |X wnorm|^2 ->
+//   mel filterbank (feature.rs:163-174) -> optional ln(zero_handling) -> time-minor store.
+// Replaces feature::mel_spectrogram{1,2} for this FFT size; functions::stft{1,2} (complex output)
+// stay on the generic kernel.
+//
+// FFT stage as in the first generation (ss_kernels_stft400.cu): 10 lanes x 20 complex points per
+// frame, 200 = 20 x 10 four-step FFT in registers (radix 5 / 2, packed FFMA2 butterflies), three
+// frames per warp.  New here, following k_fast512c:
+//   * the warps are independent (one persistent CTA per SM, no block-wide barrier after the table
+//     load): an item is a run of frames of one row; a warp works through it three frames per FFT
+//     round, the |X|^2 rows go to a private 12-row ring in shared memory and every time 8 more
+//     frames are complete the ring feeds one 8-frame MMA tile;
+//   * the samples of the next round (720 contiguous floats) are fetched with cp.async into the
+//     transpose tile while the current round finishes, so the global-load latency is off the
+//     critical path and the window multiply reads shared memory;
+//   * the filterbank runs on the tensor cores, transposed: mel^T [16 MT filters][8 frames] =
+//     W [16 MT][104 bins] x P^T with mma.sync.m16n8k8 TF32 split 3-way (hi x hi + lo x hi + hi x lo,
+//     ~2^-21 relative), visiting only the 8-bin k-steps a 16-filter group's band touches; the
+//     pre-split weight fragments live in shared memory, one copy per SM;
+//   * the accumulator fragment holds (filter g [+ 8], frames 2t, 2t + 1), i.e. two neighbouring
+//     elements of the time-minor output [row][m][t] (feature.rs:173): they are stored straight from
+//     registers as 8-byte pairs, no staging tile and no __syncthreads.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "fft_ct.cuh"
+#include "ss_internal.h"
+
+namespace ss {
+
+namespace {
+
+using ssfft::sfor;
+
+constexpr int kW = 400, kM = 200, kT = 10, kR1 = 20;
+constexpr int kFpw = 3;                  // frames per warp and FFT round
+constexpr int kTileFrames = 8;           // frames per MMA tile
+constexpr int kRing = 12;                // rows of the |X|^2 ring: one tile plus the 2 frames a round may run ahead, rounded up
+constexpr int kChunkAlign = 24;          // items start at multiples of 24 frames (whole tiles, 96-byte aligned output runs)
+#ifndef SS_STFT400M_WARPS
+#define SS_STFT400M_WARPS 20
+#endif
+constexpr int kMaxWarps = SS_STFT400M_WARPS, kMaxThreads = kMaxWarps * 32;
+constexpr int kSmemBudget = 226 * 1024;
+constexpr int kXchFrame = 202;           // float2 per frame: 20 rows x 10 + 2 (frame stride = 10 mod 16 banks)
+constexpr int kXchFloats = kFpw * kXchFrame * 2;  // 1212
+constexpr int kPs = 104;                 // P row stride: bins 0..100 + zero pad; 104 % 32 == 8 -> conflict-free LDS.64 B fragments
+constexpr int kKs = kPs / 8;             // 13 k-steps of 8 bins
+constexpr int kKsTab = kKs + 1;          // bands are padded to an even number of k-steps
+constexpr int kTileFloats = kRing * kPs + 8;  // + slack for the padded k-step of the last row
+constexpr int kStage = kW + (kFpw - 1) * 160;    // samples of one round when hop = 160 (staging needs hop == 160)
+constexpr int kWarpFloats = kXchFloats + kTileFloats;
+static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
+constexpr int kMtMax = 8;                // nf <= 128
+constexpr int kTwRow = 44;               // floats per lane row of the W200 table (20 float2 + pad)
+// fixed table blob (floats)
+constexpr int kTabTw = 0;                         // [10][kTwRow]
+constexpr int kTabTw400 = kTabTw + kT * kTwRow;   // [200] float2 W400^k
+constexpr int kTabWin = kTabTw400 + 2 * kM;       // [200] float2 window pairs
+constexpr int kTabFixed = kTabWin + 2 * kM;       // then the mel A fragments [blocks][hi, lo][32] float4
+static_assert(kTabTw400 % 4 == 0 && kTabWin % 4 == 0 && kTabFixed % 4 == 0, "table alignment");
+
+__device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
+__device__ __forceinline__ float fast_ln(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.693147180559945309f;
+}
+// x = hi + lo with hi = x truncated to TF32; lo is exact in f32 and the tensor core drops its low 13 bits
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// D += A(16x8, row) * B(8x8, col), TF32 inputs, f32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+        "r"(b0), "r"(b1));
+}
+
+struct Stft400mArgs {
+  FrameParams p;
+  const float* tab;     // fixed tables + mel fragments, copied to shared memory once per CTA
+  int tab_floats;
+  int64_t n_items;      // rows * chunks_per_row; one item per warp at a time
+  int chunks_per_row;
+  int fpi;              // frames per item (a multiple of kChunkAlign)
+  int vec2;             // frames start 8-byte aligned
+  int stage;            // hop == 160 and frames start 16-byte aligned: cp.async staging of whole rounds
+  int pair_ok;          // T_out is even and the output is 8-byte aligned: float2 stores
+  int n_mt;             // m-tiles of 16 filters
+  int ks_lo[kMtMax], ks_n2[kMtMax], mel_base[kMtMax];
+};
+
+// stream sample of the virtual concatenation  mem_in ++ pad(row 0) ++ pad(row 1) ...
+__device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
+  const int64_t memlen = p.N - p.S;
+  if (q < 0) return 0.f;
+  if (q < memlen) return p.mem_in ? p.mem_in[q] : 0.0f;
+  q -= memlen;
+  const int64_t span = p.Tp * (int64_t)p.S;
+  const int64_t r = q / span;
+  const int64_t o = q - r * span;
+  if (r >= p.n_rows || o >= p.row_len) return 0.0f;
+  return p.pcm[r * p.row_stride + o];
+}
+
+__device__ __forceinline__ float2 pair_power(float2 za, float2 zb, float2 w) {
+  // E' = za + conj zb, O' = (za - conj zb)/i, T' = W400^k O'; returns |E'+T'|^2, |E'-T'|^2
+  const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
+  const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
+  const float2 tt = ssfft::cmulf(od, w);
+  const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
+  return make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
+}
+
+__global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* tab_s = smem;
+  float* warp_s = smem + a.tab_floats + (threadIdx.x >> 5) * kWarpFloats;
+  const FrameParams& p = a.p;
+  const int nf = p.nf;
+  for (int i = threadIdx.x; i < a.tab_floats / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(a.tab) + i);
+  // the pad bins of the ring rows are never written again and must be finite
+  for (int i = (threadIdx.x & 31); i < kWarpFloats; i += 32) warp_s[i] = 0.0f;
+  __syncthreads();  // the only block-wide barrier: from here on the warps are independent
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = lane < 30 ? lane : lane - 10;  // lanes 30, 31 shadow lanes 20, 21
+  const int fi = sl / 10, u = sl - fi * 10;     // FFT stage: frame of the round, lane within the frame
+  const int g = lane >> 2, t = lane & 3;        // MMA stage: fragment row group, thread in group
+  const bool real_lane = lane < 30;
+  const bool isz = (u == 0);
+  const int k1B = isz ? 10 : 20 - u;
+  const int kb = isz ? -90 : u;  // k of slots 5..9 is kb + 20 e (u == 0: 10 + 20 (e - 5))
+
+  const float4* twrow = reinterpret_cast<const float4*>(tab_s + kTabTw + u * kTwRow);
+  const float2* tw400 = reinterpret_cast<const float2*>(tab_s + kTabTw400);
+  const float2* win2 = reinterpret_cast<const float2*>(tab_s + kTabWin) + u;
+  const float4* frag_s = reinterpret_cast<const float4*>(tab_s + kTabFixed) + lane;
+
+  float2* xch = reinterpret_cast<float2*>(warp_s) + fi * kXchFrame;
+  float* Pt = warp_s + kXchFloats;  // [8][kPs]
+  const float2* twA = tw400 + u;
+  const float2* twB = tw400 + kb;
+  int plo[5];  // column of the low bin of slots 5..9
+#pragma unroll
+  for (int i = 0; i < 5; ++i) plo[i] = isz ? 10 + 20 * i : 200 - u - 20 * (i + 5);
+
+  const int64_t span = p.Tp * (int64_t)p.S;
+  const int64_t memlen = p.N - p.S;
+  const int c0 = (p.n_pad + 1) * p.S - p.N;  // row-relative position of frame 0's first sample (<= 0)
+  const int T_out = (int)p.T_out, Tc = (int)p.T;
+  const int n_warps = blockDim.x >> 5;
+
+  for (int64_t item = (int64_t)blockIdx.x * n_warps + warp; item < a.n_items; item += (int64_t)gridDim.x * n_warps) {
+    const int64_t row = item / a.chunks_per_row;
+    const int fbeg = (int)(item - row * a.chunks_per_row) * a.fpi;
+    const int fend = min(T_out, fbeg + a.fpi);
+    const float* rowp = p.pcm + row * p.row_stride;
+    float* outp = p.mel_out + row * nf * (int64_t)T_out;
+
+    const int nfr = fend - fbeg;                    // frames of this item
+    const int n_rounds = (nfr + kFpw - 1) / kFpw;
+    float* stage_s = warp_s;                        // the transpose tile doubles as the landing buffer of the next round
+    // a round can be staged when its three frames are whole, in-row and computed
+    auto stageable = [&](int rd) {
+      const int f0 = fbeg + kFpw * rd;
+      const int64_t o0 = (int64_t)f0 * p.S + c0;
+      return a.stage && f0 + kFpw <= Tc && o0 >= 0 && o0 + kStage <= p.row_len;
+    };
+    auto issue_stage = [&](int rd) {
+      const float* src = rowp + (int64_t)(fbeg + kFpw * rd) * p.S + c0;
+      for (int i = lane; i < kStage / 4; i += 32) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_s + 4 * i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * i));
+      }
+      asm volatile("cp.async.commit_group;");
+    };
+    bool staged = n_rounds > 0 && stageable(0);
+    if (staged) issue_stage(0);
+    int tile = 0;  // next 8-frame tile to run through the filterbank
+
+#pragma unroll 1
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      {
+        const int lf = kFpw * rd + fi;      // frame within the item
+        const int tf = fbeg + lf;           // this lane group's output frame
+        // frames in [T, T_out) are the reference's zero tail; frames >= fend are never stored
+        const bool computed = tf < Tc;
+        float* Pf = Pt + (lf % kRing) * kPs;
+
+        // ---- framing + window: v[j] = (x w)[2m] + i (x w)[2m+1], m = u + 10 j
+        float2 v[kR1];
+        if (staged) {
+          asm volatile("cp.async.wait_group 0;");
+          __syncwarp();
+          const float* sx = stage_s + fi * 160 + 2 * u;
+          sfor<0, kR1>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            v[j] = __fmul2_rn(*reinterpret_cast<const float2*>(sx + 20 * j), win2[10 * j]);
+          });
+          __syncwarp();  // the buffer is the transpose tile again
+        } else {
+          const int64_t o0 = (int64_t)tf * p.S + c0;  // first sample of the frame, relative to the row start
+          if (!computed) {
+            sfor<0, kR1>([&](auto jj) { v[decltype(jj)::value] = make_float2(0.f, 0.f); });
+          } else if (o0 >= 0 && o0 + kW <= p.row_len) {
+            const float* px = rowp + o0 + 2 * u;
+            if (a.vec2) {
+              sfor<0, kR1>([&](auto jj) {
+                constexpr int j = decltype(jj)::value;
+                const float2 x = __ldg(reinterpret_cast<const float2*>(px + 20 * j));
+                const float2 w = win2[10 * j];
+                v[j] = __fmul2_rn(x, w);
+              });
+            } else {
+              sfor<0, kR1>([&](auto jj) {
+                constexpr int j = decltype(jj)::value;
+                const float2 w = win2[10 * j];
+                v[j] = make_float2(__ldg(px + 20 * j) * w.x, __ldg(px + 20 * j + 1) * w.y);
+              });
+            }
+          } else {  // frame touches the overlap memory / previous row / zero padding
+            const int64_t q0 = memlen + row * span + o0 + 2 * u;
+            sfor<0, kR1>([&](auto jj) {
+              constexpr int j = decltype(jj)::value;
+              const float2 w = win2[10 * j];
+              const int64_t q = q0 + 20 * j;
+              // samples of this row beyond row_len are zero padding; earlier positions come from the stream
+              const int64_t o = o0 + 2 * u + 20 * j;
+              const float xa = o >= 0 ? (o < p.row_len ? rowp[o] : 0.f) : stream_at(p, q);
+              const float xb = o + 1 >= 0 ? (o + 1 < p.row_len ? rowp[o + 1] : 0.f) : stream_at(p, q + 1);
+              v[j] = make_float2(xa * w.x, xb * w.y);
+            });
+          }
+        }
+        // ---- stage 1: 20-point FFT over j, in registers
+        ssfft::fft_5x2<kR1>(v);
+        // ---- twiddle W200^{u k1} and transpose
+        sfor<0, kR1 / 2>([&](auto kk) {
+          constexpr int k1 = 2 * decltype(kk)::value;
+          const float4 w = twrow[k1 / 2];
+          float2 y0 = v[k1], y1 = v[k1 + 1];
+          if constexpr (k1 > 0) y0 = ssfft::cmulf(y0, make_float2(w.x, w.y));
+          y1 = ssfft::cmulf(y1, make_float2(w.z, w.w));
+          xch[k1 * kT + u] = y0;
+          xch[(k1 + 1) * kT + u] = y1;
+        });
+        __syncwarp();
+        float2 gA[kT], gB[kT];
+        {
+          const float4* rA = reinterpret_cast<const float4*>(xch + u * kT);
+          const float4* rB = reinterpret_cast<const float4*>(xch + k1B * kT);
+          sfor<0, kT / 2>([&](auto tt) {
+            constexpr int i = decltype(tt)::value;
+            const float4 xa = rA[i], xb = rB[i];
+            gA[2 * i] = make_float2(xa.x, xa.y); gA[2 * i + 1] = make_float2(xa.z, xa.w);
+            gB[2 * i] = make_float2(xb.x, xb.y); gB[2 * i + 1] = make_float2(xb.z, xb.w);
+          });
+        }
+        __syncwarp();  // the transpose tile is free: it receives the samples of the next round
+        staged = rd + 1 < n_rounds && stageable(rd + 1);
+        if (staged) issue_stage(rd + 1);
+        // ---- stage 2: 10-point FFTs over the lane index.  g?[k2] = Z[k1? + 20 k2]
+        ssfft::fft_5x2<kT>(gA);
+        ssfft::fft_5x2<kT>(gB);
+
+        // ---- real-FFT post-processing, |X|^2 of the bins a mel filter can reach (<= 100).
+        // u != 0: slot e pairs Z[u+20e] (gA[e]) with Z[200-(u+20e)] = gB[9-e].
+        // u == 0: groups 0 and 10 mirror onto themselves: e=0 -> k=0; e=1..4 -> (gA[e], gA[10-e]);
+        //         e=5..9 -> (gB[e-5], gB[14-e]) with k = 10 + 20 (e-5); bin 100 = |gA[5]|^2 below.
+        if (real_lane) {
+          float* pA = Pf + u;
+          sfor<0, 10>([&](auto ee) {
+            constexpr int e = decltype(ee)::value;
+            float2 za, zb;
+            if constexpr (e == 0) {
+              za = gA[0];
+              zb = isz ? gA[0] : gB[9];
+            } else if constexpr (e < 5) {
+              za = gA[e];
+              zb = isz ? gA[10 - e] : gB[9 - e];
+            } else {
+              za = isz ? gB[e - 5] : gA[e];
+              zb = isz ? gB[14 - e] : gB[9 - e];
+            }
+            const float2 m = pair_power(za, zb, (e < 5 ? twA : twB)[20 * e]);
+            if constexpr (e < 5) pA[20 * e] = m.x;        // bin u + 20 e <= 89
+            else Pf[plo[e - 5]] = isz ? m.x : m.y;        // the bin of the pair that is <= 100
+          });
+          if (isz)  // X[100] = conj Z[100]; x4 to match the pairs; bins 101..103 stay zero
+            *reinterpret_cast<float4*>(Pf + 100) = make_float4(4.0f * fmaf(gA[5].x, gA[5].x, gA[5].y * gA[5].y), 0.f, 0.f, 0.f);
+        }
+      }
+      // a tile is complete once 8 more frames exist (or the item ends)
+      const int produced = min(nfr, kFpw * (rd + 1));
+      if (produced < kTileFrames * (tile + 1) && rd + 1 < n_rounds) continue;
+      __syncwarp();
+
+      // ---- mel filterbank on the tensor cores (feature.rs:163-174), transposed:
+      //   mel^T [16 MT filters][8 frames] = W [16 MT][104 bins] (banded, pre-split on the host) x P^T,
+      // contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1 (one 8-byte load).
+      // The accumulator holds (filter 16 mt + g [+ 8], frames tile_f0 + 2t [+ 1]): pairs along the
+      // time-minor output [row][m][t].
+#pragma unroll 1
+      for (; kTileFrames * tile < produced && (kTileFrames * (tile + 1) <= produced || rd + 1 == n_rounds); ++tile) {
+        const int fa = fbeg + kTileFrames * tile + 2 * t;  // first frame of this lane's pair
+        const bool va = fa < fend, vb = fa + 1 < fend;
+        const float* prow = Pt + ((kTileFrames * tile + g) % kRing) * kPs + 2 * t;
+#pragma unroll 1
+        for (int mt = 0; mt < a.n_mt; ++mt) {
+          float accB[4] = {0.f, 0.f, 0.f, 0.f}, accS[4] = {0.f, 0.f, 0.f, 0.f}, accT[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* pp = prow + 8 * a.ks_lo[mt];
+          const float4* ap = frag_s + a.mel_base[mt] * 64;
+          // two k-steps per iteration (the band is padded to an even count with zero-weight blocks)
+#pragma unroll 1
+          for (int n2 = a.ks_n2[mt]; n2 > 0; --n2) {
+            const float2 pv0 = *reinterpret_cast<const float2*>(pp);
+            const float2 pv1 = *reinterpret_cast<const float2*>(pp + 8);
+            const float4 h0 = ap[0], l0 = ap[32], h1 = ap[64], l1 = ap[96];
+            pp += 16;
+            ap += 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float2 pv = h ? pv1 : pv0;
+              const float4 wh = h ? h1 : h0, wl = h ? l1 : l0;
+              uint32_t bh0, bl0, bh1, bl1;
+              split_tf32(pv.x, bh0, bl0);
+              split_tf32(pv.y, bh1, bl1);
+              mma_tf32(accB, wh, bh0, bh1);  // hi x hi
+              mma_tf32(accS, wl, bh0, bh1);  // lo x hi
+              mma_tf32(accT, wh, bl0, bl1);  // hi x lo
+            }
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int f = 16 * mt + g + 8 * hh;
+            float m0 = accB[2 * hh] + (accS[2 * hh] + accT[2 * hh]);
+            float m1 = accB[2 * hh + 1] + (accS[2 * hh + 1] + accT[2 * hh + 1]);
+            if (p.log_mode) {
+              m0 = fast_ln(zero_handling(m0));
+              m1 = fast_ln(zero_handling(m1));
+            }
+            if (f < nf) {
+              float* dst = outp + (int64_t)f * T_out + fa;
+              if (a.pair_ok && vb) {
+                *reinterpret_cast<float2*>(dst) = make_float2(m0, m1);
+              } else {
+                if (va) dst[0] = m0;
+                if (vb) dst[1] = m1;
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();  // ring rows are rewritten by later rounds
+    }
+  }
+}
+
+// round-to-nearest (ties away) conversion f32 -> TF32, as cvt.rna.tf32.f32
+static float tf32_rna(float x) {
+  uint32_t b;
+  std::memcpy(&b, &x, 4);
+  b = (b + 0x1000u) & 0xffffe000u;  // the weights are finite and far from overflow
+  float r;
+  std::memcpy(&r, &b, 4);
+  return r;
+}
+
+struct FragTables400 {
+  int n_mt = 0;
+  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
+  std::vector<float> mel;  // [blocks][hi, lo][32][4]
+};
+
+// A fragments of mma.m16n8k8 (row-major 16 filters x 8 bins) for lane (g, t): rows g, g + 8;
+// contraction slot s <-> bin 8 ks + 2 (s % 4) + s / 4.  Only the k-steps inside each 16-filter
+// group's band are stored, padded to an even count.
+static bool build_frags(const Derived& d, const MelBank& mb, float pscale, FragTables400* ft) {
+  const int nf = d.nf;
+  if (mb.max_bin > 100 || nf > 16 * kMtMax || nf < 1) return false;
+  const int MT = (nf + 15) / 16, ncol = 8 * kKsTab;
+  ft->n_mt = MT;
+  std::vector<float> dense((size_t)16 * MT * ncol, 0.f);  // [filter][bin]
+  for (int f = 0; f < nf; ++f)
+    for (int i = 0; i < mb.len[f]; ++i) dense[(size_t)f * ncol + mb.start[f] + i] = mb.w[mb.wofs[f] + i] * pscale;
+  int n_blocks = 0;
+  ft->mel.clear();
+  for (int mt = 0; mt < MT; ++mt) {
+    int lo = kKs, hi = 0;
+    for (int ks = 0; ks < kKs; ++ks) {
+      bool any = false;
+      for (int r = 0; r < 16; ++r)
+        for (int c = 0; c < 8; ++c) any = any || dense[(size_t)(16 * mt + r) * ncol + 8 * ks + c] != 0.f;
+      if (any) { lo = std::min(lo, ks); hi = std::max(hi, ks + 1); }
+    }
+    ft->ks_lo[mt] = 0;
+    ft->ks_n2[mt] = 0;
+    ft->mel_base[mt] = n_blocks;
+    if (hi <= lo) continue;  // 16 empty filters: no k-steps, the outputs are exact zeros
+    const int n2 = (hi - lo + 1) / 2;
+    ft->ks_lo[mt] = lo;
+    ft->ks_n2[mt] = n2;
+    for (int ks = lo; ks < lo + 2 * n2; ++ks, ++n_blocks) {
+      const size_t o = ft->mel.size();
+      ft->mel.resize(o + 2 * 32 * 4, 0.f);
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        for (int i = 0; i < 4; ++i) {
+          const int r = g + 8 * (i & 1), s = t + 4 * (i >> 1);
+          const float v = dense[(size_t)(16 * mt + r) * ncol + 8 * ks + 2 * (s & 3) + (s >> 2)];
+          const float h = tf32_rna(v);
+          ft->mel[o + lane * 4 + i] = h;
+          ft->mel[o + (32 + lane) * 4 + i] = v - h;
+        }
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+struct Stft400mTables {
+  float* d_tab = nullptr;
+  int tab_floats = 0;
+  int n_mt = 0;
+  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
+};
+
+bool stft400m_supported(const Derived& d, const MelBank& mb) {
+  if (d.W != kW || !d.stft_ok) return false;
+  FragTables400 ft;
+  if (!build_frags(d, mb, 1.0f, &ft)) return false;
+  const size_t fixed = (size_t)(kTabFixed + ft.mel.size()) * sizeof(float);
+  return fixed + 4 * kWarpFloats * sizeof(float) <= (size_t)kSmemBudget;
+}
+
+int stft400m_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft400mTables** out) {
+  FragTables400 ft;
+  const float pscale = 0.25f * d.wnorm * d.wnorm;  // (wnorm / 2)^2: the 1/2 of E, O and the STFT normalisation (functions.rs:166-169)
+  if (!build_frags(d, mb, pscale, &ft)) return (int)cudaErrorInvalidValue;
+  std::vector<float> h(kTabFixed, 0.f);
+  const double pi = 3.14159265358979323846264338327950288;
+  for (int u = 0; u < kT; ++u)
+    for (int k1 = 0; k1 < kR1; ++k1) {
+      const double ang = -2.0 * pi * (double)(u * k1) / (double)kM;
+      h[kTabTw + u * kTwRow + 2 * k1] = (float)std::cos(ang);
+      h[kTabTw + u * kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
+    }
+  for (int k = 0; k < kM; ++k) {
+    const double ang = -2.0 * pi * (double)k / (double)kW;
+    h[kTabTw400 + 2 * k] = (float)std::cos(ang);
+    h[kTabTw400 + 2 * k + 1] = (float)std::sin(ang);
+  }
+  for (int n = 0; n < kW; ++n) h[kTabWin + n] = window[n];
+  h.insert(h.end(), ft.mel.begin(), ft.mel.end());
+  Stft400mTables* t = new Stft400mTables;
+  t->tab_floats = (int)h.size();
+  t->n_mt = ft.n_mt;
+  for (int i = 0; i < kMtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_n2[i] = ft.ks_n2[i]; t->mel_base[i] = ft.mel_base[i]; }
+  cudaError_t e = cudaMalloc(&t->d_tab, h.size() * sizeof(float));
+  if (e != cudaSuccess) { delete t; return (int)e; }
+  e = cudaMemcpy(t->d_tab, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(t->d_tab); delete t; return (int)e; }
+  *out = t;
+  return 0;
+}
+
+void stft400m_free_tables(Stft400mTables* t) {
+  if (!t) return;
+  if (t->d_tab) cudaFree(t->d_tab);
+  delete t;
+}
+
+// mel_spectrogram only (p.mel_out set, p.stft_out null); returns -1000 if the shape is declined
+int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count, void* stream) {
+  if (p.N != kW || !p.mel_out || p.stft_out || p.T_out < 1 || p.T_out > (1LL << 31) - 64) return -1000;
+  Stft400mArgs a;
+  a.p = p;
+  a.tab = t->d_tab;
+  a.tab_floats = t->tab_floats;
+  a.n_mt = t->n_mt;
+  for (int i = 0; i < kMtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
+  const size_t fixed = (size_t)t->tab_floats * sizeof(float);
+  const int n_warps = (int)std::min<size_t>(kMaxWarps, (kSmemBudget - fixed) / (kWarpFloats * sizeof(float)));
+  if (n_warps < 4) return -1000;
+  const int64_t warps_resident = (int64_t)sm_count * n_warps;
+  // items: runs of whole tiles, 24-frame aligned, small enough that every resident warp gets a few
+  int64_t fpi = 20 * kChunkAlign;
+  auto items = [&](int64_t f) { return p.n_rows * ((p.T_out + f - 1) / f); };
+  while (fpi > kChunkAlign && items(fpi) < 4 * warps_resident) fpi /= 2;
+  fpi = (fpi + kChunkAlign - 1) / kChunkAlign * kChunkAlign;
+  a.fpi = (int)fpi;
+  a.chunks_per_row = (int)((p.T_out + fpi - 1) / fpi);
+  a.n_items = p.n_rows * (int64_t)a.chunks_per_row;
+  a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
+  // whole rounds can be staged with 16-byte cp.async when every round starts 16-byte aligned
+  const int64_t c0 = (int64_t)(p.n_pad + 1) * p.S - p.N;
+  a.stage = p.S == 160 && (p.row_stride % 4 == 0) && (((c0 % 4) + 4) % 4 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
+  a.pair_ok = (p.T_out % 2 == 0) && (reinterpret_cast<uintptr_t>(p.mel_out) % 8 == 0);
+  const size_t smem = fixed + (size_t)n_warps * kWarpFloats * sizeof(float);
+  const int64_t grid = std::min<int64_t>((a.n_items + n_warps - 1) / n_warps, (int64_t)sm_count);
+  if (grid <= 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(k_stft400m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_stft400m<<<(unsigned)grid, n_warps * 32, smem, (cudaStream_t)stream>>>(a);
+  count_launch();
+  note_kernel("k_stft400m");
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ss
