@@ -80,7 +80,6 @@ struct DeviceCtx {
   int sm_count = 148;
   DevBuf tables;  // one allocation holding every device table
   DevTables tab;
-  Fast512Tables* fast512 = nullptr;
   Fast512bTables* fast512b = nullptr;
   Fast512cTables* fast512c = nullptr;
   Stft400Tables* stft400 = nullptr;
@@ -101,7 +100,6 @@ struct ss_plan {
   std::vector<float> window, dct;
   std::vector<float> analysis_mem;  // [W-H], config.rs:126,162
   std::vector<ss::DeviceCtx> devs;
-  bool fast512 = false;
   bool fast512b = false;
   bool fast512c = false;
   bool stft400 = false;
@@ -148,10 +146,6 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   dc->tab.n_stages = pl->fft.n_stages;
   for (int i = 0; i < kMaxStages; ++i) dc->tab.radix[i] = pl->fft.radix[i];
   for (auto& ln : dc->lanes) SS_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-  if (pl->fast512) {
-    int e = fast512_build_tables(pl->d, pl->mb, &dc->fast512);
-    if (e) return cuda_fail((cudaError_t)e, "fast512_build_tables");
-  }
   if (pl->fast512b) {
     int e = fast512b_build_tables(pl->d, pl->mb, &dc->fast512b);
     if (e) return cuda_fail((cudaError_t)e, "fast512b_build_tables");
@@ -211,16 +205,13 @@ static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const f
   p.tab = dc->tab;
   bool cmvn_done = false;
   int e;
-  const bool use_fast = (pl->fast512 || pl->fast512b || pl->fast512c) &&
-                        !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  // SS_FAST512_GEN=1|2 selects an older generation of the n_fft = 512 kernel for A/B measurements
-  // (1: 8 lanes x 32 points, CUDA-core epilogue; 2: 16 lanes x 16 points, CUDA-core epilogue;
-  // default 3: 16 lanes x 16 points, tensor-core mel + DCT)
+  const bool use_fast = (pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  // SS_FAST512_GEN=2 selects the previous generation of the n_fft = 512 kernel for A/B measurements
+  // (2: CUDA-core mel program + DCT, CTA per clip; default 3: tensor-core mel + DCT, warp per item)
   static const int gen = getenv("SS_FAST512_GEN") ? atoi(getenv("SS_FAST512_GEN")) : 3;
   if (use_fast) {
-    if (pl->fast512c && (gen >= 3 || !(pl->fast512 || pl->fast512b))) e = launch_fast512c(p, dc->fast512c, dc->sm_count, stream);
-    else if (pl->fast512b && (gen == 2 || !pl->fast512)) e = launch_fast512b(p, dc->fast512b, dc->sm_count, stream);
-    else e = launch_fast512(p, dc->fast512, dc->sm_count, stream);
+    if (pl->fast512c && (gen >= 3 || !pl->fast512b)) e = launch_fast512c(p, dc->fast512c, dc->sm_count, stream);
+    else e = launch_fast512b(p, dc->fast512b, dc->sm_count, stream);
     cmvn_done = true;  // the fast path normalises in-kernel or enqueues its own cmvn pass
     if (e == -1000) {  // the fast path declined this shape; fall through to the generic kernel
       cmvn_done = false;
@@ -469,7 +460,6 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   build_dct(pl->d, &pl->dct);
   pl->fft_ok = pl->d.W <= (1 << 20) && build_fft_plan((int)pl->d.W, &pl->fft);
   if (pl->d.stft_ok) pl->analysis_mem.assign((size_t)(pl->d.W - pl->d.H), 0.f);  // config.rs:162
-  pl->fast512 = pl->fft_ok && fast512_supported(pl->d, pl->mb);
   pl->fast512b = pl->fft_ok && fast512b_supported(pl->d, pl->mb);
   pl->fast512c = pl->fft_ok && fast512c_supported(pl->d, pl->mb);
   pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
@@ -523,7 +513,6 @@ void ss_plan_destroy(ss_plan* pl) {
     }
     dc.tables.release();
     dc.dev_scratch.release();
-    if (dc.fast512) fast512_free_tables(dc.fast512);
     if (dc.fast512b) fast512b_free_tables(dc.fast512b);
     if (dc.fast512c) fast512c_free_tables(dc.fast512c);
     if (dc.stft400) stft400_free_tables(dc.stft400);
@@ -547,7 +536,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->num_cepstral = d.nc;
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
-  info->fast_path = (pl->fast512 || pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  info->fast_path = (pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
   info->fast_stft = (pl->stft400 || pl->stft400m || pl->stft2048) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }

@@ -111,13 +111,6 @@ struct FrameParams {
 // ---- kernel launchers (each returns cudaError_t as int; all enqueue on `stream`) ---------
 int launch_frames_generic(const FrameParams& p, void* stream);
 int launch_stft_mem_update(const FrameParams& p, void* stream);
-// n_fft == 512 register-FFT path for speechpy framing (ss_kernels_fast512.cu)
-bool fast512_supported(const Derived& d, const MelBank& mb);
-struct Fast512Tables;  // opaque device tables
-int fast512_build_tables(const Derived& d, const MelBank& mb, Fast512Tables** out);
-void fast512_free_tables(Fast512Tables* t);
-int launch_fast512(const FrameParams& p, const Fast512Tables* t, int sm_count, void* stream);
-
 // second-generation n_fft == 512 kernel: 16 lanes x 16 points per frame (ss_kernels_fast512b.cu)
 bool fast512b_supported(const Derived& d, const MelBank& mb);
 struct Fast512bTables;

@@ -4,7 +4,7 @@
 // Replaces feature::{mfe, lmfe, mfcc} (feature.rs:99-245) + processing::{stack_frames,
 // power_spectrum, cmvn} (processing.rs:65-181,265-300) for this FFT size.
 //
-// Versus the first generation (ss_kernels_fast512.cu: 8 lanes x 32 points per frame, 128
+// Versus the first generation (removed; 8 lanes x 32 points per frame, 128
 // registers, 15 warps/SM) this kernel uses 16 lanes x 16 points per frame:
 //   * real FFT(512) = complex FFT(256) of z[m] = x[2m] + i x[2m+1] + split; 256 = 16 x 16:
 //     16-point register FFT (compile-time twiddles, zero-padded inputs pruned), W256^{u k1}

@@ -101,6 +101,7 @@ struct FastArgsC {
   int fpi;                 // frames per item (a multiple of the tile height, or >= T)
   int fuse_cmvn;           // 0 none, 1 mean, 2 mean+var: one warp takes the whole clip and normalises it in place
   int vec2;                // every frame start is 8-byte aligned
+  int stage;               // > 0: 16-byte chunks per staged pair (frame starts 16-byte aligned, S + L fits the buffer)
   int nf_even;             // nf is even: float2 stores of the mel rows
   int ks_lo[kMtMax], ks_n2[kMtMax];  // first k-step (8 bins each) and number of k-step pairs of the band, per m-tile of 16 filters
 };
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
   sincospif(-(float)u / 256.0f, &wu.y, &wu.x);
 
   float2* xch = reinterpret_cast<float2*>(warp_s) + fi * kXchFrame;
+  float* stage_s = warp_s + kXchFloats / 2;   // landing buffer of the next pair's samples
   float* Pt = warp_s + kXchFloats;            // [kTileRows][kPs]
   float* e_s = Pt + kTileRows * kPs;          // [kTileRows] frame energies
   // does this lane's last column group (j = JMAX - 1) lie inside the frame?
@@ -145,7 +147,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
   for (int64_t item = (int64_t)blockIdx.x * n_warps + warp; item < a.n_items; item += (int64_t)gridDim.x * n_warps) {
     const int64_t clip = item / a.chunks_per_clip;
     const int chunk = (int)(item - clip * a.chunks_per_clip);
-    const float* rowp = p.pcm + clip * p.row_stride + 2 * u;
+    const float* rowp0 = p.pcm + clip * p.row_stride;
+    const float* rowp = rowp0 + 2 * u;
+    bool staged = false;  // the first pair of an item is loaded directly
     const int64_t obase = clip * T;  // first output row of the clip
     const int fbeg = chunk * a.fpi;
     const int fend = min(T, fbeg + a.fpi);
@@ -161,15 +165,30 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
 
         // ---- framing: v[j] = x[2m] + i x[2m+1], m = u + 16 j; zero beyond L (processing.rs:147-156).
         // An out-of-range frame of the last pair re-reads frame T-1 (in bounds); it is never stored.
+        // A staged pair was fetched with cp.async into the upper half of the transpose tile while
+        // the previous pair was finishing (see below).
         float2 v[16];
-        {
+        if (staged) {
+          asm volatile("cp.async.wait_group 0;");
+          __syncwarp();
+          const float* sx = stage_s + fi * p.S + 2 * u;
+          sfor<0, 16>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            if constexpr (j >= JMAX) {
+              v[j] = make_float2(0.0f, 0.0f);
+            } else if constexpr (!EXACT) {
+              v[j].x = (2 * u + 32 * j < L) ? sx[32 * j] : 0.0f;
+              v[j].y = (2 * u + 32 * j + 1 < L) ? sx[32 * j + 1] : 0.0f;
+            } else if constexpr (j == JMAX - 1) {
+              v[j].x = last0 ? sx[32 * j] : 0.0f;
+              v[j].y = last1 ? sx[32 * j + 1] : 0.0f;
+            } else {
+              v[j] = *reinterpret_cast<const float2*>(sx + 32 * j);
+            }
+          });
+          __syncwarp();  // the buffer is part of the transpose tile again
+        } else {
           const float* px = rowp + (int64_t)(valid ? fr : T - 1) * p.S;
-          // pull the samples of the next pair into the L1 while this one is transformed (one 128-byte
-          // line per lane; the 60 % that overlaps the current pair is already there)
-          if (tile_f0 + 2 * pr + 3 < fend) {
-            const float* nx = rowp - 2 * u + (int64_t)(tile_f0 + 2 * pr + 2) * p.S + 32 * lane;
-            if (32 * lane < p.S + L) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-          }
           sfor<0, 16>([&](auto jj) {
             constexpr int j = decltype(jj)::value;
             if constexpr (j >= JMAX) {
@@ -209,7 +228,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
             gg[2 * i + 1] = make_float2(x.z, x.w);
           });
         }
-        __syncwarp();  // the transpose tile is rewritten by the next pair
+        __syncwarp();  // the transpose tile is free
+        // ---- request the samples of the next pair (S + L contiguous floats) while this pair is
+        // finished: 16-byte cp.async into the upper half of the tile (the lower half holds the
+        // log-mel tile during the epilogue).  Only whole, in-row pairs are staged.
+        {
+          const int nf0 = tile_f0 + 2 * pr + 2;  // first frame of the next pair
+          staged = a.stage && nf0 + 1 < fend;
+          if (staged) {
+            const float* src = rowp0 + (int64_t)nf0 * p.S;
+            for (int i = lane; i < a.stage; i += 32) {
+              const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_s + 4 * i);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * i));
+            }
+            asm volatile("cp.async.commit_group;");
+          }
+        }
         // ---- stage 2: 16-point FFT over the lane index.  gg[k2] = Z[u + 16 k2]
         ssfft::fft_pow2<16>(gg);
 
@@ -357,24 +391,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
     }
 
     // ---- per-clip CMVN (processing.rs:265-300): the warp re-reads the [T][nc] block it has just
-    // written (L2-resident), lane = (row parity, column), eight rows in flight per lane: column mean
+    // written (L2-resident), lane = (row parity, column), 16 rows in flight per lane: column mean
     // and variance of the column (shifted by its first row: a one-sweep, cancellation-safe form of the
     // reference's mean-subtract-then-std), then normalise in place.
     if (a.fuse_cmvn) {
       __syncwarp();
-      float* blk = p.mfcc + obase * nc;
       const int c = lane & 15, r0 = lane >> 4;
       const bool act = c < nc;
-      const float* col = blk + (act ? c : 0);
+      float* col = p.mfcc + obase * nc + (act ? c : 0);
       const float K = __ldcg(col);  // row 0 of the column
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int rb = r0; rb < T; rb += 16) {
-        float x[8];
+      for (int rb = r0; rb < T; rb += 32) {
+        float x[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (rb + 2 * j < T) ? __ldcg(col + (rb + 2 * j) * nc) : K;
+        for (int j = 0; j < 16; ++j) x[j] = (rb + 2 * j < T) ? __ldcg(col + (rb + 2 * j) * nc) : K;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float d = x[j] - K;
           s1 += d;
           s2 = fmaf(d, d, s2);
@@ -388,13 +421,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
       if (a.fuse_cmvn == 2) inv = 1.0f / (sqrtf(fmaxf(s2 - s1 * s1 * invT, 0.f) * invT) + kCmvnEps);
       if (act) {
 #pragma unroll 1
-        for (int rb = r0; rb < T; rb += 16) {
-          float x[8];
+        for (int rb = r0; rb < T; rb += 32) {
+          float x[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = (rb + 2 * j < T) ? __ldcg(col + (rb + 2 * j) * nc) : 0.f;
+          for (int j = 0; j < 16; ++j) x[j] = (rb + 2 * j < T) ? __ldcg(col + (rb + 2 * j) * nc) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (rb + 2 * j < T) blk[(rb + 2 * j) * nc + c] = (x[j] - mean) * inv;
+          for (int j = 0; j < 16; ++j)
+            if (rb + 2 * j < T) col[(rb + 2 * j) * nc] = (x[j] - mean) * inv;
         }
       }
     }
@@ -560,6 +593,14 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   }
   a.n_items = p.n_rows * a.chunks_per_clip;
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
+  // cp.async staging of whole pairs: 16-byte aligned frame starts, the pair's S + L samples (rounded up to
+  // 16 bytes) fit the upper half of the transpose tile and stay inside the row for every staged pair
+  {
+    const int chunks = (p.S + p.L + 3) / 4;
+    const bool fits = 4 * chunks <= kXchFloats / 2 && (p.T - 2) * (int64_t)p.S + 4 * chunks <= p.row_len;
+    const bool aligned = (p.S % 4 == 0) && (p.row_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
+    a.stage = (fits && aligned && p.T >= 2) ? chunks : 0;
+  }
   auto al8 = [](const float* q) { return reinterpret_cast<uintptr_t>(q) % 8 == 0; };
   a.nf_even = (p.nf % 2 == 0) && al8(p.mfe) && al8(p.lmfe) && al8(p.ssc);
   const bool ssc = p.ssc != nullptr;

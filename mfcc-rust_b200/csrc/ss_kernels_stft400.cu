@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, SS_STFT400_MINB) k_stft400(const Stf
     }
     __syncwarp();
 
-    // ---- banded mel program (see ss_kernels_fast512.cu) -> output tile [nf][24]
+    // ---- banded mel program (see ss_kernels_fast512b.cu) -> output tile [nf][24]
     {
       float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
       float* out_col = stash + warp * kFpw + fi;
@@ -263,7 +263,7 @@ struct MelProgram400 {
   std::vector<float> w;
 };
 
-// same construction as fast512's mel program, for 10 lanes and bins [0, 104)
+// same construction as the mel program of ss_kernels_fast512b.cu, for 10 lanes and bins [0, 104)
 static bool build_program(const Derived& d, const MelBank& mb, float pscale, MelProgram400* mp) {
   const int nf = d.nf;
   if (mb.max_bin > 100) return false;
