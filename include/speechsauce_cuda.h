@@ -155,6 +155,11 @@ int ss_stack_frames(const float* in, int64_t n, int64_t frame_len, int64_t frame
                     int zero_padding, uint32_t flags, float* out, int64_t* numframes);
 /* processing::power_spectrum (processing.rs:179-181): (1/n_fft)*|rfft(zero-padded row)|, out [rows][n_fft/2+1] */
 int ss_power_spectrum(const float* frames, int64_t rows, int64_t frame_len, int64_t n_fft, float* out);
+/* processing::log_power_spectrum (processing.rs:194-214; private and unused in the reference):
+ * 10 log10 of the power spectrum, -200 below 1e-20; with normalize != 0 the LAST value above the
+ * threshold in row-major order (not the maximum: the reference's `mx` is overwritten by every
+ * element) is subtracted from every element.  out [rows][n_fft/2+1] */
+int ss_log_power_spectrum(const float* frames, int64_t rows, int64_t frame_len, int64_t n_fft, int normalize, float* out);
 /* processing::cmvn (processing.rs:265-300) on one [rows][cols] matrix / a batch of them */
 int ss_cmvn(const float* in, int64_t rows, int64_t cols, int variance_normalization, float* out);
 int ss_cmvn_batch(const float* in, int64_t n_mats, int64_t rows, int64_t cols,
@@ -194,6 +199,8 @@ int ss_stack_frames_dev(void* cuda_stream, const float* d_in, int64_t n, int64_t
                         int64_t numframes);
 int ss_power_spectrum_dev(void* cuda_stream, const float* d_frames, int64_t rows, int64_t frame_len,
                           int64_t n_fft, float* d_out);
+int ss_log_power_spectrum_dev(void* cuda_stream, const float* d_frames, int64_t rows, int64_t frame_len,
+                              int64_t n_fft, int normalize, float* d_out);
 int ss_cmvn_dev(void* cuda_stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols,
                 int variance_normalization, float* d_out);
 

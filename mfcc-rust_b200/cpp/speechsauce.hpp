@@ -213,6 +213,13 @@ inline Array2 power_spectrum(View2 frames, size_t fft_points) {
   check(ss_power_spectrum(frames.data, (int64_t)frames.rows, (int64_t)frames.cols, (int64_t)fft_points, out.v.data()));
   return out;
 }
+// processing.rs:194 (private in the reference)
+inline Array2 log_power_spectrum(View2 frames, size_t fft_points, bool normalize) {
+  Array2 out(frames.rows, fft_points / 2 + 1);
+  check(ss_log_power_spectrum(frames.data, (int64_t)frames.rows, (int64_t)frames.cols, (int64_t)fft_points, normalize ? 1 : 0,
+                              out.v.data()));
+  return out;
+}
 // processing.rs:265
 inline Array2 cmvn(View2 vec, bool variance_normalization) {
   Array2 out(vec.rows, vec.cols);

@@ -927,6 +927,37 @@ int ss_power_spectrum(const float* frames, int64_t rows, int64_t L, int64_t n_ff
   return SS_OK;
 }
 
+// processing::log_power_spectrum (processing.rs:194-214): private and unused in the reference
+static thread_local DevBuf g_logps_scratch;
+int ss_log_power_spectrum_dev(void* stream, const float* d_frames, int64_t rows, int64_t L, int64_t n_fft, int normalize,
+                              float* d_out) {
+  int rc = ss_power_spectrum_dev(stream, d_frames, rows, L, n_fft, d_out);
+  if (rc || rows == 0) return rc;
+  if ((rc = g_logps_scratch.reserve(16))) return rc;
+  int e = launch_log_power(d_out, rows * (n_fft / 2 + 1), normalize, g_logps_scratch.p, stream);
+  if (e) return cuda_fail((cudaError_t)e, "log_power_spectrum launch");
+  return SS_OK;
+}
+
+int ss_log_power_spectrum(const float* frames, int64_t rows, int64_t L, int64_t n_fft, int normalize, float* out) {
+  if (!frames || !out) return fail(SS_ERR_INVALID_ARG, "null argument");
+  if (rows < 0 || L <= 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  if (L > n_fft) return fail(SS_ERR_INVALID_ARG, "frame_len %lld > n_fft %lld (ndrustfft panics, processing.rs:159)", (long long)L, (long long)n_fft);
+  if (rows == 0) return SS_OK;
+  DefaultCtx* c;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  const int64_t F = n_fft / 2 + 1;
+  if ((rc = c->a.reserve((size_t)rows * L * 4))) return rc;
+  if ((rc = c->b.reserve((size_t)rows * F * 4))) return rc;
+  SS_CUDA(cudaMemcpyAsync(c->a.p, frames, (size_t)rows * L * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = ss_log_power_spectrum_dev(c->stream, static_cast<float*>(c->a.p), rows, L, n_fft, normalize, static_cast<float*>(c->b.p))))
+    return rc;
+  SS_CUDA(cudaMemcpyAsync(out, c->b.p, (size_t)rows * F * 4, cudaMemcpyDeviceToHost, c->stream));
+  SS_CUDA(cudaStreamSynchronize(c->stream));
+  return SS_OK;
+}
+
 static thread_local DevBuf g_cmvn_scratch;
 int ss_cmvn_dev(void* stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols, int varnorm,
                 float* d_out) {

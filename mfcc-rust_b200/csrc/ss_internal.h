@@ -153,6 +153,7 @@ int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_
 int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int varnorm, float* out,
                 float* scratch, void* stream);
 size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols);
+int launch_log_power(float* x, int64_t n, int normalize, void* scratch16, void* stream);
 int launch_derivative(const float* in, int64_t rows, int64_t cols, int dw, float* out, void* stream);
 int launch_derivative_cube(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
 int launch_cmvnw(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int win, int varnorm, float* out,

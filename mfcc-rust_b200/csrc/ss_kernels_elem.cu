@@ -300,6 +300,52 @@ int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_
   return (int)cudaGetLastError();
 }
 
+// ---- processing::log_power_spectrum (processing.rs:194-214) on an already computed power spectrum:
+// x > 1e-20 ? 10 log10 x : -200, and (quirk Q7) the normaliser is the LAST value above the threshold in
+// row-major order, not the maximum.  scratch[0] = 1 + index of that element (0: none), scratch[1] = bits of mx.
+__global__ void k_logps_map(float* __restrict__ x, int64_t n, unsigned long long* __restrict__ scratch) {
+  unsigned long long last = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (v > 1e-20f) {
+      x[i] = 10.0f * log10f(v);
+      last = (unsigned long long)i + 1;  // i grows along the grid-stride loop
+    } else {
+      x[i] = -200.0f;  // 10 log10(1e-20)
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if ((threadIdx.x & 31) == 0 && last) atomicMax(scratch, last);
+}
+__global__ void k_logps_pick(const float* __restrict__ x, unsigned long long* __restrict__ scratch) {
+  const float mx = scratch[0] ? x[scratch[0] - 1] : 1e-20f;  // `let mut mx = 1e-20_f32`
+  scratch[1] = (unsigned long long)__float_as_uint(mx);
+}
+__global__ void k_logps_sub(float* __restrict__ x, int64_t n, const unsigned long long* __restrict__ scratch) {
+  const float mx = __uint_as_float((unsigned)scratch[1]);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = x[i] - mx;
+}
+
+// scratch: 16 bytes of device memory
+int launch_log_power(float* x, int64_t n, int normalize, void* scratch, void* stream) {
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* sc = static_cast<unsigned long long*>(scratch);
+  cudaError_t e = cudaMemsetAsync(sc, 0, 16, st);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t blocks = std::min<int64_t>((n + 255) / 256, 16LL * kSmCountGuess);
+  k_logps_map<<<(unsigned)blocks, 256, 0, st>>>(x, n, sc);
+  count_launch();
+  if (normalize) {
+    k_logps_pick<<<1, 1, 0, st>>>(x, sc);
+    k_logps_sub<<<(unsigned)blocks, 256, 0, st>>>(x, n, sc);
+    count_launch(2);
+  }
+  return (int)cudaGetLastError();
+}
+
 int launch_derivative(const float* in, int64_t rows, int64_t cols, int dw, float* out, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
   float scale = 0.f;

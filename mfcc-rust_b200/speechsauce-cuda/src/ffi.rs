@@ -87,6 +87,9 @@ extern "C" {
     pub fn ss_stack_frames(input: *const f32, n: i64, frame_len: i64, frame_step: i64, zero_padding: c_int, flags: u32,
                            out: *mut f32, numframes: *mut i64) -> c_int;
     pub fn ss_power_spectrum(frames: *const f32, rows: i64, frame_len: i64, n_fft: i64, out: *mut f32) -> c_int;
+    pub fn ss_log_power_spectrum(frames: *const f32, rows: i64, frame_len: i64, n_fft: i64, normalize: c_int, out: *mut f32) -> c_int;
+    pub fn ss_log_power_spectrum_dev(cuda_stream: *mut c_void, d_frames: *const f32, rows: i64, frame_len: i64, n_fft: i64,
+                                     normalize: c_int, d_out: *mut f32) -> c_int;
     pub fn ss_cmvn(input: *const f32, rows: i64, cols: i64, variance_normalization: c_int, out: *mut f32) -> c_int;
     pub fn ss_cmvn_batch(input: *const f32, n_mats: i64, rows: i64, cols: i64, variance_normalization: c_int, out: *mut f32) -> c_int;
     pub fn ss_features_dev(plan: *mut ss_plan, dev_index: c_int, cuda_stream: *mut c_void, d_pcm: *const f32, n_clips: i64,

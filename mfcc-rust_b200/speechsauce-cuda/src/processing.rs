@@ -35,6 +35,17 @@ pub fn power_spectrum(frames: Array2<f32>, fft_points: usize) -> Array2<f32> {
     out
 }
 
+/// processing.rs:194 (private in the reference)
+pub fn log_power_spectrum(frames: Array2<f32>, fft_points: usize, normalize: bool) -> Array2<f32> {
+    let f = frames.as_standard_layout();
+    let (rows, l) = f.dim();
+    let mut out = Array2::<f32>::zeros((rows, fft_points / 2 + 1));
+    unsafe {
+        check(ffi::ss_log_power_spectrum(f.as_ptr(), rows as i64, l as i64, fft_points as i64, normalize as i32, out.as_mut_ptr()))
+    };
+    out
+}
+
 /// processing.rs:265
 pub fn cmvn(vec: ArrayView2<f32>, variance_normalization: bool) -> Array2<f32> {
     let v = vec.as_standard_layout();

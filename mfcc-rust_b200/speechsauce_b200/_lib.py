@@ -90,6 +90,8 @@ SYMBOLS = {
     "ss_preemphasis_dev": (C.c_int, [_vp, _fp, _fp, _i64, _i64, _i64, _i64, _f]),
     "ss_stack_frames_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, C.c_uint32, _fp, _i64]),
     "ss_power_spectrum_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, _fp]),
+    "ss_log_power_spectrum": (C.c_int, [_fp, _i64, _i64, _i64, C.c_int, _fp]),
+    "ss_log_power_spectrum_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, _fp]),
     "ss_cmvn_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, _fp]),
     "ss_derivative_extraction": (C.c_int, [_fp, _i64, _i64, C.c_int, _fp]),
     "ss_extract_derivative_feature": (C.c_int, [_fp, _i64, _i64, _fp]),

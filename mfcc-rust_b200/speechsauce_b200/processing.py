@@ -58,6 +58,15 @@ def power_spectrum(frames, fft_points=512):
     return out
 
 
+def log_power_spectrum(frames, fft_points=512, normalize=True):
+    """processing::log_power_spectrum (processing.rs:194-214, private in the reference): 10 log10 of the
+    power spectrum (-200 below 1e-20); `normalize` subtracts the last value above the threshold."""
+    f = _f32(frames, 2)
+    out = np.empty((f.shape[0], fft_points // 2 + 1), np.float32)
+    check(lib.ss_log_power_spectrum(_lib.fptr(f), f.shape[0], f.shape[1], int(fft_points), int(bool(normalize)), _lib.fptr(out)))
+    return out
+
+
 def cmvn(vec, variance_normalization=False):
     """processing::cmvn (processing.rs:265-300); 2-D, or 3-D = a batch of matrices."""
     v = _f32(vec)

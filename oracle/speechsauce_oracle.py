@@ -235,6 +235,22 @@ def power_spectrum(frames, fft_points, dtype=F32):
     return (dtype(1.0) / dtype(fft_points)) * fft_spectrum(frames, fft_points, dtype)
 
 
+def log_power_spectrum(frames, fft_points, normalize=True, dtype=F32):
+    """processing.rs:194-214 (private, unused by the features): 10 log10(power_spectrum) where the value
+    exceeds 1e-20, else -200.  `mx` is overwritten by every element above the threshold as `map_mut`
+    walks the array in row-major order, so `normalize` subtracts the LAST such value, not the maximum
+    (quirk Q7); with no element above the threshold mx stays 1e-20."""
+    p = power_spectrum(frames, fft_points, dtype)
+    above = p > dtype(1e-20)
+    out = np.full(p.shape, dtype(-200.0), dtype)
+    out[above] = dtype(10.0) * np.log10(p[above])
+    if normalize:
+        idx = np.flatnonzero(above.ravel())
+        mx = out.ravel()[idx[-1]] if idx.size else dtype(1e-20)
+        out = (out - mx).astype(dtype)
+    return out
+
+
 def cmvn(vec, variance_normalization=False, dtype=F32):
     """processing.rs:265-300.  mean_axis(0): sequential row accumulation then /rows;
     std_axis(0, ddof=0): Welford (ndarray 0.15 `var_axis`); eps = 2^-30."""

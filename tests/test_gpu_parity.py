@@ -286,6 +286,24 @@ def test_power_spectrum():
         sb.processing.power_spectrum(fr, 256)  # frame longer than the FFT: ndrustfft panics
 
 
+def test_log_power_spectrum():
+    """processing::log_power_spectrum (processing.rs:194-214), including the last-value normaliser (Q7)."""
+    fr = o.synth_signal(33, 400, 8)
+    fr[7] = 0.0                                   # a silent frame: -200 everywhere
+    fr[32, 1:] = 0.0                              # the last row is an impulse: flat spectrum
+    for nfft, norm in [(512, False), (512, True), (400, True), (1024, True)]:
+        got = sb.processing.log_power_spectrum(fr, nfft, norm)
+        want = o.log_power_spectrum(fr, nfft, norm)
+        assert got.shape == want.shape
+        assert (got[7] == want[7]).all()
+        # 10 log10 turns the rel 1e-4 spectrum tolerance into 4.3e-4 dB; bins that are zero only by
+        # cancellation carry the FFT's own noise in both implementations
+        loud = o.power_spectrum(fr, nfft) > 1e-6
+        assert_log_close(got[loud], want[loud], what=f"log_power_spectrum {nfft} normalize={norm}")
+    silent = sb.processing.log_power_spectrum(np.zeros((4, 64), np.float32), 64, True)
+    assert (silent == -200.0).all()
+
+
 def test_cmvn():
     rng = np.random.default_rng(3)
     v = rng.uniform(0, 1, (50, 100)).astype(np.float32)  # the reference's test (lib.rs:71-91)

@@ -77,6 +77,26 @@ def test_power_spectrum_closed_form():
     np.testing.assert_allclose(P[0, 1:], want, rtol=2e-5, atol=2e-7)
 
 
+def test_log_power_spectrum_closed_form_and_last_value_normaliser():
+    """processing.rs:194-214: 10 log10 P above 1e-20, else -200; `normalize` subtracts the LAST value
+    above the threshold in row-major order (Q7), not the maximum."""
+    fr = np.zeros((3, 320), np.float32)
+    fr[0] = 1.0                      # Dirichlet kernel: every bin above the threshold
+    fr[1, 0] = 1e-3                  # impulse: flat spectrum 1e-3 / 512
+    # row 2 stays silent: every bin is -200
+    raw = o.log_power_spectrum(fr, 512, normalize=False)
+    assert raw.shape == (3, 257) and raw.dtype == np.float32
+    assert abs(raw[0, 0] - 10 * np.log10(0.625)) < 1e-5
+    np.testing.assert_allclose(raw[1], 10 * np.log10(1e-3 / 512), atol=1e-4)
+    assert (raw[2] == -200.0).all()
+    nrm = o.log_power_spectrum(fr, 512, normalize=True)
+    # the last element above the threshold is the impulse row's last bin, not the maximum (row 0, bin 0)
+    np.testing.assert_allclose(nrm, raw - raw[1, 256], atol=1e-5)
+    assert nrm.max() > 30.0
+    silent = o.log_power_spectrum(np.zeros((2, 64), np.float32), 64, normalize=True)
+    assert (silent == -200.0).all()   # mx stays 1e-20
+
+
 def test_filterbank_indices_and_peaks():
     want = [0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 18, 20, 22, 25, 27, 29, 32, 35, 38, 41, 44,
             48, 51, 55, 60, 64, 69, 74, 79, 85, 91, 98, 105, 112, 120, 129]
