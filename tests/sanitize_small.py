@@ -29,6 +29,27 @@ for flags in (0, _lib.SS_FLAG_FORCE_GENERIC):
         y = o.synth_signal(n, ttd, 3)
         sb.feature.mel_spectrogram2(y, k, log=True)
         sb.functions.stft2(y, k)
+# the fused in-kernel CMVN of k_fast512c needs one clip per resident warp: device-resident batch
+import ctypes as C  # noqa: E402
+
+import torch  # noqa: E402
+cfg = sb.SpeechConfig(**C1, devices=[0])
+nb = 3100
+dx = torch.from_numpy(o.synth_signal(nb, 16000, 7)).cuda()
+lm = torch.empty((nb, 97, 40), dtype=torch.float32, device="cuda")
+mf = torch.empty((nb, 97, 13), dtype=torch.float32, device="cuda")
+outs = _lib.ss_feature_outputs(None, None, C.c_void_p(lm.data_ptr()), None, C.c_void_p(mf.data_ptr()), 2, 0)
+_lib.check(sb.lib.ss_features_dev(cfg.plan, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(dx.data_ptr()),
+                                  nb, 16000, 16000, C.byref(outs)))
+torch.cuda.synchronize()
+# other filter / cepstrum counts (fourth m-tile, odd nf, 16 cepstra) and a longer stream (chunked items)
+for nf, nc in ((64, 16), (41, 8), (17, 12)):
+    k = sb.SpeechConfig(**dict(C1, num_filters=nf, num_cepstral=nc), devices=[0])
+    sb.feature.features(x[:2], k, mfe=True, energy=True, lmfe=True, ssc=True, mfcc=True)
+sb.feature.features(o.synth_signal(1, 16000 * 20 + 3, 8), cfg, mfe=True, ssc=True, mfcc=True)
+k4 = sb.SpeechConfig(**C4, devices=[0])
+sb.feature.mel_spectrogram2(o.synth_signal(3, 16000 * 3, 9), k4, log=True)   # staged rounds + ring wrap-around
+sb.processing.log_power_spectrum(o.synth_signal(9, 400, 4), 512, True)
 sb.processing.preemphasis(x[0]); sb.processing.preemphasis(x)
 sb.processing.stack_frames(x[0], 16000, 0.025, 0.01, None, True)
 sb.processing.power_spectrum(o.synth_signal(9, 400, 4), 512)
