@@ -604,8 +604,10 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   auto al8 = [](const float* q) { return reinterpret_cast<uintptr_t>(q) % 8 == 0; };
   a.nf_even = (p.nf % 2 == 0) && al8(p.mfe) && al8(p.lmfe) && al8(p.ssc);
   const bool ssc = p.ssc != nullptr;
-  const size_t smem = fixed + (size_t)n_warps * kWarpFloats * sizeof(float);
-  const int64_t grid = std::min<int64_t>((a.n_items + n_warps - 1) / n_warps, (int64_t)sm_count);
+  // small jobs: fewer warps per CTA so that the items spread over the SMs instead of queueing on a few
+  const int wl = (int)std::min<int64_t>(n_warps, std::max<int64_t>(1, (a.n_items + sm_count - 1) / sm_count));
+  const size_t smem = fixed + (size_t)wl * kWarpFloats * sizeof(float);
+  const int64_t grid = std::min<int64_t>((a.n_items + wl - 1) / wl, (int64_t)sm_count);
   if (grid <= 0) return 0;
   const int jn = (p.L + 31) / 32;
   cudaError_t e;
@@ -613,7 +615,7 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   do {                                                                                                         \
     e = cudaFuncSetAttribute(k_fast512c<J, X, C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     if (e != cudaSuccess) return (int)e;                                                                       \
-    k_fast512c<J, X, C, N><<<(unsigned)grid, n_warps * 32, smem, (cudaStream_t)stream>>>(a);                       \
+    k_fast512c<J, X, C, N><<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);                       \
   } while (0)
 #define SS_LAUNCH_FASTC_N(J, X, C)                                          \
   do {                                                                      \

@@ -509,12 +509,14 @@ int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count,
   const int64_t c0 = (int64_t)(p.n_pad + 1) * p.S - p.N;
   a.stage = p.S == 160 && (p.row_stride % 4 == 0) && (((c0 % 4) + 4) % 4 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
   a.pair_ok = (p.T_out % 2 == 0) && (reinterpret_cast<uintptr_t>(p.mel_out) % 8 == 0);
-  const size_t smem = fixed + (size_t)n_warps * kWarpFloats * sizeof(float);
-  const int64_t grid = std::min<int64_t>((a.n_items + n_warps - 1) / n_warps, (int64_t)sm_count);
+  // small jobs: fewer warps per CTA so that the items spread over the SMs instead of queueing on a few
+  const int wl = (int)std::min<int64_t>(n_warps, std::max<int64_t>(1, (a.n_items + sm_count - 1) / sm_count));
+  const size_t smem = fixed + (size_t)wl * kWarpFloats * sizeof(float);
+  const int64_t grid = std::min<int64_t>((a.n_items + wl - 1) / wl, (int64_t)sm_count);
   if (grid <= 0) return 0;
   cudaError_t e = cudaFuncSetAttribute(k_stft400m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_stft400m<<<(unsigned)grid, n_warps * 32, smem, (cudaStream_t)stream>>>(a);
+  k_stft400m<<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);
   count_launch();
   note_kernel("k_stft400m");
   return (int)cudaGetLastError();
