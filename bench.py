@@ -125,6 +125,25 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run this process's host threads (and so first-touch its pinned buffers) on
+    the CPUs NVML reports as local to the GPU, so eight concurrent H2D / D2H streams do not all pull
+    from one socket's memory.  Returns the number of CPUs bound to, or None when NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args, w):
     """The reference arm: the CPU restatement (oracle port, C + OpenMP over clips) on rank 0."""
     rank = int(os.environ.get("RANK", "0"))
@@ -204,6 +223,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -294,7 +314,7 @@ def main():
             dt = float(dt.item())
             e2e = {"value": world * n_e * length / w["cfg"]["sample_rate"] / dt, "unit": "audio-s/s",
                    "h2d_bytes_per_step": int(hx.numel() * 4), "d2h_bytes_per_step": int(sum(v.numel() for v in houts.values()) * 4),
-                   "clips_per_step": n_e, "ms_per_step": dt * 1e3, "steps": ke,
+                   "clips_per_step": n_e, "ms_per_step": dt * 1e3, "steps": ke, "host_cpus_bound": numa,
                    "timing": "host wall clock around the blocking ss_features / ss_mel_spectrogram call"}
             # spot-check the e2e result against the device-resident one.  Row 0 is skipped: on the
             # STFT path the host call carries the plan's overlap memory across calls like the
