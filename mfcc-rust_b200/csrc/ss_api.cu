@@ -260,7 +260,7 @@ static void stft_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float*
 static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
   // SS_STFT400_GEN=1 selects the first-generation fft_points = 400 kernel for A/B measurements
   static const int gen400 = getenv("SS_STFT400_GEN") ? atoi(getenv("SS_STFT400_GEN")) : 2;
-  if (pl->stft400m && dc->stft400m && gen400 >= 2 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+  if (pl->stft400m && dc->stft400m && gen400 >= 2 && (p.mel_out || p.stft_out) && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400m(p, dc->stft400m, dc->sm_count, stream);
     if (e != -1000) return e;
   }

@@ -2,8 +2,8 @@
 // (config c4, the Whisper-shaped log-mel: 16 kHz, hop 160, 80 mels):
 //   stream framing (functions.rs:86-160) -> Vorbis window -> real FFT(400) -> |X wnorm|^2 ->
 //   mel filterbank (feature.rs:163-174) -> optional ln(zero_handling) -> time-minor store.
-// Replaces feature::mel_spectrogram{1,2} for this FFT size; functions::stft{1,2} (complex output)
-// stay on the generic kernel.
+// Replaces feature::mel_spectrogram{1,2} and functions::stft{1,2} (complex output, written straight
+// from the registers of the real-FFT split) for this FFT size.
 //
 // FFT stage as in the first generation (ss_kernels_stft400.cu): 10 lanes x 20 complex points per
 // frame, 200 = 20 x 10 four-step FFT in registers (radix 5 / 2, packed FFMA2 butterflies), three
@@ -112,13 +112,13 @@ __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
   return p.pcm[r * p.row_stride + o];
 }
 
-__device__ __forceinline__ float2 pair_power(float2 za, float2 zb, float2 w) {
-  // E' = za + conj zb, O' = (za - conj zb)/i, T' = W400^k O'; returns |E'+T'|^2, |E'-T'|^2
+// E' = za + conj zb, O' = (za - conj zb)/i, T' = W400^k O': xa = E' + T' = 2 X[k], xb = E' - T' = 2 conj X[200-k]
+__device__ __forceinline__ void pair_split(float2 za, float2 zb, float2 w, float2& xa, float2& xb) {
   const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
   const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
   const float2 tt = ssfft::cmulf(od, w);
-  const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
-  return make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
+  xa = ssfft::cadd(e, tt);
+  xb = ssfft::csub(e, tt);
 }
 
 __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs a) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
     const int fbeg = (int)(item - row * a.chunks_per_row) * a.fpi;
     const int fend = min(T_out, fbeg + a.fpi);
     const float* rowp = p.pcm + row * p.row_stride;
-    float* outp = p.mel_out + row * nf * (int64_t)T_out;
+    float* outp = p.mel_out ? p.mel_out + row * nf * (int64_t)T_out : nullptr;
 
     const int nfr = fend - fbeg;                    // frames of this item
     const int n_rounds = (nfr + kFpw - 1) / kFpw;
@@ -280,6 +280,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
         //         e=5..9 -> (gB[e-5], gB[14-e]) with k = 10 + 20 (e-5); bin 100 = |gA[5]|^2 below.
         if (real_lane) {
           float* pA = Pf + u;
+          // complex output of functions::stft1/2 (functions.rs:86-123,199-233): [row][T_out][201] (re, im),
+          // X wnorm for computed frames, zeros in the reference's zero tail (v = 0 there)
+          float2* so = (p.stft_out && tf < fend) ? p.stft_out + (row * (int64_t)T_out + tf) * (kM + 1) : nullptr;
+          const float hs = 0.5f * p.wnorm;
           sfor<0, 10>([&](auto ee) {
             constexpr int e = decltype(ee)::value;
             float2 za, zb;
@@ -293,14 +297,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
               za = isz ? gB[e - 5] : gA[e];
               zb = isz ? gB[14 - e] : gB[9 - e];
             }
-            const float2 m = pair_power(za, zb, (e < 5 ? twA : twB)[20 * e]);
+            float2 xa, xb;
+            pair_split(za, zb, (e < 5 ? twA : twB)[20 * e], xa, xb);
+            const float2 m = make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
             if constexpr (e < 5) pA[20 * e] = m.x;        // bin u + 20 e <= 89
             else Pf[plo[e - 5]] = isz ? m.x : m.y;        // the bin of the pair that is <= 100
+            if (so) {
+              const int k = (e < 5 ? u : kb) + 20 * e;    // xa is bin k, xb the conjugate of bin 200 - k
+              so[k] = make_float2(xa.x * hs, xa.y * hs);
+              so[kM - k] = make_float2(xb.x * hs, -xb.y * hs);
+            }
           });
-          if (isz)  // X[100] = conj Z[100]; x4 to match the pairs; bins 101..103 stay zero
+          if (isz) {  // X[100] = conj Z[100]; x4 to match the pairs; bins 101..103 stay zero
             *reinterpret_cast<float4*>(Pf + 100) = make_float4(4.0f * fmaf(gA[5].x, gA[5].x, gA[5].y * gA[5].y), 0.f, 0.f, 0.f);
+            if (so) so[100] = make_float2(gA[5].x * p.wnorm, -gA[5].y * p.wnorm);
+          }
         }
       }
+      if (!p.mel_out) continue;  // stft only
       // a tile is complete once 8 more frames exist (or the item ends)
       const int produced = min(nfr, kFpw * (rd + 1));
       if (produced < kTileFrames * (tile + 1) && rd + 1 < n_rounds) continue;
@@ -483,9 +497,9 @@ void stft400m_free_tables(Stft400mTables* t) {
   delete t;
 }
 
-// mel_spectrogram only (p.mel_out set, p.stft_out null); returns -1000 if the shape is declined
+// mel_spectrogram (p.mel_out) and / or the complex STFT (p.stft_out); returns -1000 if the shape is declined
 int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count, void* stream) {
-  if (p.N != kW || !p.mel_out || p.stft_out || p.T_out < 1 || p.T_out > (1LL << 31) - 64) return -1000;
+  if (p.N != kW || (!p.mel_out && !p.stft_out) || p.T_out < 1 || p.T_out > (1LL << 31) - 64) return -1000;
   Stft400mArgs a;
   a.p = p;
   a.tab = t->d_tab;

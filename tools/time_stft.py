@@ -1,0 +1,35 @@
+"""Times functions::stft2-shaped output (complex [ch][T'][F]) device-resident: the Whisper-shaped config c4
+on a slice (the full batch's output is 39.5 GB), register-FFT kernel vs the generic one."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT / "mfcc-rust_b200"), str(ROOT / "oracle")]
+import torch  # noqa: E402
+import speechsauce_b200 as sb  # noqa: E402
+from speechsauce_b200 import _lib  # noqa: E402
+
+C4 = dict(sample_rate=16000, fft_points=400, frame_length=0.01, frame_stride=0.01, num_cepstral=13, num_filters=80,
+          low_frequency=0.0, high_frequency=8000.0)
+n, ttd = 1024, 480000
+x = torch.empty((n, ttd), dtype=torch.float32, device="cuda").normal_(0, 0.1)
+T = 3000
+out = torch.empty((n, T, 201, 2), dtype=torch.float32, device="cuda")
+sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for name, flags in (("fast", 0), ("generic", _lib.SS_FLAG_FORCE_GENERIC)):
+    cfg = sb.SpeechConfig(**C4, devices=[0], flags=flags)
+
+    def step():
+        _lib.check(sb.lib.ss_stft_dev(cfg.plan, 0, sp, C.c_void_p(x.data_ptr()), n, ttd, ttd, C.c_void_p(out.data_ptr()), None, None))
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gb = (x.numel() + out.numel()) * 4 / 1e9
+    print(f"stft c4-shaped, {n} rows: {name:8s} {sb.lib.ss_last_kernel_name().decode():18s} {ms:8.3f} ms  {gb / ms * 1e3:7.1f} GB/s algorithmic")
