@@ -268,7 +268,7 @@ static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, voi
     const int e = launch_stft400(p, dc->stft400, dc->sm_count, stream);
     if (e != -1000) return e;
   }
-  if (pl->stft2048 && dc->stft2048 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+  if (pl->stft2048 && dc->stft2048 && (p.mel_out || p.stft_out) && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft2048(p, dc->stft2048, dc->sm_count, stream);
     if (e != -1000) return e;
   }

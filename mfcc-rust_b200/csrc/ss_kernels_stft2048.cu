@@ -65,6 +65,7 @@ __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
   return p.pcm[r * p.row_stride + o];
 }
 
+template <bool STFT>  // STFT: complex output of functions::stft1/2 instead of the mel spectrogram
 __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) {
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
@@ -168,9 +169,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
         const float2 w = twk[32 * k2];
         const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
         const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
-        const float2 xa = ssfft::cadd(e, ssfft::cmulf(od, w));
-        pA[32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
+        const float2 tt = ssfft::cmulf(od, w);
+        const float2 xa = ssfft::cadd(e, tt);  // 2 X[k]
+        if constexpr (STFT) {
+          // [row][T_out][1025] (re, im): X wnorm (functions.rs:166-169); zeros in the reference's zero tail (v = 0)
+          if (t < p.T_out) {
+            float2* so = p.stft_out + (row * p.T_out + t) * (int64_t)(kM + 1);
+            const float2 xb = ssfft::csub(e, tt);  // 2 conj X[1024 - k]
+            const float hs = 0.5f * p.wnorm;
+            so[u + 32 * k2] = make_float2(xa.x * hs, xa.y * hs);
+            so[kM - (u + 32 * k2)] = make_float2(xb.x * hs, -xb.y * hs);
+          }
+        } else {
+          pA[32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
+        }
       });
+      if constexpr (STFT) {
+        if (isz && t < p.T_out)  // X[512] = conj Z[512]
+          p.stft_out[(row * p.T_out + t) * (int64_t)(kM + 1) + 512] = make_float2(g[16].x * p.wnorm, -g[16].y * p.wnorm);
+        continue;
+      }
       if (isz) {
         Pf[512] = 4.0f * fmaf(g[16].x, g[16].x, g[16].y * g[16].y);  // X[512] = conj Z[512]
         Pf[513] = 0.f; Pf[514] = 0.f; Pf[515] = 0.f;
@@ -200,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
       }
       __syncwarp();  // P is overwritten by the next frame's transpose
     }
+    if constexpr (STFT) continue;
     __syncthreads();  // tile complete; everyone is done reading the other tile
     {
       const int64_t nvalid = min((int64_t)kFpr, p.T_out - t_round);
@@ -310,7 +329,7 @@ void stft2048_free_tables(Stft2048Tables* t) {
 }
 
 int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count, void* stream) {
-  if (p.N != kW || !p.mel_out || p.stft_out || p.T_out < 1) return -1000;
+  if (p.N != kW || (!p.mel_out == !p.stft_out) || p.T_out < 1) return -1000;  // exactly one of the two outputs
   Stft2048Args a;
   a.p = p;
   a.tab = t->d_tab;
@@ -323,9 +342,16 @@ int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count,
   if (smem > 227 * 1024) return -1000;
   const int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sm_count);
   if (grid <= 0) return 0;
-  cudaError_t e = cudaFuncSetAttribute(k_stft2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  k_stft2048<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
+  cudaError_t e;
+  if (p.stft_out) {
+    e = cudaFuncSetAttribute(k_stft2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_stft2048<true><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(k_stft2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_stft2048<false><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
+  }
   count_launch();
   note_kernel("k_stft2048");
   return (int)cudaGetLastError();

@@ -12,13 +12,14 @@ from speechsauce_b200 import _lib  # noqa: E402
 
 C4 = dict(sample_rate=16000, fft_points=400, frame_length=0.01, frame_stride=0.01, num_cepstral=13, num_filters=80,
           low_frequency=0.0, high_frequency=8000.0)
-n, ttd = 1024, 480000
-x = torch.empty((n, ttd), dtype=torch.float32, device="cuda").normal_(0, 0.1)
-T = 3000
-out = torch.empty((n, T, 201, 2), dtype=torch.float32, device="cuda")
+C3 = dict(sample_rate=22050, fft_points=2048, frame_length=512 / 22050, frame_stride=0.01, num_cepstral=13,
+          num_filters=128, low_frequency=0.0, high_frequency=11025.0)
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-for name, flags in (("fast", 0), ("generic", _lib.SS_FLAG_FORCE_GENERIC)):
-    cfg = sb.SpeechConfig(**C4, devices=[0], flags=flags)
+for shape, kw, n, ttd, T, F in (("c4", C4, 1024, 480000, 3000, 201), ("c3", C3, 2048, 110250, 216, 1025)):
+  x = torch.empty((n, ttd), dtype=torch.float32, device="cuda").normal_(0, 0.1)
+  out = torch.empty((n, T, F, 2), dtype=torch.float32, device="cuda")
+  for name, flags in (("fast", 0), ("generic", _lib.SS_FLAG_FORCE_GENERIC)):
+    cfg = sb.SpeechConfig(**kw, devices=[0], flags=flags)
 
     def step():
         _lib.check(sb.lib.ss_stft_dev(cfg.plan, 0, sp, C.c_void_p(x.data_ptr()), n, ttd, ttd, C.c_void_p(out.data_ptr()), None, None))
@@ -32,4 +33,4 @@ for name, flags in (("fast", 0), ("generic", _lib.SS_FLAG_FORCE_GENERIC)):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     gb = (x.numel() + out.numel()) * 4 / 1e9
-    print(f"stft c4-shaped, {n} rows: {name:8s} {sb.lib.ss_last_kernel_name().decode():18s} {ms:8.3f} ms  {gb / ms * 1e3:7.1f} GB/s algorithmic")
+    print(f"stft {shape}-shaped, {n} rows: {name:8s} {sb.lib.ss_last_kernel_name().decode():18s} {ms:8.3f} ms  {gb / ms * 1e3:7.1f} GB/s algorithmic")
