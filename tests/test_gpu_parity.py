@@ -195,6 +195,46 @@ def test_fast512_fused_cmvn_on_a_full_grid():
             np.testing.assert_allclose(mfcc.std(1), 1, atol=1e-4)
 
 
+def test_fast512_odd_strides_tiny_clips_and_padded_rows():
+    """Shapes that switch off the vector / cp.async paths of k_fast512c or leave partial tiles: an odd
+    frame step and length, clips of 1..9 frames, and rows with a stride that is not the clip length
+    (straight through the C ABI)."""
+    import ctypes as C
+    kw = dict(CONFIGS["c1"], frame_length=0.0203125, frame_stride=0.0100625)   # L = 325, S = 161
+    cfg, oc = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+    assert cfg.info.fast_path == 1 and (oc.frame_sample_length, oc.frame_step) == (325, 161)
+    x = o.synth_signal(3, 16001, 0x5EED0201)
+    r = sb.feature.features(x, cfg, mfe=True, energy=True, lmfe=True, mfcc=True)
+    assert sb.lib.ss_last_kernel_name() == b"k_fast512c"
+    for i in range(3):
+        f, e = o.mfe(x[i], oc)
+        assert_spec_close(r["mfe"][i], f, what="odd stride mfe")
+        assert_spec_close(r["energy"][i], e, what="odd stride energy")
+        assert_log_close(r["mfcc"][i], o.mfcc(x[i], oc), what="odd stride mfcc")
+    cfg, oc = sb.SpeechConfig(**CONFIGS["c1"]), o.SpeechConfig(**CONFIGS["c1"])
+    for T in (1, 2, 3, 7, 8, 9):
+        n = 400 + 160 * T + 17          # floor((n - 400) / 160) = T frames
+        y = o.synth_signal(2, n, 0x5EED0210 + T)
+        assert o.num_frames(n, 400, 160, False) == T
+        r = sb.feature.features(y, cfg, mfe=True, lmfe=True, mfcc=True, cmvn_mode=2)
+        assert r["mfcc"].shape == (2, T, 13)
+        assert_spec_close(r["mfe"][1], o.mfe(y[1], oc)[0], what=f"T={T} mfe")
+        if T > 1:  # cmvn of a single row is 0 / (0 + eps)
+            assert_log_close(r["mfcc"][1], o.cmvn(o.mfcc(y[1], oc), True), atol=2e-3, what=f"T={T} cmvn(mfcc)")
+    # rows 16,003 floats apart (neither 8- nor 16-byte aligned), 16,000 samples each
+    stride = 16003
+    buf = np.zeros((4, stride), np.float32)
+    buf[:, :16000] = o.synth_signal(4, 16000, 0x5EED0220)
+    buf[:, 16000:] = np.float32(1e9)    # must never be read into a frame
+    lm = np.empty((4, 97, 40), np.float32)
+    mf = np.empty((4, 97, 13), np.float32)
+    outs = _lib.ss_feature_outputs(None, None, _lib.fptr(lm), None, _lib.fptr(mf), 0, 0)
+    _lib.check(sb.lib.ss_features(cfg.plan, _lib.fptr(buf), 4, 16000, stride, C.byref(outs)))
+    for i in range(4):
+        assert_log_close(lm[i], o.lmfe(buf[i, :16000], oc), what="strided rows lmfe")
+        assert_log_close(mf[i], o.mfcc(buf[i, :16000], oc), what="strided rows mfcc")
+
+
 def test_fast512_long_stream_chunks():
     """Config c5's shape in small: two 90 s streams are cut into chunks of whole tiles, one per warp."""
     cfg = sb.SpeechConfig(**CONFIGS["c1"])
