@@ -211,8 +211,8 @@ int ss_debug_filterbank(const ss_plan* plan, float* out_nf_by_F);
 int ss_debug_window(const ss_plan* plan, float* out_W);
 /* number of kernels this library has launched from the calling process since load */
 int64_t ss_kernel_launch_count(void);
-/* name of the fused frame kernel the calling thread launched last ("k_fast512c", "k_stft400", ...; "" before the
-   first launch); valid until the next call on the thread */
+/* name of the fused frame kernel this process launched last ("k_fast512c", "k_stft400m", ...; "" before the
+   first launch); a pointer to a string literal */
 const char* ss_last_kernel_name(void);
 
 #ifdef __cplusplus

@@ -21,8 +21,8 @@ namespace ss {
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-static thread_local const char* g_last_kernel = "";
-void note_kernel(const char* name) { g_last_kernel = name; }
+static std::atomic<const char*> g_last_kernel{""};  // process-wide: multi-device plans launch from worker threads
+void note_kernel(const char* name) { g_last_kernel.store(name, std::memory_order_relaxed); }
 
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -421,7 +421,7 @@ extern "C" {
 const char* ss_last_error(void) { return g_err.c_str(); }
 const char* ss_version(void) { return "speechsauce-cuda 0.1.0 (sm_100a)"; }
 int64_t ss_kernel_launch_count(void) { return g_launches.load(); }
-const char* ss_last_kernel_name(void) { return g_last_kernel; }
+const char* ss_last_kernel_name(void) { return g_last_kernel.load(std::memory_order_relaxed); }
 
 int ss_device_count(void) {
   int n = 0;
