@@ -121,6 +121,7 @@ __device__ __forceinline__ void pair_split(float2 za, float2 zb, float2 w, float
   xb = ssfft::csub(e, tt);
 }
 
+template <bool STFT>  // STFT: also / only the complex output of functions::stft1/2
 __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
           float* pA = Pf + u;
           // complex output of functions::stft1/2 (functions.rs:86-123,199-233): [row][T_out][201] (re, im),
           // X wnorm for computed frames, zeros in the reference's zero tail (v = 0 there)
-          float2* so = (p.stft_out && tf < fend) ? p.stft_out + (row * (int64_t)T_out + tf) * (kM + 1) : nullptr;
+          float2* so = (STFT && p.stft_out && tf < fend) ? p.stft_out + (row * (int64_t)T_out + tf) * (kM + 1) : nullptr;
           const float hs = 0.5f * p.wnorm;
           sfor<0, 10>([&](auto ee) {
             constexpr int e = decltype(ee)::value;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
             const float2 m = make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
             if constexpr (e < 5) pA[20 * e] = m.x;        // bin u + 20 e <= 89
             else Pf[plo[e - 5]] = isz ? m.x : m.y;        // the bin of the pair that is <= 100
-            if (so) {
+            if (STFT && so) {
               const int k = (e < 5 ? u : kb) + 20 * e;    // xa is bin k, xb the conjugate of bin 200 - k
               so[k] = make_float2(xa.x * hs, xa.y * hs);
               so[kM - k] = make_float2(xb.x * hs, -xb.y * hs);
@@ -310,11 +311,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
           });
           if (isz) {  // X[100] = conj Z[100]; x4 to match the pairs; bins 101..103 stay zero
             *reinterpret_cast<float4*>(Pf + 100) = make_float4(4.0f * fmaf(gA[5].x, gA[5].x, gA[5].y * gA[5].y), 0.f, 0.f, 0.f);
-            if (so) so[100] = make_float2(gA[5].x * p.wnorm, -gA[5].y * p.wnorm);
+            if (STFT && so) so[100] = make_float2(gA[5].x * p.wnorm, -gA[5].y * p.wnorm);
           }
         }
       }
-      if (!p.mel_out) continue;  // stft only
+      if (STFT && !p.mel_out) continue;  // stft only
       // a tile is complete once 8 more frames exist (or the item ends)
       const int produced = min(nfr, kFpw * (rd + 1));
       if (produced < kTileFrames * (tile + 1) && rd + 1 < n_rounds) continue;
@@ -528,9 +529,16 @@ int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count,
   const size_t smem = fixed + (size_t)wl * kWarpFloats * sizeof(float);
   const int64_t grid = std::min<int64_t>((a.n_items + wl - 1) / wl, (int64_t)sm_count);
   if (grid <= 0) return 0;
-  cudaError_t e = cudaFuncSetAttribute(k_stft400m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  k_stft400m<<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);
+  cudaError_t e;
+  if (p.stft_out) {
+    e = cudaFuncSetAttribute(k_stft400m<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_stft400m<true><<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(k_stft400m<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_stft400m<false><<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);
+  }
   count_launch();
   note_kernel("k_stft400m");
   return (int)cudaGetLastError();
