@@ -85,6 +85,7 @@ struct DeviceCtx {
   Stft400Tables* stft400 = nullptr;
   Stft400mTables* stft400m = nullptr;
   Stft2048Tables* stft2048 = nullptr;
+  Stft2048mTables* stft2048m = nullptr;
   Lane lanes[kLanes];
   DevBuf dev_scratch;  // scratch for the *_dev entry points (cmvn partials)
   std::string err;     // worker-thread error message
@@ -105,6 +106,7 @@ struct ss_plan {
   bool stft400 = false;
   bool stft400m = false;
   bool stft2048 = false;
+  bool stft2048m = false;
 };
 
 namespace ss {
@@ -165,6 +167,10 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   if (pl->stft2048) {
     int e = stft2048_build_tables(pl->d, pl->mb, pl->window, &dc->stft2048);
     if (e) return cuda_fail((cudaError_t)e, "stft2048_build_tables");
+  }
+  if (pl->stft2048m) {
+    int e = stft2048m_build_tables(pl->d, pl->mb, pl->window, &dc->stft2048m);
+    if (e) return cuda_fail((cudaError_t)e, "stft2048m_build_tables");
   }
   return SS_OK;
 }
@@ -266,6 +272,12 @@ static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, voi
   }
   if (pl->stft400 && dc->stft400 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400(p, dc->stft400, dc->sm_count, stream);
+    if (e != -1000) return e;
+  }
+  // SS_STFT2048_GEN=1 selects the first-generation fft_points = 2048 mel kernel for A/B measurements
+  static const int gen2048 = getenv("SS_STFT2048_GEN") ? atoi(getenv("SS_STFT2048_GEN")) : 2;
+  if (pl->stft2048m && dc->stft2048m && gen2048 >= 2 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+    const int e = launch_stft2048m(p, dc->stft2048m, dc->sm_count, stream);
     if (e != -1000) return e;
   }
   if (pl->stft2048 && dc->stft2048 && (p.mel_out || p.stft_out) && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
@@ -465,6 +477,7 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
   pl->stft400m = pl->fft_ok && stft400m_supported(pl->d, pl->mb);
   pl->stft2048 = pl->fft_ok && stft2048_supported(pl->d, pl->mb);
+  pl->stft2048m = pl->fft_ok && stft2048m_supported(pl->d, pl->mb);
   std::vector<int> devs;
   if (n_devices < 0) {
     int n = ss_device_count();
@@ -518,6 +531,7 @@ void ss_plan_destroy(ss_plan* pl) {
     if (dc.stft400) stft400_free_tables(dc.stft400);
     if (dc.stft400m) stft400m_free_tables(dc.stft400m);
     if (dc.stft2048) stft2048_free_tables(dc.stft2048);
+    if (dc.stft2048m) stft2048m_free_tables(dc.stft2048m);
   }
   if (prev >= 0) cudaSetDevice(prev);
   delete pl;
@@ -537,7 +551,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
   info->fast_path = (pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  info->fast_stft = (pl->stft400 || pl->stft400m || pl->stft2048) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
+  info->fast_stft = (pl->stft400 || pl->stft400m || pl->stft2048 || pl->stft2048m) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }
 

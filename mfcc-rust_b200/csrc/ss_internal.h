@@ -146,6 +146,13 @@ int stft2048_build_tables(const Derived& d, const MelBank& mb, const std::vector
 void stft2048_free_tables(Stft2048Tables* t);
 int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count, void* stream);
 
+// second-generation fft_points == 2048 mel kernel: CTA-shared |X|^2 tile, mel on mma.sync TF32x3 (ss_kernels_stft2048m.cu)
+bool stft2048m_supported(const Derived& d, const MelBank& mb);
+struct Stft2048mTables;
+int stft2048m_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft2048mTables** out);
+void stft2048m_free_tables(Stft2048mTables* t);
+int launch_stft2048m(const FrameParams& p, const Stft2048mTables* t, int sm_count, void* stream);
+
 int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
                        int64_t shift, float cof, void* stream);
 int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,

@@ -17,7 +17,7 @@ def last_json_line(path):
     return [l for l in path.read_text().splitlines() if l.startswith("{")][-1]
 
 
-for f in ["c1", "c2", "c3", "c4", "c5", "c2_reference", "c2_gen2", "c4_gen1", "c2_generic"]:
+for f in ["c1", "c2", "c3", "c4", "c5", "c2_reference", "c2_gen2", "c4_gen1", "c3_gen1", "c2_generic"]:
     (pr / f"bench_r1_{f}.json").write_text(last_json_line(g / f"bench_r1_{f}.json") + "\n")
 
 rows = [r for r in csv.reader((g / "launches_r1.csv").read_text().splitlines()) if len(r) > 10]
@@ -57,12 +57,12 @@ for rep, kn, name, cfg, clips, phases in [
         ("prof_fast512c_r1", "k_fast512cILi13ELb1ELb0ELi5", "ncu_fast512c_r1", "c2", 65536, True),
         ("prof_fast512c_c5_r1", "k_fast512cILi13ELb1ELb1ELi5", "ncu_fast512c_c5_r1", "c5", 128, True),
         ("prof_stft400m_r1", "k_stft400mILb0", "ncu_stft400m_r1", None, None, False),
-        ("prof_stft2048_r1", "k_stft2048ILb0", "ncu_stft2048_r1", "c3", 4096, False)]:
+        ("prof_stft2048m_r1", "k_stft2048m", "ncu_stft2048m_r1", "c3", 4096, False)]:
     rp = str(g / f"{rep}.ncu-rep")
     txt = run("ncu_summary.py", rp) + "\n" + (run("ncu_phases.py", rp, kn) + "\n" if phases else "") + run("ncu_lines.py", rp, kn, "30")
     (pr / f"{name}.txt").write_text(txt)
     if cfg:
-        tr[cfg] = {"kernel": kn.split("IL")[0], "clips": clips, "dram_bytes": traffic(txt),
+        tr[cfg] = {"kernel": kn.split("IL")[0].split("E")[0] if kn.startswith("k_fast") else kn.split("IL")[0], "clips": clips, "dram_bytes": traffic(txt),
                    "source": f"profiles/{name}.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full)"}
 (pr / "ncu_traffic.json").write_text(json.dumps(tr, indent=1) + "\n")
 for c in ["c1", "c2", "c3", "c4", "c5"]:
