@@ -254,6 +254,27 @@ def test_fast512_long_stream_chunks():
     assert_log_close(r["mfcc"][1], o.mfcc(x[1], oc), what="long stream mfcc vs oracle")
 
 
+def test_cuda_path_matches_the_committed_golden_fixtures():
+    """tests/golden/*.npz (generated by tests/golden/make_golden.py, pinned against oracle drift by
+    test_oracle_kat.py): the CUDA path reproduces them from the same seeded inputs, one fixture per
+    BASELINE config shape (c1, a c2 slice, c3, c4)."""
+    import json
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    meta = json.loads((gold / "golden.json").read_text())
+    for name, m in meta.items():
+        z = np.load(gold / f"{name}.npz")
+        cfg = sb.SpeechConfig(**m["config"])
+        x = o.synth_signal(m["n_clips"], m["clip_len"], m["seed"])
+        if m["kind"] == "speechpy":
+            r = sb.feature.features(x, cfg, mfe=True, energy=True, mfcc=True)
+            assert_spec_close(r["mfe"], z["mfe"], what=f"{name} mfe")
+            assert_spec_close(r["energy"], z["energy"], what=f"{name} energy")
+            assert_log_close(r["mfcc"], z["mfcc"], what=f"{name} mfcc")
+        else:
+            assert_spec_close(sb.feature.mel_spectrogram2(x, cfg), z["mel"], what=f"{name} mel")
+
+
 def test_reference_shape_tests_1M_samples():
     """speechsauce/src/lib.rs:94-134 re-expressed: default config, 1e6 samples -> (6248, 13), no NaN."""
     sig = o.synth_signal(1, 1_000_000, 7)[0]
