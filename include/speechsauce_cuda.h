@@ -41,6 +41,11 @@ typedef enum {
 /* ss_config.flags */
 #define SS_FLAG_FRAMING_LITERAL 0x1u /* reproduce processing.rs:110-120 as written (all-zero frames for T > 2) */
 #define SS_FLAG_FORCE_GENERIC   0x2u /* never pick a size-specialised kernel (used by the parity tests) */
+#define SS_FLAG_LIBROSA         0x4u /* the plan serves ss_librosa_melspectrogram only: periodic Hann window of
+                                        fft_points, hop = trunc(frame_length*sample_rate), centred frames with
+                                        reflect padding, Slaney mel scale with Slaney (area) normalisation.  The
+                                        reference's README / Contributing.md name librosa compatibility as the
+                                        project's direction; its code has no such path. */
 
 /* cmvn_mode */
 #define SS_CMVN_NONE 0
@@ -155,6 +160,13 @@ int ss_stack_frames(const float* in, int64_t n, int64_t frame_len, int64_t frame
                     int zero_padding, uint32_t flags, float* out, int64_t* numframes);
 /* processing::power_spectrum (processing.rs:179-181): (1/n_fft)*|rfft(zero-padded row)|, out [rows][n_fft/2+1] */
 int ss_power_spectrum(const float* frames, int64_t rows, int64_t frame_len, int64_t n_fft, float* out);
+/* librosa.feature.melspectrogram(y, sr, n_fft, hop_length, window="hann", center=True, pad_mode="reflect",
+ * power=2.0, n_mels, fmin, fmax, htk=False, norm="slaney") for a plan created with SS_FLAG_LIBROSA.
+ * out [ch][n_mels][1 + ttd / hop] (time-minor, like librosa's [..., n_mels, t]).  db_mode 0: power;
+ * 1: librosa.power_to_db(S, ref=1.0, amin=1e-10, top_db=None) = 10 log10(max(1e-10, S)).  Needs ttd > n_fft/2. */
+int ss_librosa_melspectrogram(ss_plan* plan, const float* pcm, int64_t ch, int64_t ttd, int64_t row_stride,
+                              float* out, int db_mode);
+int64_t ss_librosa_num_frames(int64_t ttd, int64_t hop); /* 1 + ttd / hop */
 /* processing::log_power_spectrum (processing.rs:194-214; private and unused in the reference):
  * 10 log10 of the power spectrum, -200 below 1e-20; with normalize != 0 the LAST value above the
  * threshold in row-major order (not the maximum: the reference's `mx` is overwritten by every
@@ -199,6 +211,8 @@ int ss_stack_frames_dev(void* cuda_stream, const float* d_in, int64_t n, int64_t
                         int64_t numframes);
 int ss_power_spectrum_dev(void* cuda_stream, const float* d_frames, int64_t rows, int64_t frame_len,
                           int64_t n_fft, float* d_out);
+int ss_librosa_melspectrogram_dev(ss_plan* plan, int dev_index, void* cuda_stream, const float* d_pcm, int64_t ch,
+                                  int64_t ttd, int64_t row_stride, float* d_out, int db_mode);
 int ss_log_power_spectrum_dev(void* cuda_stream, const float* d_frames, int64_t rows, int64_t frame_len,
                               int64_t n_fft, int normalize, float* d_out);
 int ss_cmvn_dev(void* cuda_stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols,

@@ -175,6 +175,14 @@ inline Array3 mel_spectrogram2(View2 signal, const SpeechConfig& cfg) {
   check(ss_mel_spectrogram(cfg.plan(), signal.data, (int64_t)signal.rows, (int64_t)signal.cols, (int64_t)signal.cols, out.v.data(), nullptr, 0));
   return out;
 }
+// librosa.feature.melspectrogram (Hann, centred reflect-padded frames, Slaney mel bank, power 2) for a config
+// created with flags = SS_FLAG_LIBROSA and frame_length = (hop + 0.5) / sample_rate -> [ch][n_mels][1 + ttd / hop]
+inline Array3 melspectrogram_librosa(View2 signal, const SpeechConfig& cfg, bool db = false) {
+  const int64_t tp = ss_librosa_num_frames((int64_t)signal.cols, (int64_t)cfg.frame_size);
+  Array3 out(signal.rows, cfg.num_filters, (size_t)(tp < 0 ? 0 : tp));
+  check(ss_librosa_melspectrogram(cfg.plan(), signal.data, (int64_t)signal.rows, (int64_t)signal.cols, (int64_t)signal.cols, out.v.data(), db ? 1 : 0));
+  return out;
+}
 // feature.rs:151 (intended semantics) -> [nf][T']
 inline Array2 mel_spectrogram1(View1 signal, const SpeechConfig& cfg) {
   const int64_t tp = ss_stft_num_frames((int64_t)signal.len, (int64_t)cfg.frame_size);

@@ -290,6 +290,7 @@ static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, voi
 static int check_speechpy(ss_plan* pl, int64_t clip_len, int64_t row_stride, int64_t* T) {
   if (!pl) return fail(SS_ERR_INVALID_ARG, "null plan");
   const Derived& d = pl->d;
+  if (d.librosa) return fail(SS_ERR_INVALID_ARG, "this plan was created with SS_FLAG_LIBROSA: use ss_librosa_melspectrogram");
   if (!d.speechpy_ok)
     return fail(SS_ERR_INVALID_ARG,
                 "framing undefined for this config: need 0 < round(sr*frame_length)=%lld <= fft_points=%lld and "
@@ -310,6 +311,7 @@ static int check_speechpy(ss_plan* pl, int64_t clip_len, int64_t row_stride, int
 static int check_stft(ss_plan* pl, int64_t ch, int64_t ttd, int64_t row_stride) {
   if (!pl) return fail(SS_ERR_INVALID_ARG, "null plan");
   const Derived& d = pl->d;
+  if (d.librosa) return fail(SS_ERR_INVALID_ARG, "this plan was created with SS_FLAG_LIBROSA: use ss_librosa_melspectrogram");
   if (!d.stft_ok)
     return fail(SS_ERR_INVALID_ARG,
                 "stft undefined for this config: need 0 < frame_size=%lld <= fft_points/2=%lld (usize underflow "
@@ -787,6 +789,95 @@ int ss_mel_spectrogram_dev(ss_plan* pl, int dev_index, void* stream, const float
                            int64_t row_stride, float* d_out, const float* d_mem_in, float* d_mem_out, int log_mode) {
   if (!d_out) return fail(SS_ERR_INVALID_ARG, "null output");
   return stft_dev(pl, dev_index, stream, d_pcm, ch, ttd, row_stride, nullptr, d_out, d_mem_in, d_mem_out, log_mode);
+}
+
+// ------------------------------------------------------------- librosa-compatible mel spectrogram
+// (SS_FLAG_LIBROSA plans).  No overlap memory, no dropped or zero frames: every one
+// of the 1 + ttd / hop centred frames is computed; rows are independent.
+static int check_librosa(ss_plan* pl, int64_t ch, int64_t ttd, int64_t row_stride, int db_mode) {
+  if (!pl) return fail(SS_ERR_INVALID_ARG, "null plan");
+  const Derived& d = pl->d;
+  if (!d.librosa) return fail(SS_ERR_INVALID_ARG, "ss_librosa_melspectrogram needs a plan created with SS_FLAG_LIBROSA");
+  if (!d.stft_ok) return fail(SS_ERR_INVALID_ARG, "need 0 < hop=%lld <= fft_points=%lld", (long long)d.H, (long long)d.W);
+  if (!pl->fft_ok) return fail(SS_ERR_UNSUPPORTED, "fft_points=%lld has a prime factor > 61", (long long)d.W);
+  if (d.W > 8192) return fail(SS_ERR_UNSUPPORTED, "fft_points=%lld > 8192", (long long)d.W);
+  if (ch < 0 || row_stride < ttd) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  if (ttd <= d.W / 2) return fail(SS_ERR_INVALID_ARG, "reflect padding needs more than n_fft/2 = %lld samples per row", (long long)(d.W / 2));
+  if (db_mode < 0 || db_mode > 1) return fail(SS_ERR_INVALID_ARG, "db_mode must be 0 or 1");
+  return SS_OK;
+}
+
+static void librosa_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float* d_pcm, int64_t ch, int64_t ttd,
+                           int64_t row_stride, float* d_out, int db_mode) {
+  const Derived& d = pl->d;
+  p->pcm = d_pcm;
+  p->n_rows = ch;
+  p->row_len = ttd;
+  p->row_stride = row_stride;
+  p->Tp = 1 + ttd / d.H;
+  p->n_pad = 0;
+  p->T = p->Tp;
+  p->T_out = p->Tp;
+  p->N = (int)d.W;
+  p->F = (int)d.F;
+  p->L = (int)d.W;
+  p->S = (int)d.H;
+  p->nf = d.nf;
+  p->nc = d.nc;
+  p->mode = kModeLibrosa;
+  p->wnorm = 1.0f;
+  p->log_mode = db_mode ? 2 : 0;
+  p->mel_out = d_out;
+  p->tab = dc->tab;
+}
+
+int64_t ss_librosa_num_frames(int64_t ttd, int64_t hop) { return (hop > 0 && ttd >= 0) ? 1 + ttd / hop : -1; }
+
+int ss_librosa_melspectrogram_dev(ss_plan* pl, int dev_index, void* stream, const float* d_pcm, int64_t ch, int64_t ttd,
+                                  int64_t row_stride, float* d_out, int db_mode) {
+  if (!d_out) return fail(SS_ERR_INVALID_ARG, "null output");
+  int rc = check_librosa(pl, ch, ttd, row_stride, db_mode);
+  if (rc) return rc;
+  if (dev_index < 0 || dev_index >= (int)pl->devs.size())
+    return fail(pl->devs.empty() ? SS_ERR_NO_DEVICE : SS_ERR_INVALID_ARG, "dev_index %d out of range", dev_index);
+  if (ch == 0) return SS_OK;
+  FrameParams p;
+  librosa_params(pl, &pl->devs[dev_index], &p, d_pcm, ch, ttd, row_stride, d_out, db_mode);
+  int e = launch_frames_generic(p, stream);
+  if (e) return cuda_fail((cudaError_t)e, "librosa mel kernel launch");
+  return SS_OK;
+}
+
+int ss_librosa_melspectrogram(ss_plan* pl, const float* pcm, int64_t ch, int64_t ttd, int64_t row_stride, float* out,
+                              int db_mode) {
+  if (!out) return fail(SS_ERR_INVALID_ARG, "null output");
+  int rc = check_librosa(pl, ch, ttd, row_stride, db_mode);
+  if (rc) return rc;
+  if (!pcm && ch > 0) return fail(SS_ERR_INVALID_ARG, "null pcm");
+  if (ch == 0) return SS_OK;
+  const Derived& d = pl->d;
+  const int64_t Tp = 1 + ttd / d.H;
+  const size_t per_row_in = (size_t)ttd * sizeof(float), per_row_out = (size_t)Tp * d.nf * sizeof(float);
+  return run_on_devices(pl, ch, [&](DeviceCtx* dc, int64_t c0, int64_t c1) -> int {
+    SS_CUDA(cudaSetDevice(dc->device));
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / std::max<size_t>(1, per_row_in + per_row_out)));
+    chunk = std::min(chunk, c1 - c0);
+    int li = 0;
+    for (int64_t a = c0; a < c1; a += chunk, li = (li + 1) % kLanes) {
+      const int64_t n = std::min(chunk, c1 - a);
+      Lane& ln = dc->lanes[li];
+      int r = ln.in.reserve(std::max<size_t>(16, n * per_row_in));
+      if (r) return r;
+      if ((r = ln.out.reserve(n * per_row_out))) return r;
+      if ((r = copy_rows_h2d(static_cast<float*>(ln.in.p), pcm + a * row_stride, n, ttd, row_stride, ln.stream))) return r;
+      FrameParams p;
+      librosa_params(pl, dc, &p, static_cast<float*>(ln.in.p), n, ttd, ttd, static_cast<float*>(ln.out.p), db_mode);
+      int e = launch_frames_generic(p, ln.stream);
+      if (e) return cuda_fail((cudaError_t)e, "librosa mel kernel launch");
+      SS_CUDA(cudaMemcpyAsync(out + (size_t)a * d.nf * Tp, ln.out.p, n * per_row_out, cudaMemcpyDeviceToHost, ln.stream));
+    }
+    return sync_lanes(dc);
+  });
 }
 
 // ------------------------------------------------------------- standalone processing functions

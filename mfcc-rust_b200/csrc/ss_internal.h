@@ -22,6 +22,7 @@ struct Derived {
   float dct2_scale = 2.f;
   bool stft_ok = false;      // 0 < H <= W/2
   bool speechpy_ok = false;  // 0 < L <= W and S > 0
+  bool librosa = false;      // SS_FLAG_LIBROSA: Hann window, centred reflect-padded frames, Slaney mel bank
 };
 
 // Mel filterbank in banded (CSR-like) form: filter i covers bins [start[i], start[i]+len[i])
@@ -68,7 +69,7 @@ struct DevTables {
   int radix[kMaxStages] = {0};
 };
 
-enum Mode : int { kModeSpeechpy = 0, kModeStft = 1, kModePowerSpectrum = 2 };
+enum Mode : int { kModeSpeechpy = 0, kModeStft = 1, kModePowerSpectrum = 2, kModeLibrosa = 3 };
 
 // One launch of the frame pipeline: `n_rows` rows (clips / channels), `T` frames each.
 struct FrameParams {

@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, con
   const int g = tid / tpg, lt = tid % tpg;
   const int64_t row = blockIdx.x / tiles_per_row;
   const int64_t t0 = (blockIdx.x % tiles_per_row) * TF;
-  const bool stft = p.mode == kModeStft;
+  const bool librosa = p.mode == kModeLibrosa;
+  const bool stft = p.mode == kModeStft || librosa;  // both: window from the table, |X|^2, time-minor mel output
   const int64_t fr = t0 + g;  // this thread group's frame
   float2* bufA = fftbuf + (size_t)g * 2 * (M + 1);
   float2* bufB = bufA + (M + 1);
@@ -149,6 +150,12 @@ __global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, con
       if (n >= N) return 0.f;
       if (!stft) return fetch_speechpy(p, rowp, fr, n);
       if (fr >= p.T) return 0.f;
+      if (librosa) {  // librosa.stft(center=True, pad_mode="reflect"): frame fr covers y_padded[fr H .. fr H + N)
+        int64_t i = fr * (int64_t)p.S + n - N / 2;
+        if (i < 0) i = -i;
+        if (i >= p.row_len) i = 2 * (p.row_len - 1) - i;
+        return rowp[i] * __ldg(&p.tab.window[n]);
+      }
       const int64_t q = q0 + n;
       float v;
       if (q >= rbase) {
@@ -251,7 +258,8 @@ __global__ void __launch_bounds__(256) k_frames_generic(const FrameParams p, con
         ssc_s[o] = acc2 / acc;
         log_s[o] = logf(acc);
       } else {
-        mel_s[o] = p.log_mode ? logf(zero_handling(acc)) : acc;
+        if (p.log_mode == 2) mel_s[o] = 10.0f * log10f(fmaxf(acc, 1e-10f));  // librosa.power_to_db(ref=1, amin=1e-10, top_db=None)
+        else mel_s[o] = p.log_mode ? logf(zero_handling(acc)) : acc;
       }
     }
   }
@@ -321,7 +329,7 @@ int launch_frames_generic(const FrameParams& p, void* stream) {
   const int TF = fpc;
   const size_t smem = (size_t)fpc * 2 * (M + 1) * sizeof(float2) + (size_t)(3 * TF * p.nf + TF + 16) * sizeof(float);
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
-  const int64_t frames = p.mode == kModeStft ? p.T_out : p.T;
+  const int64_t frames = (p.mode == kModeStft || p.mode == kModeLibrosa) ? p.T_out : p.T;
   const int64_t tiles_per_row = (frames + TF - 1) / TF;
   const int64_t nblocks = tiles_per_row * p.n_rows;
   if (nblocks <= 0) return 0;

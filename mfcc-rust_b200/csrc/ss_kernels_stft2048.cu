@@ -284,7 +284,7 @@ struct Stft2048Tables {
 };
 
 bool stft2048_supported(const Derived& d, const MelBank& mb) {
-  if (d.W != kW || !d.stft_ok || d.nf > kNfMax) return false;
+  if (d.librosa || d.W != kW || !d.stft_ok || d.nf > kNfMax) return false;
   MelProgram2048 mp;
   return build_program(d, mb, 1.0f, &mp);
 }

@@ -341,7 +341,7 @@ struct Stft2048mTables {
 };
 
 bool stft2048m_supported(const Derived& d, const MelBank& mb) {
-  if (d.W != kW || !d.stft_ok) return false;
+  if (d.librosa || d.W != kW || !d.stft_ok) return false;
   FragTables2048 ft;
   return build_frags(d, mb, 1.0f, &ft);
 }

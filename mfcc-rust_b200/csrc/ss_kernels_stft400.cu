@@ -311,7 +311,7 @@ struct Stft400Tables {
 };
 
 bool stft400_supported(const Derived& d, const MelBank& mb) {
-  if (d.W != kW || !d.stft_ok || d.nf > kNfMax) return false;
+  if (d.librosa || d.W != kW || !d.stft_ok || d.nf > kNfMax) return false;
   MelProgram400 mp;
   return build_program(d, mb, 1.0f, &mp);
 }

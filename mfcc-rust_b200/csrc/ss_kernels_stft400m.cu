@@ -454,7 +454,7 @@ struct Stft400mTables {
 };
 
 bool stft400m_supported(const Derived& d, const MelBank& mb) {
-  if (d.W != kW || !d.stft_ok) return false;
+  if (d.librosa || d.W != kW || !d.stft_ok) return false;
   FragTables400 ft;
   if (!build_frags(d, mb, 1.0f, &ft)) return false;
   const size_t fixed = (size_t)(kTabFixed + ft.mel.size()) * sizeof(float);

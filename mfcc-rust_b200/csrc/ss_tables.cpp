@@ -57,13 +57,73 @@ std::string derive(const ss_config& c, Derived* d) {
   d->n_pad = d->stft_ok ? d->W / d->H - 1 : -1;             // functions.rs:96
   // config.rs:178: 1.0 / (fft_points.pow(2) as f32 / (2 * frame_size) as f32)
   d->wnorm = d->H > 0 ? 1.0f / ((float)(d->W * d->W) / (float)(2 * d->H)) : 0.f;
+  d->librosa = (c.flags & SS_FLAG_LIBROSA) != 0;
+  if (d->librosa) {  // librosa.stft: any hop <= n_fft, no dropped / zero frames, no normalisation
+    if (c.fft_points % 2) return "SS_FLAG_LIBROSA needs an even fft_points";
+    d->stft_ok = d->H > 0 && d->H <= d->W;
+    d->speechpy_ok = false;
+    d->n_pad = 0;
+    d->wnorm = 1.0f;
+  }
   return "";
 }
 
 static inline float hz_to_mel(float f) { return 1127.0f * std::log(1.0f + f / 700.0f); }      // functions.rs:19-21
 static inline float mel_to_hz(float m) { return 700.0f * (std::exp(m / 1127.0f) - 1.0f); }    // functions.rs:31-33
 
+// Slaney mel scale (librosa.hz_to_mel / mel_to_hz with htk=False): linear below 1 kHz, log above
+static inline double slaney_hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static inline double slaney_mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm="slaney"), computed in f64 and
+// stored as f32 like librosa does, in the banded form the kernels use
+static void build_melbank_slaney(const Derived& d, MelBank* mb) {
+  const int nf = d.nf;
+  const double sr = (double)d.cfg.sample_rate;
+  const double m0 = slaney_hz_to_mel(d.cfg.low_frequency), m1 = slaney_hz_to_mel(d.cfg.high_frequency);
+  std::vector<double> fpt(nf + 2);
+  for (int i = 0; i < nf + 2; ++i) fpt[i] = slaney_mel_to_hz(m0 + (m1 - m0) * (double)i / (double)(nf + 1));
+  mb->idx.assign(nf + 2, 0);
+  mb->start.assign(nf, 0);
+  mb->len.assign(nf, 0);
+  mb->wofs.assign(nf, 0);
+  mb->w.clear();
+  mb->max_len = 0;
+  mb->max_bin = -1;
+  for (int i = 0; i < nf; ++i) {
+    const double enorm = 2.0 / (fpt[i + 2] - fpt[i]);
+    int lo = -1, hi = -1;
+    std::vector<float> w((size_t)d.F, 0.f);
+    for (int64_t k = 0; k < d.F; ++k) {
+      const double f = (double)k * sr / (double)d.W;
+      const double lower = (f - fpt[i]) / (fpt[i + 1] - fpt[i]), upper = (fpt[i + 2] - f) / (fpt[i + 2] - fpt[i + 1]);
+      const double v = std::max(0.0, std::min(lower, upper)) * enorm;
+      w[k] = (float)v;
+      if (w[k] != 0.f) {
+        if (lo < 0) lo = (int)k;
+        hi = (int)k;
+      }
+    }
+    mb->wofs[i] = (int)mb->w.size();
+    if (lo >= 0) {
+      mb->start[i] = lo;
+      mb->len[i] = hi - lo + 1;
+      for (int k = lo; k <= hi; ++k) mb->w.push_back(w[k]);
+      mb->max_len = std::max(mb->max_len, mb->len[i]);
+      mb->max_bin = std::max(mb->max_bin, hi);
+    }
+  }
+  if (mb->w.empty()) mb->w.push_back(0.f);
+}
+
 void build_melbank(const Derived& d, MelBank* mb) {
+  if (d.librosa) return build_melbank_slaney(d, mb);
   // feature.rs:43-88 with functions::triangle (functions.rs:43-60)
   const int nf = d.nf;
   const float sr = (float)d.cfg.sample_rate;
@@ -119,6 +179,10 @@ void build_window(const Derived& d, std::vector<float>* out) {
   const double pi = 3.14159265358979323846264338327950288;
   const int64_t W = d.W, Wh = d.W / 2;
   out->resize(W);
+  if (d.librosa) {  // scipy.signal.get_window("hann", W, fftbins=True): periodic Hann
+    for (int64_t i = 0; i < W; ++i) (*out)[i] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * (double)i / (double)W));
+    return;
+  }
   for (int64_t i = 0; i < W; ++i) {
     double s = std::sin(0.5 * pi * ((double)i + 0.5) / (double)Wh);
     (*out)[i] = (float)std::sin(0.5 * pi * s * s);

@@ -124,6 +124,25 @@ impl SpeechConfig {
         })
     }
 
+    /// A plan for `feature::melspectrogram_librosa` (SS_FLAG_LIBROSA = 0x4): periodic Hann window of
+    /// `n_fft`, centred reflect-padded frames every `hop_length` samples, Slaney mel bank.  The hop travels
+    /// in `frame_length` (the library derives hop = trunc(frame_length * sample_rate) like config.rs:154).
+    pub fn librosa(sample_rate: usize, n_fft: usize, hop_length: usize, n_mels: usize, fmin: f32, fmax: f32) -> Self {
+        Self::from_raw(ffi::ss_config {
+            sample_rate: sample_rate as i64,
+            fft_points: n_fft as i64,
+            frame_length: (hop_length as f32 + 0.5) / sample_rate as f32,
+            frame_stride: hop_length as f32 / sample_rate as f32,
+            num_cepstral: n_mels.min(13) as i64,
+            num_filters: n_mels as i64,
+            low_frequency: fmin,
+            high_frequency: fmax,
+            dc_elimination: 1,
+            flags: 0x4,
+            dct2_scale: 0.0,
+        })
+    }
+
     fn from_raw(raw: ffi::ss_config) -> Self {
         let mut plan: *mut ffi::ss_plan = ptr::null_mut();
         // n_devices = -1: every visible GPU; batches shard over them

@@ -68,6 +68,19 @@ pub fn mel_spectrogram2(signal: ArrayView2<f32>, cfg: &SpeechConfig) -> Array3<f
     out
 }
 
+/// librosa.feature.melspectrogram(y, sr, n_fft, hop_length, window="hann", center=True, pad_mode="reflect",
+/// power=2.0, n_mels, fmin, fmax, htk=False, norm="slaney") on the rows of `signal`, for a config made by
+/// `SpeechConfig::librosa` -> [ch, n_mels, 1 + ttd / hop]; `db`: power_to_db(ref=1.0, amin=1e-10, top_db=None).
+/// Not in the reference (its README names librosa compatibility as the goal).
+pub fn melspectrogram_librosa(signal: ArrayView2<f32>, cfg: &SpeechConfig, db: bool) -> Array3<f32> {
+    let x = signal.as_standard_layout();
+    let (ch, ttd) = x.dim();
+    let tp = unsafe { ffi::ss_librosa_num_frames(ttd as i64, cfg.frame_size as i64) }.max(0) as usize;
+    let mut out = Array3::<f32>::zeros((ch, cfg.num_filters, tp));
+    unsafe { check(ffi::ss_librosa_melspectrogram(cfg.plan, x.as_ptr(), ch as i64, ttd as i64, ttd as i64, out.as_mut_ptr(), db as i32)) };
+    out
+}
+
 /// feature.rs:151 — intended semantics (decision D2): one-row mel_spectrogram2 -> [nf, T']
 pub fn mel_spectrogram1(signal: ArrayView1<f32>, cfg: &SpeechConfig) -> Array2<f32> {
     let x = signal.as_standard_layout();

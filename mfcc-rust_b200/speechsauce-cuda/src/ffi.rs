@@ -87,6 +87,11 @@ extern "C" {
     pub fn ss_stack_frames(input: *const f32, n: i64, frame_len: i64, frame_step: i64, zero_padding: c_int, flags: u32,
                            out: *mut f32, numframes: *mut i64) -> c_int;
     pub fn ss_power_spectrum(frames: *const f32, rows: i64, frame_len: i64, n_fft: i64, out: *mut f32) -> c_int;
+    pub fn ss_librosa_melspectrogram(plan: *mut ss_plan, pcm: *const f32, ch: i64, ttd: i64, row_stride: i64, out: *mut f32,
+                                     db_mode: c_int) -> c_int;
+    pub fn ss_librosa_melspectrogram_dev(plan: *mut ss_plan, dev_index: c_int, cuda_stream: *mut c_void, d_pcm: *const f32,
+                                         ch: i64, ttd: i64, row_stride: i64, d_out: *mut f32, db_mode: c_int) -> c_int;
+    pub fn ss_librosa_num_frames(ttd: i64, hop: i64) -> i64;
     pub fn ss_log_power_spectrum(frames: *const f32, rows: i64, frame_len: i64, n_fft: i64, normalize: c_int, out: *mut f32) -> c_int;
     pub fn ss_log_power_spectrum_dev(cuda_stream: *mut c_void, d_frames: *const f32, rows: i64, frame_len: i64, n_fft: i64,
                                      normalize: c_int, d_out: *mut f32) -> c_int;

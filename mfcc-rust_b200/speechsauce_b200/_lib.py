@@ -21,7 +21,7 @@ class SpeechsauceError(RuntimeError):
 
 
 SS_OK, SS_ERR_INVALID_ARG, SS_ERR_CUDA, SS_ERR_UNSUPPORTED, SS_ERR_NO_DEVICE, SS_ERR_ALLOC = 0, -1, -2, -3, -4, -5
-SS_FLAG_FRAMING_LITERAL, SS_FLAG_FORCE_GENERIC = 0x1, 0x2
+SS_FLAG_FRAMING_LITERAL, SS_FLAG_FORCE_GENERIC, SS_FLAG_LIBROSA = 0x1, 0x2, 0x4
 SS_CMVN_NONE, SS_CMVN_MEAN, SS_CMVN_MEAN_VAR = 0, 1, 2
 
 
@@ -91,6 +91,9 @@ SYMBOLS = {
     "ss_stack_frames_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, C.c_uint32, _fp, _i64]),
     "ss_power_spectrum_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, _fp]),
     "ss_log_power_spectrum": (C.c_int, [_fp, _i64, _i64, _i64, C.c_int, _fp]),
+    "ss_librosa_melspectrogram": (C.c_int, [_vp, _fp, _i64, _i64, _i64, _fp, C.c_int]),
+    "ss_librosa_melspectrogram_dev": (C.c_int, [_vp, C.c_int, _vp, _fp, _i64, _i64, _i64, _fp, C.c_int]),
+    "ss_librosa_num_frames": (_i64, [_i64, _i64]),
     "ss_log_power_spectrum_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, _fp]),
     "ss_cmvn_dev": (C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_int, _fp]),
     "ss_derivative_extraction": (C.c_int, [_fp, _i64, _i64, C.c_int, _fp]),

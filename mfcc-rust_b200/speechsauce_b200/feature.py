@@ -49,6 +49,27 @@ def features(signal, cfg, *, mfe=False, energy=False, lmfe=False, ssc=False, mfc
     return {k: (v[0] if one else v) for k, v in out.items()}
 
 
+def librosa_config(sr, n_fft=2048, hop_length=512, n_mels=128, fmin=0.0, fmax=None, **kw):
+    """A plan for `melspectrogram_librosa` (SS_FLAG_LIBROSA).  frame_length carries the hop: the library
+    derives hop = trunc(frame_length * sample_rate) in f32 like config.rs:154, hence the half-sample margin."""
+    from .config import SpeechConfig
+    return SpeechConfig(sample_rate=sr, fft_points=n_fft, frame_length=(hop_length + 0.5) / sr, frame_stride=hop_length / sr,
+                        num_cepstral=min(13, n_mels), num_filters=n_mels, low_frequency=fmin, high_frequency=fmax,
+                        flags=_lib.SS_FLAG_LIBROSA, **kw)
+
+
+def melspectrogram_librosa(y, cfg, db=False):
+    """librosa.feature.melspectrogram(y, sr, n_fft, hop_length, window="hann", center=True,
+    pad_mode="reflect", power=2.0, n_mels, fmin, fmax, htk=False, norm="slaney") -> [..., n_mels, 1 + n / hop];
+    `db`: librosa.power_to_db(S, ref=1.0, amin=1e-10, top_db=None)."""
+    x, one = _rows(y)
+    n, ttd = x.shape
+    T = int(lib.ss_librosa_num_frames(ttd, cfg.frame_size))
+    out = np.empty((n, cfg.num_filters, max(T, 0)), np.float32)
+    check(lib.ss_librosa_melspectrogram(cfg.plan, _lib.fptr(x), n, ttd, ttd, _lib.fptr(out), int(bool(db))))
+    return out[0] if one else out
+
+
 def mfe(signal, cfg):
     """feature::mfe (feature.rs:200-233) -> (features [T, nf], frame_energies [T])."""
     r = features(signal, cfg, mfe=True, energy=True)

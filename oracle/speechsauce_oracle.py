@@ -251,6 +251,59 @@ def log_power_spectrum(frames, fft_points, normalize=True, dtype=F32):
     return out
 
 
+# ---- librosa-compatible mel spectrogram (no reference code: the reference's
+# README.md:3,44-46 and Contributing.md:7-8 only name librosa compatibility as the goal).  Restated
+# from librosa's documented algorithm (librosa.stft / librosa.filters.mel / librosa.power_to_db) and
+# pinned against torchaudio.transforms.MelSpectrogram in tests/test_oracle_kat.py.
+def _slaney_hz_to_mel(f):
+    f = np.asarray(f, np.float64)
+    f_sp, min_log_hz = 200.0 / 3.0, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, f / f_sp)
+
+
+def _slaney_mel_to_hz(m):
+    m = np.asarray(m, np.float64)
+    f_sp, min_log_hz = 200.0 / 3.0, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def librosa_mel_filters(sr, n_fft, n_mels, fmin=0.0, fmax=None):
+    """librosa.filters.mel(sr=, n_fft=, n_mels=, fmin=, fmax=, htk=False, norm="slaney") -> [n_mels, 1 + n_fft/2] f32"""
+    fmax = sr / 2.0 if fmax is None else fmax
+    fftfreqs = np.arange(1 + n_fft // 2, dtype=np.float64) * sr / n_fft
+    mel_f = _slaney_mel_to_hz(np.linspace(_slaney_hz_to_mel(fmin), _slaney_hz_to_mel(fmax), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    w = np.maximum(0.0, np.minimum(lower, upper))
+    w *= (2.0 / (mel_f[2:] - mel_f[:-2]))[:, None]
+    return w.astype(np.float32)
+
+
+def librosa_melspectrogram(y, sr, n_fft=2048, hop_length=512, n_mels=128, fmin=0.0, fmax=None, db=False, dtype=F32):
+    """librosa.feature.melspectrogram(y=, sr=, n_fft=, hop_length=, window="hann", center=True,
+    pad_mode="reflect", power=2.0, n_mels=, fmin=, fmax=) on rows of `y`; `db` applies
+    librosa.power_to_db(S, ref=1.0, amin=1e-10, top_db=None).  Returns [..., n_mels, 1 + n / hop]."""
+    y = np.asarray(y, dtype)
+    one = y.ndim == 1
+    y2 = y[None] if one else y
+    n = y2.shape[1]
+    win = (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n_fft) / n_fft)).astype(dtype)   # periodic Hann
+    yp = np.pad(y2, ((0, 0), (n_fft // 2, n_fft // 2)), mode="reflect")
+    T = 1 + n // hop_length
+    idx = np.arange(T)[:, None] * hop_length + np.arange(n_fft)[None, :]
+    frames = yp[:, idx] * win                                       # [rows, T, n_fft]
+    X = np.fft.rfft(frames.astype(np.float64), axis=-1)
+    S = (X.real ** 2 + X.imag ** 2).astype(dtype)                    # power = 2
+    mel = np.einsum("mf,rtf->rmt", librosa_mel_filters(sr, n_fft, n_mels, fmin, fmax).astype(dtype), S).astype(dtype)
+    if db:
+        mel = (dtype(10.0) * np.log10(np.maximum(mel, dtype(1e-10)))).astype(dtype)
+    return mel[0] if one else mel
+
+
 def cmvn(vec, variance_normalization=False, dtype=F32):
     """processing.rs:265-300.  mean_axis(0): sequential row accumulation then /rows;
     std_axis(0, ddof=0): Welford (ndarray 0.15 `var_axis`); eps = 2^-30."""

@@ -365,6 +365,35 @@ def test_log_power_spectrum():
     assert (silent == -200.0).all()
 
 
+def test_librosa_mode_matches_oracle():
+    """SS_FLAG_LIBROSA: Hann window, centred reflect-padded frames, Slaney mel bank, |X|^2, optional
+    power_to_db; checked against the oracle that tests/test_oracle_kat.py pins to torchaudio."""
+    for sr, n_fft, hop, n_mels, fmin, fmax, n in [(22050, 2048, 512, 128, 0.0, None, 22050 + 37),
+                                                  (16000, 400, 160, 80, 0.0, 8000.0, 16000),
+                                                  (16000, 512, 128, 40, 50.0, 7000.0, 3001), (8000, 256, 256, 26, 0.0, None, 129)]:
+        cfg = sb.feature.librosa_config(sr, n_fft, hop, n_mels, fmin, fmax)
+        assert cfg.frame_size == hop
+        y = o.synth_signal(3, n, 0x5EED0310 + n_fft)
+        y[1, : n // 2] = 0.0
+        got = sb.feature.melspectrogram_librosa(y, cfg)
+        want = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, fmin, fmax)
+        assert got.shape == want.shape == (3, n_mels, 1 + n // hop)
+        assert_spec_close(got, want, what=f"librosa mel {n_fft}/{hop}/{n_mels}")
+        assert_spec_close(sb.feature.melspectrogram_librosa(y[2], cfg), want[2], what="1-D input")
+        gdb = sb.feature.melspectrogram_librosa(y, cfg, db=True)
+        wdb = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, fmin, fmax, db=True)
+        loud = want > 1e-6 * want.max()
+        assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what="power_to_db")   # 1e-4 relative = 4.3e-4 dB
+        assert (gdb >= -100.001).all()
+    cfg = sb.feature.librosa_config(16000, 400, 160, 80)
+    with pytest.raises(sb.SpeechsauceError):
+        sb.feature.melspectrogram_librosa(np.zeros(200, np.float32), cfg)          # reflect padding needs > n_fft/2 samples
+    with pytest.raises(sb.SpeechsauceError):
+        sb.feature.mel_spectrogram2(np.zeros((1, 4000), np.float32), cfg)          # reference-semantics entry point
+    with pytest.raises(sb.SpeechsauceError):
+        sb.feature.melspectrogram_librosa(np.zeros(4000, np.float32), sb.SpeechConfig(**CONFIGS["c4"]))
+
+
 def test_cmvn():
     rng = np.random.default_rng(3)
     v = rng.uniform(0, 1, (50, 100)).astype(np.float32)  # the reference's test (lib.rs:71-91)

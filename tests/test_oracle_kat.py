@@ -97,6 +97,29 @@ def test_log_power_spectrum_closed_form_and_last_value_normaliser():
     assert (silent == -200.0).all()   # mx stays 1e-20
 
 
+def test_librosa_mode_oracle_is_pinned_by_torchaudio():
+    """The librosa-compatible mode has no reference code; its oracle restates
+    librosa's documented algorithm and is pinned here against an independent implementation of the
+    same definition, torchaudio.transforms.MelSpectrogram(norm="slaney", mel_scale="slaney")."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    for sr, n_fft, hop, n_mels, fmin, fmax in [(22050, 2048, 512, 128, 0.0, None), (16000, 400, 160, 80, 0.0, 8000.0),
+                                               (16000, 512, 128, 40, 50.0, 7000.0)]:
+        y = o.synth_signal(2, sr + 37, 0x5EED0300 + n_fft)
+        fm = sr / 2.0 if fmax is None else fmax
+        ms = torchaudio.transforms.MelSpectrogram(sample_rate=sr, n_fft=n_fft, hop_length=hop, f_min=fmin, f_max=fm,
+                                                  n_mels=n_mels, power=2.0, center=True, pad_mode="reflect",
+                                                  norm="slaney", mel_scale="slaney")
+        want = ms(torch.from_numpy(y)).numpy()
+        got = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, fmin, fmax)
+        assert got.shape == want.shape == (2, n_mels, 1 + (sr + 37) // hop)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6 * want.max())
+        fb = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, fmin, fm, n_mels, sr, norm="slaney", mel_scale="slaney")
+        np.testing.assert_allclose(o.librosa_mel_filters(sr, n_fft, n_mels, fmin, fmax), fb.numpy().T, atol=2e-6)
+    db = o.librosa_melspectrogram(np.zeros(4000, np.float32), 16000, 400, 160, 80, db=True)
+    assert np.abs(db + 100.0).max() < 1e-4     # 10 log10(amin = 1e-10)
+
+
 def test_filterbank_indices_and_peaks():
     want = [0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 18, 20, 22, 25, 27, 29, 32, 35, 38, 41, 44,
             48, 51, 55, 60, 64, 69, 74, 79, 85, 91, 98, 105, 112, 120, 129]
