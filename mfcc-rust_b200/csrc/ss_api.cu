@@ -831,6 +831,15 @@ static void librosa_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const flo
   p->tab = dc->tab;
 }
 
+// the register-FFT kernel when n_fft = 400 (Whisper's front end), else the generic one
+static int launch_librosa_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
+  if (pl->stft400m && dc->stft400m && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+    const int e = launch_stft400m(p, dc->stft400m, dc->sm_count, stream);
+    if (e != -1000) return e;
+  }
+  return launch_frames_generic(p, stream);
+}
+
 int64_t ss_librosa_num_frames(int64_t ttd, int64_t hop) { return (hop > 0 && ttd >= 0) ? 1 + ttd / hop : -1; }
 
 int ss_librosa_melspectrogram_dev(ss_plan* pl, int dev_index, void* stream, const float* d_pcm, int64_t ch, int64_t ttd,
@@ -843,7 +852,7 @@ int ss_librosa_melspectrogram_dev(ss_plan* pl, int dev_index, void* stream, cons
   if (ch == 0) return SS_OK;
   FrameParams p;
   librosa_params(pl, &pl->devs[dev_index], &p, d_pcm, ch, ttd, row_stride, d_out, db_mode);
-  int e = launch_frames_generic(p, stream);
+  int e = launch_librosa_any(pl, &pl->devs[dev_index], p, stream);
   if (e) return cuda_fail((cudaError_t)e, "librosa mel kernel launch");
   return SS_OK;
 }
@@ -872,7 +881,7 @@ int ss_librosa_melspectrogram(ss_plan* pl, const float* pcm, int64_t ch, int64_t
       if ((r = copy_rows_h2d(static_cast<float*>(ln.in.p), pcm + a * row_stride, n, ttd, row_stride, ln.stream))) return r;
       FrameParams p;
       librosa_params(pl, dc, &p, static_cast<float*>(ln.in.p), n, ttd, ttd, static_cast<float*>(ln.out.p), db_mode);
-      int e = launch_frames_generic(p, ln.stream);
+      int e = launch_librosa_any(pl, dc, p, ln.stream);
       if (e) return cuda_fail((cudaError_t)e, "librosa mel kernel launch");
       SS_CUDA(cudaMemcpyAsync(out + (size_t)a * d.nf * Tp, ln.out.p, n * per_row_out, cudaMemcpyDeviceToHost, ln.stream));
     }

@@ -49,13 +49,19 @@ constexpr int kMaxWarps = SS_STFT400M_WARPS, kMaxThreads = kMaxWarps * 32;
 constexpr int kSmemBudget = 226 * 1024;
 constexpr int kXchFrame = 202;           // float2 per frame: 20 rows x 10 + 2 (frame stride = 10 mod 16 banks)
 constexpr int kXchFloats = kFpw * kXchFrame * 2;  // 1212
-constexpr int kPs = 104;                 // P row stride: bins 0..100 + zero pad; 104 % 32 == 8 -> conflict-free LDS.64 B fragments
-constexpr int kKs = kPs / 8;             // 13 k-steps of 8 bins
-constexpr int kKsTab = kKs + 1;          // bands are padded to an even number of k-steps
-constexpr int kTileFloats = kRing * kPs + 8;  // + slack for the padded k-step of the last row
+// |X|^2 tile geometry.  Reference semantics: the bank reaches bins 0..100 only (quirk Q8) -> 104 columns;
+// librosa plans (SS_FLAG_LIBROSA): the Slaney bank spans all 201 bins -> 208 columns.  Both strides are
+// 8 mod 32 words, so the LDS.64 B-fragment loads stay conflict-free.
+template <bool FULL>
+struct Geo {
+  static constexpr int kPs = FULL ? 208 : 104;     // P row stride
+  static constexpr int kKs = kPs / 8;              // k-steps of 8 bins
+  static constexpr int kTileFloats = kRing * kPs + 8;  // + slack for the padded k-step of the last row
+  static constexpr int kWarpFloats = kFpw * 202 * 2 + kTileFloats;
+};
 constexpr int kStage = kW + (kFpw - 1) * 160;    // samples of one round when hop = 160 (staging needs hop == 160)
-constexpr int kWarpFloats = kXchFloats + kTileFloats;
-static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
+static_assert(Geo<false>::kWarpFloats % 4 == 0 && Geo<true>::kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
+static_assert(Geo<false>::kWarpFloats == kXchFloats + Geo<false>::kTileFloats, "transpose tile size");
 constexpr int kMtMax = 8;                // nf <= 128
 constexpr int kTwRow = 44;               // floats per lane row of the W200 table (20 float2 + pad)
 // fixed table blob (floats)
@@ -121,8 +127,11 @@ __device__ __forceinline__ void pair_split(float2 za, float2 zb, float2 w, float
   xb = ssfft::csub(e, tt);
 }
 
-template <bool STFT>  // STFT: also / only the complex output of functions::stft1/2
+// STFT: also / only the complex output of functions::stft1/2.  FULL: librosa plan -- centred frames with
+// reflect padding, every one of the 201 bins kept for the full-spectrum Slaney bank, optional power_to_db.
+template <bool STFT, bool FULL>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs a) {
+  constexpr int kPs = Geo<FULL>::kPs, kWarpFloats = Geo<FULL>::kWarpFloats;
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
   float* warp_s = smem + a.tab_floats + (threadIdx.x >> 5) * kWarpFloats;
@@ -158,7 +167,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
 
   const int64_t span = p.Tp * (int64_t)p.S;
   const int64_t memlen = p.N - p.S;
-  const int c0 = (p.n_pad + 1) * p.S - p.N;  // row-relative position of frame 0's first sample (<= 0)
+  // row-relative position of frame 0's first sample (<= 0): the stream model of the reference, or the centre
+  // of frame 0 on sample 0 (librosa.stft(center=True))
+  const int c0 = FULL ? -kW / 2 : (p.n_pad + 1) * p.S - p.N;
   const int T_out = (int)p.T_out, Tc = (int)p.T;
   const int n_warps = blockDim.x >> 5;
 
@@ -238,8 +249,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
               const int64_t q = q0 + 20 * j;
               // samples of this row beyond row_len are zero padding; earlier positions come from the stream
               const int64_t o = o0 + 2 * u + 20 * j;
-              const float xa = o >= 0 ? (o < p.row_len ? rowp[o] : 0.f) : stream_at(p, q);
-              const float xb = o + 1 >= 0 ? (o + 1 < p.row_len ? rowp[o + 1] : 0.f) : stream_at(p, q + 1);
+              float xa, xb;
+              if (FULL) {  // pad_mode="reflect"
+                const int64_t n = p.row_len;
+                int64_t ia = o < 0 ? -o : o, ib = o + 1 < 0 ? -(o + 1) : o + 1;
+                if (ia >= n) ia = 2 * (n - 1) - ia;
+                if (ib >= n) ib = 2 * (n - 1) - ib;
+                xa = rowp[ia];
+                xb = rowp[ib];
+              } else {
+                xa = o >= 0 ? (o < p.row_len ? rowp[o] : 0.f) : stream_at(p, q);
+                xb = o + 1 >= 0 ? (o + 1 < p.row_len ? rowp[o + 1] : 0.f) : stream_at(p, q + 1);
+              }
               v[j] = make_float2(xa * w.x, xb * w.y);
             });
           }
@@ -301,16 +322,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
             float2 xa, xb;
             pair_split(za, zb, (e < 5 ? twA : twB)[20 * e], xa, xb);
             const float2 m = make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
-            if constexpr (e < 5) pA[20 * e] = m.x;        // bin u + 20 e <= 89
-            else Pf[plo[e - 5]] = isz ? m.x : m.y;        // the bin of the pair that is <= 100
+            if constexpr (FULL) {  // both bins of the pair: k and 200 - k
+              const int k = (e < 5 ? u : kb) + 20 * e;
+              Pf[k] = m.x;
+              Pf[kM - k] = m.y;
+            } else if constexpr (e < 5) {
+              pA[20 * e] = m.x;                           // bin u + 20 e <= 89
+            } else {
+              Pf[plo[e - 5]] = isz ? m.x : m.y;           // the bin of the pair that is <= 100
+            }
             if (STFT && so) {
               const int k = (e < 5 ? u : kb) + 20 * e;    // xa is bin k, xb the conjugate of bin 200 - k
               so[k] = make_float2(xa.x * hs, xa.y * hs);
               so[kM - k] = make_float2(xb.x * hs, -xb.y * hs);
             }
           });
-          if (isz) {  // X[100] = conj Z[100]; x4 to match the pairs; bins 101..103 stay zero
-            *reinterpret_cast<float4*>(Pf + 100) = make_float4(4.0f * fmaf(gA[5].x, gA[5].x, gA[5].y * gA[5].y), 0.f, 0.f, 0.f);
+          if (isz) {  // X[100] = conj Z[100]; x4 to match the pairs; the pad bins stay zero
+            Pf[100] = 4.0f * fmaf(gA[5].x, gA[5].x, gA[5].y * gA[5].y);
             if (STFT && so) so[100] = make_float2(gA[5].x * p.wnorm, -gA[5].y * p.wnorm);
           }
         }
@@ -361,7 +389,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
             const int f = 16 * mt + g + 8 * hh;
             float m0 = accB[2 * hh] + (accS[2 * hh] + accT[2 * hh]);
             float m1 = accB[2 * hh + 1] + (accS[2 * hh + 1] + accT[2 * hh + 1]);
-            if (p.log_mode) {
+            if (FULL && p.log_mode == 2) {  // librosa.power_to_db(ref=1, amin=1e-10, top_db=None)
+              m0 = 10.0f * log10f(fmaxf(m0, 1e-10f));
+              m1 = 10.0f * log10f(fmaxf(m1, 1e-10f));
+            } else if (p.log_mode) {
               m0 = fast_ln(zero_handling(m0));
               m1 = fast_ln(zero_handling(m1));
             }
@@ -403,8 +434,9 @@ struct FragTables400 {
 // group's band are stored, padded to an even count.
 static bool build_frags(const Derived& d, const MelBank& mb, float pscale, FragTables400* ft) {
   const int nf = d.nf;
-  if (mb.max_bin > 100 || nf > 16 * kMtMax || nf < 1) return false;
-  const int MT = (nf + 15) / 16, ncol = 8 * kKsTab;
+  const int kKs = d.librosa ? Geo<true>::kKs : Geo<false>::kKs;
+  if (mb.max_bin > (d.librosa ? kM : kM / 2) || nf > 16 * kMtMax || nf < 1) return false;
+  const int MT = (nf + 15) / 16, ncol = 8 * (kKs + 1);  // bands are padded to an even number of k-steps
   ft->n_mt = MT;
   std::vector<float> dense((size_t)16 * MT * ncol, 0.f);  // [filter][bin]
   for (int f = 0; f < nf; ++f)
@@ -451,14 +483,16 @@ struct Stft400mTables {
   int tab_floats = 0;
   int n_mt = 0;
   int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
+  bool full = false;  // librosa plan: full-spectrum tile, centred reflect-padded frames
 };
 
 bool stft400m_supported(const Derived& d, const MelBank& mb) {
-  if (d.librosa || d.W != kW || !d.stft_ok) return false;
+  if (d.W != kW || !d.stft_ok) return false;
   FragTables400 ft;
   if (!build_frags(d, mb, 1.0f, &ft)) return false;
   const size_t fixed = (size_t)(kTabFixed + ft.mel.size()) * sizeof(float);
-  return fixed + 4 * kWarpFloats * sizeof(float) <= (size_t)kSmemBudget;
+  const size_t per_warp = (d.librosa ? Geo<true>::kWarpFloats : Geo<false>::kWarpFloats) * sizeof(float);
+  return fixed + 4 * per_warp <= (size_t)kSmemBudget;
 }
 
 int stft400m_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft400mTables** out) {
@@ -483,6 +517,7 @@ int stft400m_build_tables(const Derived& d, const MelBank& mb, const std::vector
   Stft400mTables* t = new Stft400mTables;
   t->tab_floats = (int)h.size();
   t->n_mt = ft.n_mt;
+  t->full = d.librosa;
   for (int i = 0; i < kMtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_n2[i] = ft.ks_n2[i]; t->mel_base[i] = ft.mel_base[i]; }
   cudaError_t e = cudaMalloc(&t->d_tab, h.size() * sizeof(float));
   if (e != cudaSuccess) { delete t; return (int)e; }
@@ -501,6 +536,8 @@ void stft400m_free_tables(Stft400mTables* t) {
 // mel_spectrogram (p.mel_out) and / or the complex STFT (p.stft_out); returns -1000 if the shape is declined
 int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count, void* stream) {
   if (p.N != kW || (!p.mel_out && !p.stft_out) || p.T_out < 1 || p.T_out > (1LL << 31) - 64) return -1000;
+  if (t->full != (p.mode == kModeLibrosa) || (t->full && (p.stft_out || !p.mel_out))) return -1000;
+  const int kWarpFloats = t->full ? Geo<true>::kWarpFloats : Geo<false>::kWarpFloats;
   Stft400mArgs a;
   a.p = p;
   a.tab = t->d_tab;
@@ -521,7 +558,7 @@ int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count,
   a.n_items = p.n_rows * (int64_t)a.chunks_per_row;
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
   // whole rounds can be staged with 16-byte cp.async when every round starts 16-byte aligned
-  const int64_t c0 = (int64_t)(p.n_pad + 1) * p.S - p.N;
+  const int64_t c0 = t->full ? -kW / 2 : (int64_t)(p.n_pad + 1) * p.S - p.N;
   a.stage = p.S == 160 && (p.row_stride % 4 == 0) && (((c0 % 4) + 4) % 4 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
   a.pair_ok = (p.T_out % 2 == 0) && (reinterpret_cast<uintptr_t>(p.mel_out) % 8 == 0);
   // small jobs: fewer warps per CTA so that the items spread over the SMs instead of queueing on a few
@@ -530,17 +567,16 @@ int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count,
   const int64_t grid = std::min<int64_t>((a.n_items + wl - 1) / wl, (int64_t)sm_count);
   if (grid <= 0) return 0;
   cudaError_t e;
-  if (p.stft_out) {
-    e = cudaFuncSetAttribute(k_stft400m<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    k_stft400m<true><<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(k_stft400m<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    k_stft400m<false><<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);
-  }
+  auto go = [&](auto kern) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) kern<<<(unsigned)grid, wl * 32, smem, (cudaStream_t)stream>>>(a);
+  };
+  if (t->full) go(k_stft400m<false, true>);
+  else if (p.stft_out) go(k_stft400m<true, false>);
+  else go(k_stft400m<false, false>);
+  if (e != cudaSuccess) return (int)e;
   count_launch();
-  note_kernel("k_stft400m");
+  note_kernel(t->full ? "k_stft400m<librosa>" : "k_stft400m");
   return (int)cudaGetLastError();
 }
 

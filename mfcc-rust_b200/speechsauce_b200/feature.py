@@ -53,9 +53,10 @@ def librosa_config(sr, n_fft=2048, hop_length=512, n_mels=128, fmin=0.0, fmax=No
     """A plan for `melspectrogram_librosa` (SS_FLAG_LIBROSA).  frame_length carries the hop: the library
     derives hop = trunc(frame_length * sample_rate) in f32 like config.rs:154, hence the half-sample margin."""
     from .config import SpeechConfig
+    flags = _lib.SS_FLAG_LIBROSA | kw.pop("flags", 0)
     return SpeechConfig(sample_rate=sr, fft_points=n_fft, frame_length=(hop_length + 0.5) / sr, frame_stride=hop_length / sr,
                         num_cepstral=min(13, n_mels), num_filters=n_mels, low_frequency=fmin, high_frequency=fmax,
-                        flags=_lib.SS_FLAG_LIBROSA, **kw)
+                        flags=flags, **kw)
 
 
 def melspectrogram_librosa(y, cfg, db=False):

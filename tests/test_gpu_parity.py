@@ -394,6 +394,32 @@ def test_librosa_mode_matches_oracle():
         sb.feature.melspectrogram_librosa(np.zeros(4000, np.float32), sb.SpeechConfig(**CONFIGS["c4"]))
 
 
+@pytest.mark.parametrize("hop,n_mels,fmin,fmax,n,rows", [(160, 80, 0.0, 8000.0, 480000, 2), (160, 128, 20.0, 7600.0, 16001, 3),
+                                                         (100, 40, 0.0, None, 2077, 4), (400, 80, 0.0, None, 201, 2),
+                                                         (57, 23, 300.0, 3400.0, 4000, 5)])
+def test_librosa_mode_n_fft_400_register_fft_kernel(hop, n_mels, fmin, fmax, n, rows):
+    """n_fft = 400 (Whisper's front end) runs on the register-FFT kernel with a full-spectrum |X|^2 tile: staged
+    interior rounds (hop 160), per-sample reflect edges, odd hops, the shortest legal row, 128 filters; against
+    the oracle and against the generic kernel (SS_FLAG_FORCE_GENERIC)."""
+    cfg = sb.feature.librosa_config(16000, 400, hop, n_mels, fmin, fmax)
+    y = o.synth_signal(rows, n, 0x5EED0400 + hop)
+    y[rows - 1, n // 3:] = 0.0
+    got = sb.feature.melspectrogram_librosa(y, cfg)
+    assert sb.lib.ss_last_kernel_name() == b"k_stft400m<librosa>"
+    want = o.librosa_melspectrogram(y, 16000, 400, hop, n_mels, fmin, fmax)
+    assert got.shape == want.shape == (rows, n_mels, 1 + n // hop)
+    assert_spec_close(got, want, what=f"librosa mel 400/{hop}/{n_mels}")
+    gdb = sb.feature.melspectrogram_librosa(y, cfg, db=True)
+    wdb = o.librosa_melspectrogram(y, 16000, 400, hop, n_mels, fmin, fmax, db=True)
+    loud = want > 1e-6 * want.max()
+    assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what="power_to_db")
+    assert (gdb >= -100.001).all()
+    gen = sb.feature.librosa_config(16000, 400, hop, n_mels, fmin, fmax, flags=_lib.SS_FLAG_FORCE_GENERIC)
+    ref = sb.feature.melspectrogram_librosa(y, gen)
+    assert sb.lib.ss_last_kernel_name() == b"k_frames_generic"
+    assert_spec_close(got, ref, what="register-FFT kernel vs generic kernel")
+
+
 def test_cmvn():
     rng = np.random.default_rng(3)
     v = rng.uniform(0, 1, (50, 100)).astype(np.float32)  # the reference's test (lib.rs:71-91)

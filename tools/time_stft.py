@@ -35,15 +35,17 @@ for shape, kw, n, ttd, T, F in (("c4", C4, 1024, 480000, 3000, 201), ("c3", C3, 
     gb = (x.numel() + out.numel()) * 4 / 1e9
     print(f"stft {shape}-shaped, {n} rows: {name:8s} {sb.lib.ss_last_kernel_name().decode():18s} {ms:8.3f} ms  {gb / ms * 1e3:7.1f} GB/s algorithmic")
 
-# librosa-compatible mel spectrogram (SS_FLAG_LIBROSA) on the same two shapes: any-length generic kernel
+# librosa-compatible mel spectrogram (SS_FLAG_LIBROSA) on the same two shapes: n_fft = 400 on the register-FFT
+# kernel (full-spectrum tile), everything else on the any-length generic kernel
 for shape, sr, n_fft, hop, n_mels, n, ttd in (("c4", 16000, 400, 160, 80, 1024, 480000), ("c3", 22050, 2048, 512, 128, 2048, 110250)):
-    x = torch.empty((n, ttd), dtype=torch.float32, device="cuda").normal_(0, 0.1)
-    cfg = sb.feature.librosa_config(sr, n_fft, hop, n_mels, devices=[0])
-    T = 1 + ttd // hop
-    out = torch.empty((n, n_mels, T), dtype=torch.float32, device="cuda")
+  x = torch.empty((n, ttd), dtype=torch.float32, device="cuda").normal_(0, 0.1)
+  T = 1 + ttd // hop
+  out = torch.empty((n, n_mels, T), dtype=torch.float32, device="cuda")
+  for name, flags in (("fast", 0), ("generic", _lib.SS_FLAG_FORCE_GENERIC)):
+    cfg = sb.feature.librosa_config(sr, n_fft, hop, n_mels, devices=[0], flags=flags)
 
     def step():
-        _lib.check(sb.lib.ss_librosa_melspectrogram_dev(cfg.plan, 0, sp, C.c_void_p(x.data_ptr()), n, ttd, ttd, C.c_void_p(out.data_ptr()), 0))
+        _lib.check(sb.lib.ss_librosa_melspectrogram_dev(cfg.plan, 0, sp, C.c_void_p(x.data_ptr()), n, ttd, ttd, C.c_void_p(out.data_ptr()), 1))
     for _ in range(3):
         step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,4 +55,4 @@ for shape, sr, n_fft, hop, n_mels, n, ttd in (("c4", 16000, 400, 160, 80, 1024, 
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"librosa mel {shape}-shaped, {n} rows: {sb.lib.ss_last_kernel_name().decode():18s} {ms:8.3f} ms  {n * ttd / sr / ms * 1e3:.3e} audio-s/s")
+    print(f"librosa log-mel {shape}-shaped, {n} rows: {name:8s} {sb.lib.ss_last_kernel_name().decode():20s} {ms:8.3f} ms  {n * ttd / sr / ms * 1e3:.3e} audio-s/s")
