@@ -60,9 +60,20 @@ struct Geo {
   static constexpr int kWarpFloats = kFpw * 202 * 2 + kTileFloats;
 };
 constexpr int kStage = kW + (kFpw - 1) * 160;    // samples of one round when hop = 160 (staging needs hop == 160)
+// The staged samples land with 20 floats of padding after every 160: frame fi then starts 180 fi floats in
+// (20 fi banks apart, like the transpose tile's frames) and the LDS.64 of the three frames do not collide.
+// Sample r = 2u + 20j (+1) of a frame sits at 180 fi + r + 20 (j / 8).
+constexpr int kStageSeg = 160, kStagePitch = 180;
+constexpr int kStageSegs = (kStage + kStageSeg - 1) / kStageSeg;  // 5 bulk copies: 4 x 640 B + 320 B
+static_assert(kStagePitch * (kStageSegs - 1) + kStage - kStageSeg * (kStageSegs - 1) <= kXchFloats, "staged round fits the transpose tile");
+// Physical row of logical row k1 in a frame's transpose tile.  Lane u reads rows u and 20 - u (10 for u = 0)
+// with LDS.128; this placement makes the first conflict-free across the three frames of a warp (4 wavefronts)
+// and leaves the second at 6 (natural order: 7 and 10).  Found by exhaustive search over 16-byte bank groups.
+__device__ constexpr int kRowOf[20] = {0, 5, 4, 3, 1, 6, 2, 7, 8, 11, 16, 18, 17, 15, 14, 13, 12, 10, 9, 19};
 static_assert(Geo<false>::kWarpFloats % 4 == 0 && Geo<true>::kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 static_assert(Geo<false>::kWarpFloats == kXchFloats + Geo<false>::kTileFloats, "transpose tile size");
 constexpr int kMtMax = 8;                // nf <= 128
+constexpr int kMbarFloats = 2 * 32;      // one 8-byte mbarrier per warp, after the tables
 constexpr int kTwRow = 44;               // floats per lane row of the W200 table (20 float2 + pad)
 // fixed table blob (floats)
 constexpr int kTabTw = 0;                         // [10][kTwRow]
@@ -134,22 +145,30 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
   constexpr int kPs = Geo<FULL>::kPs, kWarpFloats = Geo<FULL>::kWarpFloats;
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
-  float* warp_s = smem + a.tab_floats + (threadIdx.x >> 5) * kWarpFloats;
+  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem + a.tab_floats);  // one mbarrier per warp
+  float* warp_s = smem + a.tab_floats + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
   const FrameParams& p = a.p;
   const int nf = p.nf;
   for (int i = threadIdx.x; i < a.tab_floats / 4; i += blockDim.x)
     reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(a.tab) + i);
   // the pad bins of the ring rows are never written again and must be finite
   for (int i = (threadIdx.x & 31); i < kWarpFloats; i += 32) warp_s[i] = 0.0f;
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_all + (threadIdx.x >> 5));
+  if ((threadIdx.x & 31) == 0) {
+    asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;  // parity of the mbarrier phase the next staged round completes
   __syncthreads();  // the only block-wide barrier: from here on the warps are independent
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sl = lane < 30 ? lane : lane - 10;  // lanes 30, 31 shadow lanes 20, 21
+  const int sl = lane < 30 ? lane : lane - 2;   // lanes 30, 31 shadow lanes 28, 29 (same addresses: broadcasts)
   const int fi = sl / 10, u = sl - fi * 10;     // FFT stage: frame of the round, lane within the frame
   const int g = lane >> 2, t = lane & 3;        // MMA stage: fragment row group, thread in group
   const bool real_lane = lane < 30;
   const bool isz = (u == 0);
   const int k1B = isz ? 10 : 20 - u;
+  const int rowA = kRowOf[u], rowB = kRowOf[k1B];
   const int kb = isz ? -90 : u;  // k of slots 5..9 is kb + 20 e (u == 0: 10 + 20 (e - 5))
 
   const float4* twrow = reinterpret_cast<const float4*>(tab_s + kTabTw + u * kTwRow);
@@ -189,13 +208,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
       const int64_t o0 = (int64_t)f0 * p.S + c0;
       return a.stage && f0 + kFpw <= Tc && o0 >= 0 && o0 + kStage <= p.row_len;
     };
+    // TMA bulk copies (UBLKCP) issued by one lane: no LSU wavefronts, no per-lane address arithmetic.  The
+    // tile was last touched through the generic proxy (ordered before this point by __syncwarp), hence the
+    // proxy fence before the asynchronous proxy writes it.
     auto issue_stage = [&](int rd) {
-      const float* src = rowp + (int64_t)(fbeg + kFpw * rd) * p.S + c0;
-      for (int i = lane; i < kStage / 4; i += 32) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_s + 4 * i);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * i));
+      if (lane == 0) {
+        const float* src = rowp + (int64_t)(fbeg + kFpw * rd) * p.S + c0;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_s);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(kStage * 4) : "memory");
+#pragma unroll
+        for (int sg = 0; sg < kStageSegs; ++sg) {
+          const int n = (sg + 1 < kStageSegs ? kStageSeg : kStage - kStageSeg * (kStageSegs - 1)) * 4;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           dst + sg * kStagePitch * 4),
+                       "l"(src + sg * kStageSeg), "r"(n), "r"(mbar)
+                       : "memory");
+        }
       }
-      asm volatile("cp.async.commit_group;");
     };
     bool staged = n_rounds > 0 && stageable(0);
     if (staged) issue_stage(0);
@@ -213,12 +243,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
         // ---- framing + window: v[j] = (x w)[2m] + i (x w)[2m+1], m = u + 10 j
         float2 v[kR1];
         if (staged) {
-          asm volatile("cp.async.wait_group 0;");
-          __syncwarp();
-          const float* sx = stage_s + fi * 160 + 2 * u;
+          {
+            unsigned done;
+            do {
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t"
+                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                  "selp.b32 %0, 1, 0, p;\n\t}"
+                  : "=r"(done)
+                  : "r"(mbar), "r"(phase)
+                  : "memory");
+            } while (!done);
+            phase ^= 1u;
+          }
+          const float* sx = stage_s + fi * kStagePitch + 2 * u;
           sfor<0, kR1>([&](auto jj) {
             constexpr int j = decltype(jj)::value;
-            v[j] = __fmul2_rn(*reinterpret_cast<const float2*>(sx + 20 * j), win2[10 * j]);
+            v[j] = __fmul2_rn(*reinterpret_cast<const float2*>(sx + 20 * j + 20 * (j / 8)), win2[10 * j]);
           });
           __syncwarp();  // the buffer is the transpose tile again
         } else {
@@ -274,14 +315,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
           float2 y0 = v[k1], y1 = v[k1 + 1];
           if constexpr (k1 > 0) y0 = ssfft::cmulf(y0, make_float2(w.x, w.y));
           y1 = ssfft::cmulf(y1, make_float2(w.z, w.w));
-          xch[k1 * kT + u] = y0;
-          xch[(k1 + 1) * kT + u] = y1;
+          xch[kRowOf[k1] * kT + u] = y0;
+          xch[kRowOf[k1 + 1] * kT + u] = y1;
         });
         __syncwarp();
         float2 gA[kT], gB[kT];
         {
-          const float4* rA = reinterpret_cast<const float4*>(xch + u * kT);
-          const float4* rB = reinterpret_cast<const float4*>(xch + k1B * kT);
+          const float4* rA = reinterpret_cast<const float4*>(xch + rowA * kT);
+          const float4* rB = reinterpret_cast<const float4*>(xch + rowB * kT);
           sfor<0, kT / 2>([&](auto tt) {
             constexpr int i = decltype(tt)::value;
             const float4 xa = rA[i], xb = rB[i];
@@ -490,7 +531,7 @@ bool stft400m_supported(const Derived& d, const MelBank& mb) {
   if (d.W != kW || !d.stft_ok) return false;
   FragTables400 ft;
   if (!build_frags(d, mb, 1.0f, &ft)) return false;
-  const size_t fixed = (size_t)(kTabFixed + ft.mel.size()) * sizeof(float);
+  const size_t fixed = (size_t)(kTabFixed + ft.mel.size() + kMbarFloats) * sizeof(float);
   const size_t per_warp = (d.librosa ? Geo<true>::kWarpFloats : Geo<false>::kWarpFloats) * sizeof(float);
   return fixed + 4 * per_warp <= (size_t)kSmemBudget;
 }
@@ -544,7 +585,7 @@ int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count,
   a.tab_floats = t->tab_floats;
   a.n_mt = t->n_mt;
   for (int i = 0; i < kMtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
-  const size_t fixed = (size_t)t->tab_floats * sizeof(float);
+  const size_t fixed = (size_t)(t->tab_floats + kMbarFloats) * sizeof(float);
   const int n_warps = (int)std::min<size_t>(kMaxWarps, (kSmemBudget - fixed) / (kWarpFloats * sizeof(float)));
   if (n_warps < 4) return -1000;
   const int64_t warps_resident = (int64_t)sm_count * n_warps;
