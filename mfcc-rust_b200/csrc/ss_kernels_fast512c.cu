@@ -55,6 +55,7 @@ constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows;  // + 8 fr
 static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 constexpr int kTwRow = 36;                    // floats per lane row of the W256 table (16 float2 + pad)
 constexpr int kTabTw = 16 * kTwRow;           // CTA-shared twiddle table
+constexpr int kMbarFloats = 2 * 32;           // one 8-byte mbarrier per warp, after the tables
 constexpr int kNtMax = 8, kMtMax = 4, kNcMax = 16;  // nf <= 64, nc <= 16
 constexpr int kLgRow = 72;                    // log-mel tile row stride: >= 64 filters, 72 % 32 == 8 -> conflict-free LDS.64 B fragments
 
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
   extern __shared__ __align__(16) float smem[];
   float* tw_s = smem;
   float* tab_s = smem + kTabTw;
-  float* warp_s = tab_s + a.tab_floats + (threadIdx.x >> 5) * kWarpFloats;
+  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(tab_s + a.tab_floats);
+  float* warp_s = tab_s + a.tab_floats + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
   const FrameParams& p = a.p;
   constexpr int MT = (NT + 1) / 2;
   for (int i = threadIdx.x; i < kTabTw; i += blockDim.x) tw_s[i] = __ldg(a.tw + i);
@@ -121,6 +123,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
     reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(a.tab) + i);
   // the tile's pad columns (bins 132..135) are never written again and must be finite
   for (int i = (threadIdx.x & 31); i < kWarpFloats; i += 32) warp_s[i] = 0.0f;
+  // the staged samples of the next pair arrive by TMA bulk copy and complete on this warp's mbarrier
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_all + (threadIdx.x >> 5));
+  if ((threadIdx.x & 31) == 0) {
+    asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;  // parity of the mbarrier phase the next staged pair completes
   __syncthreads();  // the only block-wide barrier: from here on the warps are independent
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,12 +174,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
 
         // ---- framing: v[j] = x[2m] + i x[2m+1], m = u + 16 j; zero beyond L (processing.rs:147-156).
         // An out-of-range frame of the last pair re-reads frame T-1 (in bounds); it is never stored.
-        // A staged pair was fetched with cp.async into the upper half of the transpose tile while
+        // A staged pair was fetched by TMA bulk copy into the upper half of the transpose tile while
         // the previous pair was finishing (see below).
         float2 v[16];
         if (staged) {
-          asm volatile("cp.async.wait_group 0;");
-          __syncwarp();
+          {
+            unsigned done;
+            do {
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t"
+                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                  "selp.b32 %0, 1, 0, p;\n\t}"
+                  : "=r"(done)
+                  : "r"(mbar), "r"(phase)
+                  : "memory");
+            } while (!done);
+            phase ^= 1u;
+          }
           const float* sx = stage_s + fi * p.S + 2 * u;
           sfor<0, 16>([&](auto jj) {
             constexpr int j = decltype(jj)::value;
@@ -230,18 +250,21 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
         }
         __syncwarp();  // the transpose tile is free
         // ---- request the samples of the next pair (S + L contiguous floats) while this pair is
-        // finished: 16-byte cp.async into the upper half of the tile (the lower half holds the
+        // finished: one bulk copy into the upper half of the tile (the lower half holds the
         // log-mel tile during the epilogue).  Only whole, in-row pairs are staged.
         {
           const int nf0 = tile_f0 + 2 * pr + 2;  // first frame of the next pair
           staged = a.stage && nf0 + 1 < fend;
-          if (staged) {
+          if (staged && lane == 0) {
+            // one TMA bulk copy (UBLKCP) per pair: no LSU wavefronts, no per-lane address arithmetic.  The tile
+            // was last touched through the generic proxy (ordered by the __syncwarp above): proxy fence first.
             const float* src = rowp0 + (int64_t)nf0 * p.S;
-            for (int i = lane; i < a.stage; i += 32) {
-              const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_s + 4 * i);
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * i));
-            }
-            asm volatile("cp.async.commit_group;");
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_s);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(16 * a.stage) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src), "r"(16 * a.stage), "r"(mbar)
+                         : "memory");
           }
         }
         // ---- stage 2: 16-point FFT over the lane index.  gg[k2] = Z[u + 16 k2]
@@ -573,7 +596,7 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   a.dct_ofs = t->dct_ofs;
   for (int i = 0; i < kMtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
   // as many warps as the shared memory left by the tables allows (21 for the 40-filter bank)
-  const size_t fixed = (size_t)(kTabTw + t->tab_floats) * sizeof(float);
+  const size_t fixed = (size_t)(kTabTw + t->tab_floats + kMbarFloats) * sizeof(float);
   const int n_warps = (int)std::min<size_t>(kMaxWarps, (kSmemBudget - fixed) / (kWarpFloats * sizeof(float)));
   if (n_warps < 4) return -1000;
   const int64_t warps_resident = (int64_t)sm_count * n_warps;
@@ -593,7 +616,7 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   }
   a.n_items = p.n_rows * a.chunks_per_clip;
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
-  // cp.async staging of whole pairs: 16-byte aligned frame starts, the pair's S + L samples (rounded up to
+  // TMA bulk-copy staging of whole pairs: 16-byte aligned frame starts, the pair's S + L samples (rounded up to
   // 16 bytes) fit the upper half of the transpose tile and stay inside the row for every staged pair
   {
     const int chunks = (p.S + p.L + 3) / 4;
