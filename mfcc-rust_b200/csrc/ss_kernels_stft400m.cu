@@ -69,6 +69,7 @@ static_assert(kStagePitch * (kStageSegs - 1) + kStage - kStageSeg * (kStageSegs 
 // Physical row of logical row k1 in a frame's transpose tile.  Lane u reads rows u and 20 - u (10 for u = 0)
 // with LDS.128; this placement makes the first conflict-free across the three frames of a warp (4 wavefronts)
 // and leaves the second at 6 (natural order: 7 and 10).  Found by exhaustive search over 16-byte bank groups.
+__device__ constexpr int kTwSlot[10] = {0, 1, 4, 7, 3, 2, 6, 5, 8, 9};
 __device__ constexpr int kRowOf[20] = {0, 5, 4, 3, 1, 6, 2, 7, 8, 11, 16, 18, 17, 15, 14, 13, 12, 10, 9, 19};
 static_assert(Geo<false>::kWarpFloats % 4 == 0 && Geo<true>::kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 static_assert(Geo<false>::kWarpFloats == kXchFloats + Geo<false>::kTileFloats, "transpose tile size");
@@ -76,8 +77,12 @@ constexpr int kMtMax = 8;                // nf <= 128
 constexpr int kMbarFloats = 2 * 32;      // one 8-byte mbarrier per warp, after the tables
 constexpr int kTwRow = 44;               // floats per lane row of the W200 table (20 float2 + pad)
 // fixed table blob (floats)
-constexpr int kTabTw = 0;                         // [10][kTwRow]
-constexpr int kTabTw400 = kTabTw + kT * kTwRow;   // [200] float2 W400^k
+// W200 table: one copy per frame of the round, lane u's row in slot kTwSlot[u], the copies 452 floats apart:
+// the 30 lanes' LDS.128 then fall into distinct 16-byte bank groups in every quarter-warp (4 wavefronts per
+// load instead of 7 with a single row-ordered copy; exhaustive search like kRowOf)
+constexpr int kTwCopy = 452;
+constexpr int kTabTw = 0;                                          // [3][10 slots][kTwRow]
+constexpr int kTabTw400 = kTabTw + 2 * kTwCopy + kT * kTwRow;      // [200] float2 W400^k (entries 100 + 20 m: W400^(10 + 20 m))
 constexpr int kTabWin = kTabTw400 + 2 * kM;       // [200] float2 window pairs
 constexpr int kTabFixed = kTabWin + 2 * kM;       // then the mel A fragments [blocks][hi, lo][32] float4
 static_assert(kTabTw400 % 4 == 0 && kTabWin % 4 == 0 && kTabFixed % 4 == 0, "table alignment");
@@ -106,9 +111,8 @@ struct Stft400mArgs {
   FrameParams p;
   const float* tab;     // fixed tables + mel fragments, copied to shared memory once per CTA
   int tab_floats;
-  int64_t n_items;      // rows * chunks_per_row; one item per warp at a time
-  int chunks_per_row;
-  int fpi;              // frames per item (a multiple of kChunkAlign)
+  int64_t n_units;      // rows * units_per_row: the work is cut into units of kChunkAlign frames and every
+  int units_per_row;    // resident warp takes one contiguous, equally long run of units (static, balanced)
   int vec2;             // frames start 8-byte aligned
   int stage;            // hop == 160 and frames start 16-byte aligned: cp.async staging of whole rounds
   int pair_ok;          // T_out is even and the output is 8-byte aligned: float2 stores
@@ -171,15 +175,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
   const int rowA = kRowOf[u], rowB = kRowOf[k1B];
   const int kb = isz ? -90 : u;  // k of slots 5..9 is kb + 20 e (u == 0: 10 + 20 (e - 5))
 
-  const float4* twrow = reinterpret_cast<const float4*>(tab_s + kTabTw + u * kTwRow);
+  const float4* twrow = reinterpret_cast<const float4*>(tab_s + kTabTw + fi * kTwCopy + kTwSlot[u] * kTwRow);
   const float2* tw400 = reinterpret_cast<const float2*>(tab_s + kTabTw400);
   const float2* win2 = reinterpret_cast<const float2*>(tab_s + kTabWin) + u;
   const float4* frag_s = reinterpret_cast<const float4*>(tab_s + kTabFixed) + lane;
 
   float2* xch = reinterpret_cast<float2*>(warp_s) + fi * kXchFrame;
   float* Pt = warp_s + kXchFloats;  // [8][kPs]
+  // slot e of lane u pairs bins k = u + 20 e and 200 - k and needs W400^k; lane 0's slots 5..9 pair
+  // k = 10 + 20 (e - 5) instead, whose twiddles sit in the table's otherwise unused entries 20 e
   const float2* twA = tw400 + u;
-  const float2* twB = tw400 + kb;
   int plo[5];  // column of the low bin of slots 5..9
 #pragma unroll
   for (int i = 0; i < 5; ++i) plo[i] = isz ? 10 + 20 * i : 200 - u - 20 * (i + 5);
@@ -192,10 +197,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
   const int T_out = (int)p.T_out, Tc = (int)p.T;
   const int n_warps = blockDim.x >> 5;
 
-  for (int64_t item = (int64_t)blockIdx.x * n_warps + warp; item < a.n_items; item += (int64_t)gridDim.x * n_warps) {
-    const int64_t row = item / a.chunks_per_row;
-    const int fbeg = (int)(item - row * a.chunks_per_row) * a.fpi;
-    const int fend = min(T_out, fbeg + a.fpi);
+  // this warp's run of units; a run that crosses row boundaries is processed one row segment (item) at a time
+  const int64_t gw = (int64_t)blockIdx.x * n_warps + warp, n_gw = (int64_t)gridDim.x * n_warps;
+  const int64_t uend = (gw + 1) * a.n_units / n_gw;
+  for (int64_t ubeg = gw * a.n_units / n_gw; ubeg < uend;) {
+    const int64_t row = ubeg / a.units_per_row;
+    const int u0 = (int)(ubeg - row * a.units_per_row);
+    const int u1 = (int)min((int64_t)a.units_per_row, u0 + (uend - ubeg));
+    ubeg += u1 - u0;
+    const int fbeg = u0 * kChunkAlign;
+    const int fend = min(T_out, u1 * kChunkAlign);
     const float* rowp = p.pcm + row * p.row_stride;
     float* outp = p.mel_out ? p.mel_out + row * nf * (int64_t)T_out : nullptr;
 
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
               zb = isz ? gB[14 - e] : gB[9 - e];
             }
             float2 xa, xb;
-            pair_split(za, zb, (e < 5 ? twA : twB)[20 * e], xa, xb);
+            pair_split(za, zb, twA[20 * e], xa, xb);
             const float2 m = make_float2(fmaf(xa.x, xa.x, xa.y * xa.y), fmaf(xb.x, xb.x, xb.y * xb.y));
             if constexpr (FULL) {  // both bins of the pair: k and 200 - k
               const int k = (e < 5 ? u : kb) + 20 * e;
@@ -542,14 +553,18 @@ int stft400m_build_tables(const Derived& d, const MelBank& mb, const std::vector
   if (!build_frags(d, mb, pscale, &ft)) return (int)cudaErrorInvalidValue;
   std::vector<float> h(kTabFixed, 0.f);
   const double pi = 3.14159265358979323846264338327950288;
-  for (int u = 0; u < kT; ++u)
-    for (int k1 = 0; k1 < kR1; ++k1) {
-      const double ang = -2.0 * pi * (double)(u * k1) / (double)kM;
-      h[kTabTw + u * kTwRow + 2 * k1] = (float)std::cos(ang);
-      h[kTabTw + u * kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
-    }
+  static const int tw_slot[10] = {0, 1, 4, 7, 3, 2, 6, 5, 8, 9};  // = kTwSlot
+  for (int c = 0; c < kFpw; ++c)
+    for (int u = 0; u < kT; ++u)
+      for (int k1 = 0; k1 < kR1; ++k1) {
+        const double ang = -2.0 * pi * (double)(u * k1) / (double)kM;
+        h[kTabTw + c * kTwCopy + tw_slot[u] * kTwRow + 2 * k1] = (float)std::cos(ang);
+        h[kTabTw + c * kTwCopy + tw_slot[u] * kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
+      }
   for (int k = 0; k < kM; ++k) {
-    const double ang = -2.0 * pi * (double)k / (double)kW;
+    // entries 100, 120, .., 180 are read by lane 0 only, for the pairs (10 + 20 m, 190 - 20 m)
+    const int kk = (k >= 100 && k % 20 == 0) ? 10 + (k - 100) : k;
+    const double ang = -2.0 * pi * (double)kk / (double)kW;
     h[kTabTw400 + 2 * k] = (float)std::cos(ang);
     h[kTabTw400 + 2 * k + 1] = (float)std::sin(ang);
   }
@@ -588,24 +603,18 @@ int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count,
   const size_t fixed = (size_t)(t->tab_floats + kMbarFloats) * sizeof(float);
   const int n_warps = (int)std::min<size_t>(kMaxWarps, (kSmemBudget - fixed) / (kWarpFloats * sizeof(float)));
   if (n_warps < 4) return -1000;
-  const int64_t warps_resident = (int64_t)sm_count * n_warps;
-  // items: runs of whole tiles, 24-frame aligned, small enough that every resident warp gets a few
-  int64_t fpi = 20 * kChunkAlign;
-  auto items = [&](int64_t f) { return p.n_rows * ((p.T_out + f - 1) / f); };
-  while (fpi > kChunkAlign && items(fpi) < 4 * warps_resident) fpi /= 2;
-  fpi = (fpi + kChunkAlign - 1) / kChunkAlign * kChunkAlign;
-  a.fpi = (int)fpi;
-  a.chunks_per_row = (int)((p.T_out + fpi - 1) / fpi);
-  a.n_items = p.n_rows * (int64_t)a.chunks_per_row;
+  // units of 24 frames (whole tiles, 96-byte aligned output runs), dealt out in equal contiguous runs
+  a.units_per_row = (int)((p.T_out + kChunkAlign - 1) / kChunkAlign);
+  a.n_units = p.n_rows * (int64_t)a.units_per_row;
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
   // whole rounds can be staged with 16-byte cp.async when every round starts 16-byte aligned
   const int64_t c0 = t->full ? -kW / 2 : (int64_t)(p.n_pad + 1) * p.S - p.N;
   a.stage = p.S == 160 && (p.row_stride % 4 == 0) && (((c0 % 4) + 4) % 4 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
   a.pair_ok = (p.T_out % 2 == 0) && (reinterpret_cast<uintptr_t>(p.mel_out) % 8 == 0);
   // small jobs: fewer warps per CTA so that the items spread over the SMs instead of queueing on a few
-  const int wl = (int)std::min<int64_t>(n_warps, std::max<int64_t>(1, (a.n_items + sm_count - 1) / sm_count));
+  const int wl = (int)std::min<int64_t>(n_warps, std::max<int64_t>(1, (a.n_units + sm_count - 1) / sm_count));
   const size_t smem = fixed + (size_t)wl * kWarpFloats * sizeof(float);
-  const int64_t grid = std::min<int64_t>((a.n_items + wl - 1) / wl, (int64_t)sm_count);
+  const int64_t grid = std::min<int64_t>((a.n_units + wl - 1) / wl, (int64_t)sm_count);
   if (grid <= 0) return 0;
   cudaError_t e;
   auto go = [&](auto kern) {
