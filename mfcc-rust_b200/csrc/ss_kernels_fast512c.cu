@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -55,7 +56,7 @@ constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows;  // + 8 fr
 static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 constexpr int kTwRow = 36;                    // floats per lane row of the W256 table (16 float2 + pad)
 constexpr int kTabTw = 16 * kTwRow;           // CTA-shared twiddle table
-constexpr int kMbarFloats = 2 * 32;           // one 8-byte mbarrier per warp, after the tables
+constexpr int kMbarFloats = 2 * 34;           // one 8-byte mbarrier per warp + one for the table copy, after the tables
 constexpr int kNtMax = 8, kMtMax = 4, kNcMax = 16;  // nf <= 64, nc <= 16
 constexpr int kLgRow = 72;                    // log-mel tile row stride: >= 64 filters, 72 % 32 == 8 -> conflict-free LDS.64 B fragments
 
@@ -97,9 +98,9 @@ struct FastArgsC {
   int tab_floats;          // size of the two tables
   int dct_ofs;             // float offset of the dct table inside tab
   int mel_base[kMtMax];    // first block of m-tile mt inside the mel table
-  int64_t n_items;         // clips * chunks_per_clip; one item per warp at a time
-  int chunks_per_clip;
-  int fpi;                 // frames per item (a multiple of the tile height, or >= T)
+  int64_t n_units;         // clips * units_per_clip: the work is cut into units (one 8-frame tile, or the whole clip
+  int units_per_clip;      // when the CMVN is fused) and every resident warp takes one contiguous, equally long
+  int unit_frames;         // run of them (static and balanced per SM); a run is processed one clip segment at a time
   int fuse_cmvn;           // 0 none, 1 mean, 2 mean+var: one warp takes the whole clip and normalises it in place
   int vec2;                // every frame start is 8-byte aligned
   int stage;               // > 0: 16-byte chunks per staged pair (frame starts 16-byte aligned, S + L fits the buffer)
@@ -118,9 +119,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
   float* warp_s = tab_s + a.tab_floats + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
   const FrameParams& p = a.p;
   constexpr int MT = (NT + 1) / 2;
-  for (int i = threadIdx.x; i < kTabTw; i += blockDim.x) tw_s[i] = __ldg(a.tw + i);
-  for (int i = threadIdx.x; i < a.tab_floats / 4; i += blockDim.x)
-    reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(a.tab) + i);
+  // the tables (twiddles + fragments, contiguous in global and in shared memory) arrive by one TMA bulk copy
+  const unsigned mbar_tab = (unsigned)__cvta_generic_to_shared(mbar_all + 32);
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)(kTabTw + a.tab_floats) * 4u;
+    asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar_tab) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_tab), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(tw_s)),
+                 "l"(a.tw), "r"(bytes), "r"(mbar_tab)
+                 : "memory");
+  }
   // the tile's pad columns (bins 132..135) are never written again and must be finite
   for (int i = (threadIdx.x & 31); i < kWarpFloats; i += 32) warp_s[i] = 0.0f;
   // the staged samples of the next pair arrive by TMA bulk copy and complete on this warp's mbarrier
@@ -131,6 +141,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
   }
   unsigned phase = 0;  // parity of the mbarrier phase the next staged pair completes
   __syncthreads();  // the only block-wide barrier: from here on the warps are independent
+  {
+    unsigned done;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(mbar_tab)
+          : "memory");
+    } while (!done);
+  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fi = lane >> 4, u = lane & 15;   // FFT stage: frame of the pair, lane within the frame
@@ -153,15 +175,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
   // does this lane's last column group (j = JMAX - 1) lie inside the frame?
   const bool last0 = 2 * u + 32 * (JMAX - 1) < L, last1 = 2 * u + 32 * (JMAX - 1) + 1 < L;
   const int n_warps = blockDim.x >> 5;
-  for (int64_t item = (int64_t)blockIdx.x * n_warps + warp; item < a.n_items; item += (int64_t)gridDim.x * n_warps) {
-    const int64_t clip = item / a.chunks_per_clip;
-    const int chunk = (int)(item - clip * a.chunks_per_clip);
+  const int64_t gw = (int64_t)blockIdx.x * n_warps + warp, n_gw = (int64_t)gridDim.x * n_warps;
+  const int64_t uend = (gw + 1) * a.n_units / n_gw;
+  for (int64_t ubeg = gw * a.n_units / n_gw; ubeg < uend;) {
+    const int64_t clip = ubeg / a.units_per_clip;
+    const int u0 = (int)(ubeg - clip * a.units_per_clip);
+    const int u1 = (int)min((int64_t)a.units_per_clip, u0 + (uend - ubeg));
+    ubeg += u1 - u0;
     const float* rowp0 = p.pcm + clip * p.row_stride;
     const float* rowp = rowp0 + 2 * u;
     bool staged = false;  // the first pair of an item is loaded directly
     const int64_t obase = clip * T;  // first output row of the clip
-    const int fbeg = chunk * a.fpi;
-    const int fend = min(T, fbeg + a.fpi);
+    const int fbeg = u0 * a.unit_frames;
+    const int fend = (int)min((int64_t)T, (int64_t)u1 * a.unit_frames);
 
 #pragma unroll 1
     for (int tile_f0 = fbeg; tile_f0 < fend; tile_f0 += kTileRows) {
@@ -603,18 +629,11 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   // a fused CMVN needs the whole clip in one warp; worth it while there are enough clips to fill the GPU
   const bool fuse = p.mfcc && p.cmvn_mode && p.T <= 4096 && p.n_rows >= warps_resident;
   a.fuse_cmvn = fuse ? p.cmvn_mode : 0;
-  if (fuse) {
-    a.fpi = (int)p.T;
-    a.chunks_per_clip = 1;
-  } else {
-    // chunks of whole tiles, small enough that every resident warp gets a few items
-    int64_t fpi = 32 * kTileRows;
-    auto items = [&](int64_t f) { return p.n_rows * ((p.T + f - 1) / f); };
-    while (fpi > kTileRows && items(fpi) < 4 * warps_resident) fpi /= 2;
-    a.fpi = (int)fpi;
-    a.chunks_per_clip = (int)((p.T + fpi - 1) / fpi);
-  }
-  a.n_items = p.n_rows * a.chunks_per_clip;
+  // latency case: fewer tiles than SMs -> single pairs as units, so that more SMs share the few frames
+  const int uf = p.n_rows * ((p.T + kTileRows - 1) / kTileRows) < sm_count ? 2 : kTileRows;
+  a.unit_frames = fuse ? (int)p.T : uf;
+  a.units_per_clip = fuse ? 1 : (int)((p.T + uf - 1) / uf);
+  a.n_units = p.n_rows * a.units_per_clip;
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
   // TMA bulk-copy staging of whole pairs: 16-byte aligned frame starts, the pair's S + L samples (rounded up to
   // 16 bytes) fit the upper half of the transpose tile and stay inside the row for every staged pair
@@ -622,15 +641,16 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
     const int chunks = (p.S + p.L + 3) / 4;
     const bool fits = 4 * chunks <= kXchFloats / 2 && (p.T - 2) * (int64_t)p.S + 4 * chunks <= p.row_len;
     const bool aligned = (p.S % 4 == 0) && (p.row_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
-    a.stage = (fits && aligned && p.T >= 2) ? chunks : 0;
+    static const bool no_stage = getenv("SS_F512C_STAGE") && atoi(getenv("SS_F512C_STAGE")) == 0;  // A/B switch
+    a.stage = (fits && aligned && p.T >= 2 && !no_stage) ? chunks : 0;
   }
   auto al8 = [](const float* q) { return reinterpret_cast<uintptr_t>(q) % 8 == 0; };
   a.nf_even = (p.nf % 2 == 0) && al8(p.mfe) && al8(p.lmfe) && al8(p.ssc);
   const bool ssc = p.ssc != nullptr;
   // small jobs: fewer warps per CTA so that the items spread over the SMs instead of queueing on a few
-  const int wl = (int)std::min<int64_t>(n_warps, std::max<int64_t>(1, (a.n_items + sm_count - 1) / sm_count));
+  const int wl = (int)std::min<int64_t>(n_warps, std::max<int64_t>(1, (a.n_units + sm_count - 1) / sm_count));
   const size_t smem = fixed + (size_t)wl * kWarpFloats * sizeof(float);
-  const int64_t grid = std::min<int64_t>((a.n_items + wl - 1) / wl, (int64_t)sm_count);
+  const int64_t grid = std::min<int64_t>((a.n_units + wl - 1) / wl, (int64_t)sm_count);
   if (grid <= 0) return 0;
   const int jn = (p.L + 31) / 32;
   cudaError_t e;

@@ -74,7 +74,7 @@ __device__ constexpr int kRowOf[20] = {0, 5, 4, 3, 1, 6, 2, 7, 8, 11, 16, 18, 17
 static_assert(Geo<false>::kWarpFloats % 4 == 0 && Geo<true>::kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 static_assert(Geo<false>::kWarpFloats == kXchFloats + Geo<false>::kTileFloats, "transpose tile size");
 constexpr int kMtMax = 8;                // nf <= 128
-constexpr int kMbarFloats = 2 * 32;      // one 8-byte mbarrier per warp, after the tables
+constexpr int kMbarFloats = 2 * 34;      // one 8-byte mbarrier per warp + one for the table copy, after the tables
 constexpr int kTwRow = 44;               // floats per lane row of the W200 table (20 float2 + pad)
 // fixed table blob (floats)
 // W200 table: one copy per frame of the round, lane u's row in slot kTwSlot[u], the copies 452 floats apart:
@@ -153,8 +153,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
   float* warp_s = smem + a.tab_floats + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
   const FrameParams& p = a.p;
   const int nf = p.nf;
-  for (int i = threadIdx.x; i < a.tab_floats / 4; i += blockDim.x)
-    reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(a.tab) + i);
+  // the tables arrive by one TMA bulk copy
+  const unsigned mbar_tab = (unsigned)__cvta_generic_to_shared(mbar_all + 32);
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)a.tab_floats * 4u;
+    asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar_tab) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_tab), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(tab_s)),
+                 "l"(a.tab), "r"(bytes), "r"(mbar_tab)
+                 : "memory");
+  }
   // the pad bins of the ring rows are never written again and must be finite
   for (int i = (threadIdx.x & 31); i < kWarpFloats; i += 32) warp_s[i] = 0.0f;
   const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_all + (threadIdx.x >> 5));
@@ -164,6 +174,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
   }
   unsigned phase = 0;  // parity of the mbarrier phase the next staged round completes
   __syncthreads();  // the only block-wide barrier: from here on the warps are independent
+  {
+    unsigned done;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(mbar_tab)
+          : "memory");
+    } while (!done);
+  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sl = lane < 30 ? lane : lane - 2;   // lanes 30, 31 shadow lanes 28, 29 (same addresses: broadcasts)
