@@ -56,7 +56,7 @@ tr = {}
 for rep, kn, name, cfg, clips, phases in [
         ("prof_fast512c_r1", "k_fast512cILi13ELb1ELb0ELi5", "ncu_fast512c_r1", "c2", 65536, True),
         ("prof_fast512c_c5_r1", "k_fast512cILi13ELb1ELb1ELi5", "ncu_fast512c_c5_r1", "c5", 128, True),
-        ("prof_stft400m_r1", "k_stft400mILb0", "ncu_stft400m_r1", None, None, False),
+        ("prof_stft400m_r1", "k_stft400mILb0ELb0", "ncu_stft400m_r1", None, None, False),
         ("prof_stft2048m_r1", "k_stft2048m", "ncu_stft2048m_r1", "c3", 4096, False)]:
     rp = str(g / f"{rep}.ncu-rep")
     txt = run("ncu_summary.py", rp) + "\n" + (run("ncu_phases.py", rp, kn) + "\n" if phases else "") + run("ncu_lines.py", rp, kn, "30")
