@@ -6,7 +6,7 @@ import pytest
 
 import speechsauce_b200 as sb
 import speechsauce_oracle as o
-from conftest import assert_log_close, assert_spec_close
+from conftest import RTOL_SPEC, assert_log_close, assert_spec_close
 from speechsauce_b200 import _lib
 from test_host_abi import CONFIGS
 
@@ -252,6 +252,46 @@ def test_fast512_long_stream_chunks():
     f, e = o.mfe(x[1], oc)
     assert_spec_close(r["mfe"][1], f, what="long stream mfe vs oracle")
     assert_log_close(r["mfcc"][1], o.mfcc(x[1], oc), what="long stream mfcc vs oracle")
+
+
+@pytest.mark.parametrize("n,length", [(6000, 400 + 160 * 3 + 5), (4097, 400 + 160 * 11), (700, 400 + 160 * 29 + 150)])
+def test_unit_runs_across_many_short_rows(n, length):
+    """Every resident warp takes one contiguous run of units; with thousands of rows of a few frames each a run
+    crosses many row boundaries (and, with fewer units than warps, some runs are empty).  k_fast512c (tiles
+    of 8 frames, no fused CMVN) and k_stft400m (24-frame units, 1..2 per row) against the generic kernel,
+    bit-for-bit against the same rows computed alone, and the oracle on sampled rows."""
+    x = o.synth_signal(n, length, 0x5EED0500 + n)
+    cfg, gen, oc = sb.SpeechConfig(**CONFIGS["c1"]), sb.SpeechConfig(**CONFIGS["c1"], flags=GENERIC), o.SpeechConfig(**CONFIGS["c1"])
+    r = sb.feature.features(x, cfg, mfe=True, energy=True, mfcc=True)
+    assert sb.lib.ss_last_kernel_name() == b"k_fast512c"
+    g = sb.feature.features(x, gen, mfe=True, energy=True, mfcc=True)
+    assert_spec_close(r["mfe"], g["mfe"], what="short rows mfe vs generic")
+    assert_spec_close(r["energy"], g["energy"], what="short rows energy vs generic")
+    assert_log_close(r["mfcc"], g["mfcc"], what="short rows mfcc vs generic")
+    pick = [0, 1, n // 3, n - 2, n - 1]
+    alone = sb.feature.features(x[pick], cfg, mfe=True, energy=True, mfcc=True)
+    for k in ("mfe", "energy", "mfcc"):
+        assert np.array_equal(alone[k], r[k][pick]), k
+    for i in pick[:3]:
+        assert_spec_close(r["mfe"][i], o.mfe(x[i], oc)[0], what=f"short row {i} mfe vs oracle")
+        assert_log_close(r["mfcc"][i], o.mfcc(x[i], oc), what=f"short row {i} mfcc vs oracle")
+    c4, g4, o4 = sb.SpeechConfig(**CONFIGS["c4"]), sb.SpeechConfig(**CONFIGS["c4"], flags=GENERIC), o.SpeechConfig(**CONFIGS["c4"])
+    a = sb.feature.mel_spectrogram2(x, c4, log=False)
+    assert sb.lib.ss_last_kernel_name() == b"k_stft400m"
+    b = sb.feature.mel_spectrogram2(x, g4, log=False)
+    # per-row tolerance floor: a band that is empty but for the f32 FFT's own rounding (1e-10 of the row's
+    # peak in a handful of entries here) carries different noise in the two kernels and in the oracle
+    peak = b.max(axis=(1, 2), keepdims=True).astype(np.float64)
+    err = np.abs(a.astype(np.float64) - b)
+    assert (err <= RTOL_SPEC * np.abs(b) + 2e-6 * peak).all(), f"short rows mel vs generic: worst {(err / peak).max():.3e} of the row peak"
+    al = sb.feature.mel_spectrogram2(x, c4, log=True)
+    bl = sb.feature.mel_spectrogram2(x, g4, log=True)
+    loud = b > 1e-6 * peak
+    assert loud.mean() > 0.6           # 18 of the 80 filters are empty and the last frame of a row is the zero tail
+    assert_log_close(al[loud], bl[loud], what="short rows log-mel vs generic")
+    want = o.mel_spectrogram2(x[:3], o4)          # rows 0..2 of a fresh plan: the overlap memory starts at zero
+    assert_spec_close(a[:3], want, what="short rows mel vs oracle")
+    assert_log_close(al[:3][loud[:3]], np.log(want.astype(np.float64)[loud[:3]]), what="short rows log-mel vs oracle")
 
 
 def test_cuda_path_matches_the_committed_golden_fixtures():
