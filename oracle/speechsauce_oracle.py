@@ -105,16 +105,53 @@ class SpeechConfig:
 # ------------------------------------------------------------------ functions.rs helpers
 
 
+def _libm_f32(name):
+    """logf / expf of the platform libm through ctypes (None if there is no loadable libm)."""
+    import ctypes
+    import ctypes.util
+    try:
+        fn = getattr(ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6"), name)
+    except (OSError, AttributeError):
+        return None
+    fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+    return fn
+
+
+_LOGF, _EXPF = _libm_f32("logf"), _libm_f32("expf")
+
+
+def _f32_fn(x, libm_fn, np_fn):
+    x = np.asarray(x)
+    if x.dtype != F32:
+        return np_fn(x)
+    if libm_fn is None:  # correctly rounded: equal to glibc's on all but ~0.1 % of the arguments
+        return np_fn(x.astype(np.float64)).astype(F32)
+    return np.array([libm_fn(float(v)) for v in x.ravel()], F32).reshape(x.shape)
+
+
+def _ln(x):
+    """f32::ln as the reference sees it: Rust lowers f32::ln / f32::exp to the platform libm's logf / expf, so
+    the oracle calls those (the band-edge arrays are tiny).  numpy's SIMD float32 loops are 1 ulp off on a few
+    percent of the arguments, and that matters: high_freq = sr / 2 puts (F + 1) * hz / sr of the last band
+    edge exactly on an integer, where the truncation at feature.rs:70 turns one ulp into a different FFT bin
+    (3.7 % of random parameter sets; tests/test_host_abi.py sweeps it)."""
+    return _f32_fn(x, _LOGF, np.log)
+
+
+def _exp(x):
+    return _f32_fn(x, _EXPF, np.exp)
+
+
 def frequency_to_mel(f, dtype=F32):
     """functions.rs:19-21: 1127 * ln(1 + f/700)."""
     f = dtype(f)
-    return dtype(1127.0) * np.log(dtype(1.0) + f / dtype(700.0))
+    return dtype(1127.0) * _ln(dtype(1.0) + f / dtype(700.0))[()]
 
 
 def mel_to_frequency(m):
     """functions.rs:36-41: 700 * (exp(m/1127) - 1), elementwise, dtype of m."""
     t = m.dtype.type
-    return t(700.0) * (np.exp(m / t(1127.0)) - t(1.0))
+    return t(700.0) * (_exp(m / t(1127.0)) - t(1.0))
 
 
 def triangle(arr, left, middle, right):

@@ -634,3 +634,116 @@ def test_cmvnw_matches_oracle():
                 np.testing.assert_allclose(got, o.cmvnw_direct(x, win, vn), atol=5e-5, rtol=5e-5)
     with pytest.raises(sb.SpeechsauceError, match="odd"):
         sb.processing.cmvnw(np.zeros((10, 3), np.float32), 300, False)   # processing.rs:327
+
+
+# ---------------------------------------------------------------- randomised configuration sweep
+# SS_SWEEP_BLOCKS=n widens both sweeps to n blocks of 12 parameter sets (default 4 / 3; 100 / 100 = 2,400 parameter sets ran clean on a B200)
+import os
+
+_SWEEP = int(os.environ.get("SS_SWEEP_BLOCKS", "0"))
+
+
+def _random_speechpy_config(rng):
+    sr = int(rng.choice([8000, 11025, 16000, 22050, 44100, 48000]))
+    n_fft = int(rng.choice([64, 128, 200, 256, 384, 400, 480, 512, 512, 512, 512, 640, 1000, 1024, 1536, 2048, 4096]))
+    L = int(rng.integers(max(8, n_fft // 4), n_fft + 1))
+    S = int(rng.integers(max(1, L // 5), L + 1))
+    nf = int(rng.integers(4, 81))
+    nc = int(rng.integers(1, min(nf, 24) + 1))
+    lo = float(rng.choice([0.0, 0.0, 64.0, 133.33]))
+    hi = float(rng.choice([sr / 2, sr / 2, 0.9 * sr / 2, sr / 3]))
+    # + 0.25 keeps round(frame_length * sr) (processing.rs:77-78) away from the .5 ties
+    return dict(sample_rate=sr, fft_points=n_fft, frame_length=(L + 0.25) / sr, frame_stride=(S + 0.25) / sr, num_cepstral=nc,
+                num_filters=nf, low_frequency=lo, high_frequency=hi, dc_elimination=bool(rng.integers(0, 2)))
+
+
+@pytest.mark.parametrize("block", range(_SWEEP or 4))
+def test_random_speechpy_configs_match_oracle(block):
+    """48 seeded random parameter sets (sample rate, FFT length incl. mixed-radix ones, frame length / stride,
+    filter and cepstrum counts, band edges, dc_elimination) x ragged clip lengths: whatever kernel the plan picks
+    (k_fast512c inside its limits, the generic kernel otherwise) against the oracle, every output of the fused
+    call, with and without the fused CMVN."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0600 + block))
+    picked = set()
+    for i in range(12):
+        kw = _random_speechpy_config(rng)
+        cfg, oc = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+        L, S = oc.frame_sample_length, oc.frame_step
+        assert (cfg.frame_sample_length, cfg.frame_step) == (L, S)
+        n = L + S * int(rng.integers(1, 40)) + int(rng.integers(0, S))
+        n_clips = int(rng.integers(1, 6))
+        x = o.synth_signal(n_clips, n, 0x5EED0700 + 97 * block + i)
+        mode = int(rng.integers(0, 3))
+        r = sb.feature.features(x, cfg, mfe=True, energy=True, lmfe=True, ssc=True, mfcc=True, cmvn_mode=mode)
+        picked.add(sb.lib.ss_last_kernel_name())
+        what = f"block {block} config {i} {kw} n={n}"
+        for c in range(n_clips):
+            f, e = o.mfe(x[c], oc)
+            assert r["mfe"][c].shape == f.shape, what
+            assert_spec_close(r["mfe"][c], f, what=what + " mfe")
+            assert_spec_close(r["energy"][c], e, what=what + " energy")
+            # a one-bin filter on a bin where |X| happens to be 1e-4 of its usual size holds the f32 FFT's own
+            # rounding (about 1 in 10^6 entries on this noise): those entries are checked in the linear domain
+            loud = f > 1e-3 * f.max()
+            assert_log_close(r["lmfe"][c][loud], np.log(f[loud]), what=what + " lmfe")
+            assert_spec_close(np.exp(r["lmfe"][c].astype(np.float64)), f, rtol=2e-4, what=what + " exp(lmfe)")
+            raw = o.mfcc(x[c], oc)
+            m = o.cmvn(raw, mode == 2) if mode else raw
+            # variance normalisation divides by std + 2^-30: a column that is (nearly) constant over a short clip
+            # turns the f32 rounding of the cepstra into O(1) differences on both sides
+            ok = raw.std(axis=0) > 0.05 if mode == 2 else np.ones(m.shape[1], bool)
+            rows = loud.all(axis=1)       # frames without such an entry
+            got = r["mfcc"][c][rows]
+            if not kw["dc_elimination"] and mode != 2:
+                # c0 = 2 sum_f ln(mel_f) is unscaled except for element [0,0] (Q9) and reaches 1e3..2e3: its f32
+                # rounding alone is 1e-4 per term, so the abs 1e-3 bound is applied to columns 1.. only
+                assert_log_close(got[:, 0], m[rows, 0], atol=4e-3, what=what + f" mfcc c0 cmvn={mode}")
+                ok[0] = False
+            assert_log_close(got[:, ok], m[rows][:, ok], what=what + f" mfcc cmvn={mode}")
+            assert_spec_close(r["ssc"][c], o.ssc(x[c], oc), rtol=2e-4, what=what + " ssc")
+    assert len(picked) >= 1
+
+
+def _random_stft_config(rng):
+    sr = int(rng.choice([8000, 16000, 22050, 44100]))
+    W = int(rng.choice([64, 128, 200, 256, 400, 400, 480, 512, 1000, 1024, 2048, 2048]))
+    H = int(rng.integers(max(1, W // 16), W // 2 + 1))          # 0 < H <= W / 2 (functions.rs:96)
+    nf = int(rng.integers(4, 129))
+    lo = float(rng.choice([0.0, 0.0, 50.0]))
+    hi = float(rng.choice([sr / 2, sr / 2, 0.8 * sr / 2]))
+    return dict(sample_rate=sr, fft_points=W, frame_length=(H + 0.5) / sr, frame_stride=0.01, num_cepstral=min(13, nf),
+                num_filters=nf, low_frequency=lo, high_frequency=hi)
+
+
+@pytest.mark.parametrize("block", range(_SWEEP or 3))
+def test_random_stft_configs_match_oracle(block):
+    """36 seeded random STFT parameter sets (window 64..2048 incl. mixed-radix, hop anywhere in (0, W/2] so that
+    H does not divide W in most of them, 4..128 filters) x ragged row lengths: complex STFT, mel spectrogram and
+    its log against the oracle, including the row-to-row and call-to-call overlap memory (Q13)."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0800 + block))
+    for i in range(12):
+        kw = _random_stft_config(rng)
+        oc = o.SpeechConfig(**kw)
+        W, H = oc.window_size, oc.frame_size
+        ttd = int(rng.integers(1, 30)) * H + int(rng.integers(0, H)) + (W if rng.integers(0, 2) else 0)
+        rows = int(rng.integers(1, 5))
+        x = o.synth_signal(rows, ttd, 0x5EED0900 + 97 * block + i)
+        what = f"block {block} config {i} {kw} rows={rows} ttd={ttd}"
+        cfg = sb.SpeechConfig(**kw)
+        assert cfg.frame_size == H, what
+        for call in range(2):                                  # the second call starts from the carried memory
+            X, Xo = sb.functions.stft2(x, cfg), o.stft2(x, oc)
+            assert X.shape == Xo.shape, what
+            assert_spec_close(X.real, Xo.real, what=what + f" stft re call {call}")
+            assert_spec_close(X.imag, Xo.imag, what=what + f" stft im call {call}")
+            np.testing.assert_array_equal(cfg.analysis_mem, oc.analysis_mem)
+        cfg2, oc2 = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+        M, Mo = sb.feature.mel_spectrogram2(x, cfg2), o.mel_spectrogram2(x, oc2)
+        assert M.shape == Mo.shape, what
+        assert_spec_close(M, Mo, what=what + " mel")
+        cfg3, oc3 = sb.SpeechConfig(**kw), o.SpeechConfig(**kw)
+        Ml = sb.feature.mel_spectrogram2(x, cfg3, log=True)
+        Mo3 = o.mel_spectrogram2(x, oc3)
+        loud = Mo3 > 1e-6 * Mo3.max()
+        assert_log_close(Ml[Mo3 == 0], np.full((Mo3 == 0).sum(), np.log(o.EPS)), atol=1e-5, what=what + " ln(zero_handling(0))")
+        assert_log_close(Ml[loud], np.log(Mo3[loud].astype(np.float64)), what=what + " log-mel")

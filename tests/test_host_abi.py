@@ -54,6 +54,25 @@ def test_derived_sizes_and_tables_match_oracle(name):
     assert cfg.n_pad == (oc.window_size // oc.frame_size - 1 if stft_ok else -1)
 
 
+def test_filterbank_matches_oracle_on_random_parameter_sets():
+    """600 seeded random (sample rate, FFT length, filter count, band edges): the library's host-built bank is
+    identical to the oracle's, bin for bin.  high_freq = sr / 2 (and other round ratios) puts the last band edge
+    exactly on an integer before the truncation at feature.rs:70, so this also pins the last-ulp behaviour of
+    ln / exp on both sides (see speechsauce_oracle._ln)."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0A00))
+    for _ in range(600):
+        sr = int(rng.choice([8000, 11025, 16000, 22050, 32000, 44100, 48000]))
+        W = int(rng.choice([64, 128, 200, 256, 400, 480, 512, 1000, 1024, 2048, 4096]))
+        nf = int(rng.integers(1, 129))
+        lo = float(rng.choice([0.0, 20.0, 64.0, 133.33, 300.0]))
+        hi = float(rng.choice([sr / 2, sr / 2, 0.9 * sr / 2, 0.8 * sr / 2, sr / 3, sr / 4]))
+        kw = dict(sample_rate=sr, fft_points=W, frame_length=0.4 * W / sr, frame_stride=0.2 * W / sr,
+                  num_cepstral=min(13, nf), num_filters=nf, low_frequency=lo, high_frequency=hi)
+        cfg = sb.SpeechConfig(**kw, devices=[])
+        fb = o.filterbanks(nf, W // 2 + 1, sr, lo, hi)
+        np.testing.assert_array_equal(cfg.filterbank(), fb, err_msg=str(kw))
+
+
 def test_frame_counts_follow_reference_f32_arithmetic():
     for n, L, S in [(16000, 400, 160), (16000, 320, 160), (10**6, 320, 160), (57_600_000, 400, 160), (401, 400, 160),
                     (123457, 400, 160), (2**24 + 3, 400, 160)]:

@@ -140,6 +140,28 @@ def test_filterbank_indices_and_peaks():
         o.filterbanks(40, 257, 16000, 0.0, 9000.0)  # feature.rs:47-50
 
 
+def test_f32_ln_exp_are_the_platform_libm_ones():
+    """The reference's f32::ln / f32::exp are the platform libm's logf / expf, and so are the oracle's (numpy's
+    float32 loops are 1 ulp off on a few percent of the inputs, which moves a band edge by one FFT bin when
+    (F + 1) * hz / sr sits on an integer).  glibc's are within 1 ulp of the correctly rounded value."""
+    if o._LOGF is None:
+        pytest.skip("no libm to compare with")
+    rng = np.random.Generator(np.random.Philox(0x5EED0A01))
+    hz = np.concatenate([rng.uniform(0.0, 24000.0, 5000), [0.0, 4000.0, 8000.0, 11025.0, 22050.0, 24000.0]]).astype(np.float32)
+    arg = np.float32(1.0) + hz / np.float32(700.0)
+    ln = o._ln(arg)
+    assert ln.dtype == np.float32 and ln.shape == arg.shape
+    exact = np.log(arg.astype(np.float64))
+    assert (np.abs(ln - exact) <= np.spacing(np.abs(exact).astype(np.float32))).all()
+    q = np.float32(1127.0) * ln / np.float32(1127.0)
+    ex = o._exp(q)
+    exact = np.exp(q.astype(np.float64))
+    assert (np.abs(ex - exact) <= np.spacing(exact.astype(np.float32))).all()
+    assert o._ln(np.float64(2.0)).dtype == np.float64          # the f64 oracle keeps numpy's f64 functions
+    # the case that exposed it: 44.1 kHz, n_fft 1024, 58 filters up to sr / 2 -> the last edge is bin 257, not 256
+    assert o.filterbank_indices(58, 513, 44100, 64.0, 22050.0)[-1] == 257
+
+
 def test_zero_clip_and_literal_framing():
     cfg = o.SpeechConfig(16000, 512, 0.025, 0.01)
     f, e = o.mfe(np.zeros(16000, np.float32), cfg)
