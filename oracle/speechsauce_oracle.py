@@ -24,7 +24,9 @@ Every function cites the reference file:line (relative to /root/reference/) it f
 `dtype=np.float32` mirrors the reference's arithmetic ("hardcoded to use f32",
 README.md:17); `dtype=np.float64` is the same algorithm in double precision and is used
 only to bound rounding error.  Index computations (frame counts, filterbank bin edges)
-are always done in f32, exactly as the reference does, in both modes.
+are always done in f32, exactly as the reference does, in both modes; the f32 ln / exp
+inside them are the platform libm's logf / expf (what Rust's f32::ln / f32::exp call),
+reached through ctypes -- see `_ln`.
 
 Semantics policy: literal everywhere, except where
 the literal code is degenerate: `stack_frames` gathers frames[i, j] = x[i*S + j]
