@@ -637,7 +637,8 @@ def test_cmvnw_matches_oracle():
 
 
 # ---------------------------------------------------------------- randomised configuration sweep
-# SS_SWEEP_BLOCKS=n widens both sweeps to n blocks of 12 parameter sets (default 4 / 3; 100 / 100 = 2,400 parameter sets ran clean on a B200)
+# SS_SWEEP_BLOCKS=n widens every sweep to n blocks of 10-12 parameter sets (defaults 4 / 3 / 2 / 2; 100 / 100 / 20 / 20 =
+# 2,800 parameter sets ran clean on a B200)
 import os
 
 _SWEEP = int(os.environ.get("SS_SWEEP_BLOCKS", "0"))
@@ -747,3 +748,97 @@ def test_random_stft_configs_match_oracle(block):
         loud = Mo3 > 1e-6 * Mo3.max()
         assert_log_close(Ml[Mo3 == 0], np.full((Mo3 == 0).sum(), np.log(o.EPS)), atol=1e-5, what=what + " ln(zero_handling(0))")
         assert_log_close(Ml[loud], np.log(Mo3[loud].astype(np.float64)), what=what + " log-mel")
+
+
+@pytest.mark.parametrize("block", range(_SWEEP or 2))
+def test_random_librosa_configs_match_oracle(block):
+    """seeded random librosa-mode parameter sets (n_fft incl. 400 / 2048 and mixed-radix ones, any hop <= n_fft,
+    Slaney banks of 8..128 filters with random band edges) x ragged lengths down to the shortest the reflect
+    padding allows: mel power spectrogram and power_to_db against the oracle (pinned to torchaudio)."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0B00 + block))
+    for i in range(10):
+        sr = int(rng.choice([8000, 16000, 22050, 44100]))
+        n_fft = int(rng.choice([128, 256, 400, 400, 480, 512, 1000, 1024, 2048]))
+        hop = int(rng.integers(max(1, n_fft // 16), n_fft + 1))
+        n_mels = int(rng.integers(8, 129))
+        fmin = float(rng.choice([0.0, 0.0, 30.0, 125.5]))
+        fmax = [None, 0.45 * sr, 0.3 * sr][int(rng.integers(0, 3))]
+        n = n_fft // 2 + 1 + int(rng.integers(0, 40)) * hop + int(rng.integers(0, hop))
+        rows = int(rng.integers(1, 5))
+        what = f"block {block} config {i} sr={sr} n_fft={n_fft} hop={hop} n_mels={n_mels} fmin={fmin} fmax={fmax} n={n} rows={rows}"
+        cfg = sb.feature.librosa_config(sr, n_fft, hop, n_mels, fmin, fmax)
+        y = o.synth_signal(rows, n, 0x5EED0C00 + 97 * block + i)
+        got = sb.feature.melspectrogram_librosa(y, cfg)
+        want = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, fmin, fmax)
+        assert got.shape == want.shape == (rows, n_mels, 1 + n // hop), what
+        assert_spec_close(got, want, what=what + " mel")
+        gdb = sb.feature.melspectrogram_librosa(y, cfg, db=True)
+        wdb = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, fmin, fmax, db=True)
+        loud = want > 1e-6 * want.max()
+        assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what=what + " power_to_db")   # 1e-4 relative = 4.3e-4 dB
+        assert (gdb >= -100.001).all(), what
+
+
+@pytest.mark.parametrize("block", range(_SWEEP or 2))
+def test_random_processing_primitives_match_oracle(block):
+    """processing::{preemphasis, stack_frames, power_spectrum, log_power_spectrum, cmvn, cmvnw,
+    derivative_extraction} on seeded random shapes and parameters: bit-exact where the work is indexing or a
+    single rounding (preemphasis, stack_frames, derivatives), within the spectrum / log tolerances otherwise."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0D00 + block))
+    for i in range(10):
+        n = int(rng.integers(2, 200_000))
+        x = o.synth_signal(1, n, 0x5EED0E00 + 97 * block + i)[0]
+        shift = int(rng.choice([1, 1, 2, -1, -7, n, -(n - 1), int(rng.integers(1, n))]))
+        cof = float(rng.choice([0.98, 0.97, 0.5, 1.0]))
+        what = f"block {block} case {i} n={n}"
+        np.testing.assert_array_equal(sb.preemphasis(x, shift, cof), o.preemphasis(x, shift, cof), err_msg=what + f" preemphasis shift={shift}")
+        # stack_frames: L, S by round(sr * length) (processing.rs:77-78), floor / ceil frame counts in f32
+        sr = int(rng.choice([8000, 16000, 22050, 44100]))
+        L = int(rng.integers(2, min(n, 3000) + 1))
+        S = int(rng.integers(1, 2 * L))
+        zp = bool(rng.integers(0, 2))
+        fl, fs = (L + 0.25) / sr, (S + 0.25) / sr
+        try:
+            want = o.stack_frames(x, sr, fl, fs, zp)
+        except ValueError:
+            with pytest.raises(sb.SpeechsauceError):
+                sb.processing.stack_frames(x, sr, fl, fs, None, zp)
+            want = None
+        if want is not None:
+            got = sb.processing.stack_frames(x, sr, fl, fs, None, zp)
+            np.testing.assert_array_equal(got, want, err_msg=what + f" stack_frames L={L} S={S} zp={zp}")
+        # power_spectrum / log_power_spectrum on random frame matrices (frame length <= n_fft)
+        nfft = int(rng.choice([64, 200, 256, 400, 512, 1000, 1024, 2048]))
+        Lf = int(rng.integers(1, nfft + 1))
+        rows = int(rng.integers(1, 300))
+        fr = o.synth_signal(rows, Lf, 0x5EED0F00 + 97 * block + i)
+        ps, po = sb.processing.power_spectrum(fr, nfft), o.power_spectrum(fr, nfft)
+        assert_spec_close(ps, po, what=what + f" power_spectrum rows={rows} L={Lf} n_fft={nfft}")
+        for norm in (False, True):
+            lg, lo_ = sb.processing.log_power_spectrum(fr, nfft, norm), o.log_power_spectrum(fr, nfft, norm)
+            loud = po > 1e-5
+            if norm and not loud.reshape(-1)[-1]:
+                continue           # the normaliser is the last value of the matrix (Q7): noise in, noise everywhere
+            assert_log_close(lg[loud], lo_[loud], what=what + f" log_power_spectrum n_fft={nfft} normalize={norm}")
+        # cmvn / cmvnw / derivatives on a random feature matrix
+        T, C = int(rng.integers(1, 3000)), int(rng.integers(1, 65))
+        scale = float(rng.uniform(0.1, 10.0))
+        v = (rng.standard_normal((T, C)) * scale + rng.uniform(-20.0, 20.0)).astype(np.float32)
+        # the f32 column mean carries ~1e-6 of the largest magnitude whatever the summation order is; variance
+        # normalisation divides that by the (local) standard deviation
+        tol = 2e-5 * float(np.abs(v).max()) + 2e-5
+        for vn in (False, True):
+            if vn and T < 30:
+                continue           # std of a few rows: 1 / (std + 2^-30) amplifies the last ulp of the mean
+            np.testing.assert_allclose(sb.cmvn(v, vn), o.cmvn(v, vn), atol=tol / (0.5 * scale) if vn else tol, rtol=0,
+                                       err_msg=what + f" cmvn {T}x{C} vn={vn}")
+        win = 2 * int(rng.integers(0, 200)) + 1
+        for vn in (False, True):
+            if vn and win < 31:
+                continue
+            np.testing.assert_allclose(sb.processing.cmvnw(v, win, vn), o.cmvnw(v, win, vn), atol=tol / (0.3 * scale) if vn else tol,
+                                       rtol=0, err_msg=what + f" cmvnw {T}x{C} win={win} vn={vn}")
+        dw = int(rng.integers(1, 5))
+        np.testing.assert_array_equal(sb.processing.derivative_extraction(v, dw), o.derivative_extraction(v, dw),
+                                      err_msg=what + f" derivative_extraction {T}x{C} dw={dw}")
+        np.testing.assert_array_equal(sb.feature.extract_derivative_feature(v), o.extract_derivative_feature(v))
