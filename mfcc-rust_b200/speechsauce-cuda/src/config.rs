@@ -138,7 +138,7 @@ impl SpeechConfig {
             low_frequency: fmin,
             high_frequency: fmax,
             dc_elimination: 1,
-            flags: 0x4,
+            flags: ffi::SS_FLAG_LIBROSA,
             dct2_scale: 0.0,
         })
     }

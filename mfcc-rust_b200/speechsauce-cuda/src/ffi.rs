@@ -53,6 +53,7 @@ pub struct ss_plan {
 
 pub const SS_FLAG_FRAMING_LITERAL: u32 = 0x1;
 pub const SS_FLAG_FORCE_GENERIC: u32 = 0x2;
+pub const SS_FLAG_LIBROSA: u32 = 0x4;
 pub const SS_CMVN_NONE: c_int = 0;
 pub const SS_CMVN_MEAN: c_int = 1;
 pub const SS_CMVN_MEAN_VAR: c_int = 2;
