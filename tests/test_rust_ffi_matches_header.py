@@ -111,3 +111,66 @@ def test_build_rs_compiles_every_cuda_source_for_sm_100a():
     assert "sm_100a" in build_rs
     for src in sorted((ROOT / "mfcc-rust_b200" / "csrc").glob("*.cu")) + sorted((ROOT / "mfcc-rust_b200" / "csrc").glob("*.cpp")):
         assert src.name in build_rs, f"{src.name} is missing from build.rs"
+
+
+# The reference's public signatures for the hot path (parameter names dropped), keyed by
+# module::function -> (parameter types, return type).  `lmfe` / `extract_derivative_feature` /
+# `log_power_spectrum` are private in the reference and public here (D3); `ssc` is new (D4).
+REFERENCE_SIGNATURES = {
+    "feature::mfcc": (["ArrayView1<f32>", "&SpeechConfig"], "Array2<f32>"),                                  # feature.rs:99
+    "feature::mfe": (["ArrayView1<f32>", "&SpeechConfig"], "(Array2<f32>, Array1<f32>)"),                    # feature.rs:200
+    "feature::lmfe": (["ArrayView1<f32>", "&SpeechConfig"], "Array2<f32>"),                                  # feature.rs:242
+    "feature::ssc": (["ArrayView1<f32>", "&SpeechConfig"], "Array2<f32>"),                                   # README.md:15
+    "feature::mel_spectrogram1": (["ArrayView1<f32>", "&SpeechConfig"], "Array2<f32>"),                      # feature.rs:151
+    "feature::mel_spectrogram2": (["ArrayView2<f32>", "&SpeechConfig"], "Array3<f32>"),                      # feature.rs:163
+    "feature::extract_derivative_feature": (["Array2<f32>"], "Array3<f32>"),                                 # feature.rs:253
+    "processing::preemphasis": (["Array1<f32>", "isize", "f32"], "Array1<f32>"),                             # processing.rs:31
+    "processing::stack_frames": (["ArrayView1<f32>", "usize", "f32", "f32", "Option<fn(usize) -> Array2<f32>>", "bool"],
+                                 "Array2<f32>"),                                                             # processing.rs:65
+    "processing::power_spectrum": (["Array2<f32>", "usize"], "Array2<f32>"),                                 # processing.rs:179
+    "processing::log_power_spectrum": (["Array2<f32>", "usize", "bool"], "Array2<f32>"),                     # processing.rs:194
+    "processing::derivative_extraction": (["&Array2<f32>", "usize"], "Array2<f32>"),                         # processing.rs:222
+    "processing::cmvn": (["ArrayView2<f32>", "bool"], "Array2<f32>"),                                        # processing.rs:265
+    "processing::cmvnw": (["Array2<f32>", "usize", "bool"], "Array2<f32>"),                                  # processing.rs:315
+    "functions::stft2": (["ArrayView2<f32>", "&SpeechConfig"], "Array3<Complex32>"),                         # functions.rs:86
+    "functions::stft1": (["ArrayView1<f32>", "&SpeechConfig"], "Array2<Complex32>"),                         # functions.rs:199
+}
+
+
+def _split_params(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "<(":
+            depth += 1
+        elif ch in ">)" and not cur.endswith("-"):     # "->" is not a closing bracket
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return out
+
+
+def test_crate_keeps_the_reference_public_signatures():
+    src_dir = ROOT / "mfcc-rust_b200" / "speechsauce-cuda" / "src"
+    norm = lambda t: re.sub(r"\s+", " ", t.strip())
+    for key, (params, ret) in REFERENCE_SIGNATURES.items():
+        module, fn = key.split("::")
+        text = (src_dir / f"{module}.rs").read_text()
+        m = re.search(rf"pub fn {fn}\s*\(([^{{]*)\{{", text)
+        assert m, f"{key} is missing from the crate"
+        head, _, got_ret = m.group(1).rpartition(") ->")           # the last ") ->" closes the parameter list
+        got = [norm(p.split(":", 1)[1]) for p in _split_params(head)]
+        assert got == params, f"{key}: parameters {got} != {params}"
+        assert norm(got_ret) == ret, f"{key}: returns {norm(got_ret)} != {ret}"
+    cfg = (src_dir / "config.rs").read_text()
+    # SpeechConfig::new's nine positional arguments (config.rs:140-150) and the builder's setters (config.rs:35-96)
+    m = re.search(r"impl SpeechConfig \{.*?pub fn new\((.*?)\)\s*->\s*Self", cfg, flags=re.S)
+    names = [p.split(":")[0].strip() for p in _split_params(m.group(1))]
+    assert names == ["sample_rate", "fft_points", "frame_length", "frame_stride", "num_cepstral", "num_filters",
+                     "low_frequency", "high_frequency", "dc_elimination"]
+    for setter in ("high_freq", "low_freq", "dc_elimination", "num_cepstral", "frame_stride", "frame_length", "fft_points", "build"):
+        assert re.search(rf"pub fn {setter}\(", cfg), f"SpeechConfigBuilder::{setter} is missing"
