@@ -57,8 +57,7 @@ static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned"
 constexpr int kTwRow = 36;                    // floats per lane row of the W256 table (16 float2 + pad)
 constexpr int kTabTw = 16 * kTwRow;           // CTA-shared twiddle table
 constexpr int kMbarFloats = 2 * 34;           // one 8-byte mbarrier per warp + one for the table copy, after the tables
-constexpr int kNtMax = 8, kMtMax = 4, kNcMax = 16;  // nf <= 64, nc <= 16
-constexpr int kLgRow = 72;                    // log-mel tile row stride: >= 64 filters, 72 % 32 == 8 -> conflict-free LDS.64 B fragments
+constexpr int kNtMax = 8, kNcMax = 16;        // nf <= 64, nc <= 16
 
 __device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
 __device__ __forceinline__ float fast_sqrt(float x) {
@@ -92,12 +91,12 @@ struct FastArgsC {
   FrameParams p;
   const float* tw;         // [16][kTwRow] W256^{u k1}
   const float* tab;        // fragment tables, copied to shared memory once per CTA:
-                           //   mel [blocks][hi, lo][32] float4: A fragments of the filterbank (16 filters x 8 bins),
-                           //   only the k-steps inside each 16-filter group's band, then
+                           //   mel [blocks][32] float4 {hi b0, hi b1, lo b0, lo b1}: B fragments of the filterbank
+                           //   (8 bins x 8 filters), only the k-steps inside each 8-filter group's band, then
                            //   dct [NT][hi, lo][32] float4: A fragments of the DCT matrix (16 cepstra x 8 filters)
   int tab_floats;          // size of the two tables
   int dct_ofs;             // float offset of the dct table inside tab
-  int mel_base[kMtMax];    // first block of m-tile mt inside the mel table
+  int mel_base[kNtMax];    // first block of n-tile nt inside the mel table
   int64_t n_units;         // clips * units_per_clip: the work is cut into units (one 8-frame tile, or the whole clip
   int units_per_clip;      // when the CMVN is fused) and every resident warp takes one contiguous, equally long
   int unit_frames;         // run of them (static and balanced per SM); a run is processed one clip segment at a time
@@ -105,12 +104,12 @@ struct FastArgsC {
   int vec2;                // every frame start is 8-byte aligned
   int stage;               // > 0: 16-byte chunks per staged pair (frame starts 16-byte aligned, S + L fits the buffer)
   int nf_even;             // nf is even: float2 stores of the mel rows
-  int ks_lo[kMtMax], ks_n2[kMtMax];  // first k-step (8 bins each) and number of k-step pairs of the band, per m-tile of 16 filters
+  int ks_lo[kNtMax], ks_n2[kNtMax];  // first k-step (8 bins each) and number of k-step pairs of the band, per n-tile of 8 filters
 };
 
 // JMAX: column groups (32 samples each) that can be non-zero; EXACT: JMAX == ceil(L / 32), so only
 // the last group needs a bounds check; SSC: also the centroid numerator; NT: n-tiles of 8 filters
-template <int JMAX, bool EXACT, bool SSC, int NT>  // MT = (NT + 1) / 2 m-tiles of 16 filters
+template <int JMAX, bool EXACT, bool SSC, int NT>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) {
   extern __shared__ __align__(16) float smem[];
   float* tw_s = smem;
@@ -118,7 +117,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
   uint64_t* mbar_all = reinterpret_cast<uint64_t*>(tab_s + a.tab_floats);
   float* warp_s = tab_s + a.tab_floats + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
   const FrameParams& p = a.p;
-  constexpr int MT = (NT + 1) / 2;
   // the tables (twiddles + fragments, contiguous in global and in shared memory) arrive by one TMA bulk copy
   const unsigned mbar_tab = (unsigned)__cvta_generic_to_shared(mbar_all + 32);
   if (threadIdx.x == 0) {
@@ -196,7 +194,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
       for (int pr = 0; pr < npairs; ++pr) {
         const int fr = tile_f0 + 2 * pr + fi;
         const bool valid = fr < fend;
-        const int row = 4 * (pr >> 1) + (pr & 1) + 2 * fi;
+        const int row = 2 * pr + fi;  // tile rows in frame order
 
         // ---- framing: v[j] = x[2m] + i x[2m+1], m = u + 16 j; zero beyond L (processing.rs:147-156).
         // An out-of-range frame of the last pair re-reads frame T-1 (in bounds); it is never stored.
@@ -333,93 +331,97 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
       }
       __syncwarp();
 
-      // ---- mel filterbank on the tensor cores (feature.rs:229-230), transposed:
-      //   mel^T [16 MT filters][8 frames] = W [16 MT][136 bins] (banded, pre-split on the host) x P^T.
-      // M = 16 filters, N = the 8 frames of the tile, K = 8 bins per MMA, so every row of the MMA is
-      // used; only the k-steps a 16-filter group's band touches are visited (22 of 54 blocks for the
-      // 40-filter bank).  Contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1, so a
-      // lane's two P values are one 8-byte load.  The accumulator fragment holds
-      // (filter 16 mt + g [+ 8], tile row 2t [+ 1]); zero_handling -> stores -> ln follow
-      // (feature.rs:216-230, 242-245) and the log-mel values go to a [frame][filter] tile for the DCT.
-      float* lgT = warp_s;  // overlays the transpose tile, dead until the next pair
-      const int j0 = (t & 1) + 4 * (t >> 1);  // frame (within the tile) of tile row 2t; row 2t + 1 is frame j0 + 2
+      // ---- mel filterbank on the tensor cores (feature.rs:229-230):
+      //   mel [8 frames][8 filters of n-tile nt] = P [8][136 bins] x W^T (banded, pre-split on the host).
+      // The M rows of the MMA are the tile's 8 frames split in place: rows 0..7 their TF32 high parts, rows
+      // 8..15 the remainders, so A = [P_hi; P_lo] against W_hi yields hi x hi and lo x hi at once and a second
+      // MMA against W_lo adds hi x lo: two MMAs per k-step (8 bins x 8 filters), one 16-byte load of weights.
+      // Only the k-steps an 8-filter group's band touches are visited (22 of 85 for the 40-filter bank).
+      // Contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1, so a lane's two P values are
+      // one 8-byte load.  The accumulator rows g / g + 8 hold (frame g, filters 8 nt + 2t [+ 1]):
+      // zero_handling -> stores -> ln follow on the fragment (feature.rs:216-230, 242-245), and the two
+      // log-mel values are exactly this lane's B fragment of the DCT product below (contraction slot t <->
+      // filter 8 nt + 2t, slot t + 4 <-> filter 8 nt + 2t + 1; the DCT matrix fragments are permuted on the
+      // host), so ln -> DCT needs no data movement.
+      // ---- DCT-II on the tensor cores (feature.rs:120-123), transposed:
+      //   ceps^T [16][8 frames] = D [16][8 NT filters] (pre-split on the host) x logmel^T.
+      // One m-tile covers all (<= 16) cepstra; the accumulator holds (cepstrum g [+ 8], frame 2t [+ 1]).
+      float dB[4] = {0.f, 0.f, 0.f, 0.f}, dS[4] = {0.f, 0.f, 0.f, 0.f}, dT[4] = {0.f, 0.f, 0.f, 0.f};
       {
-        const int fr_a = tile_f0 + j0, fr_b = fr_a + 2;
-        const bool va = fr_a < fend, vb = fr_b < fend;
-        const int64_t oa = (obase + fr_a) * nf, ob = oa + 2 * nf;
+        const int fr_g = tile_f0 + g;
+        const bool vg = fr_g < fend;
+        const int64_t og = (obase + fr_g) * nf;
         const float* prow = Pt + g * kPs + 2 * t;
+        const float4* dp = reinterpret_cast<const float4*>(tab_s + a.dct_ofs) + lane;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          float accB[4] = {0.f, 0.f, 0.f, 0.f}, accS[4] = {0.f, 0.f, 0.f, 0.f}, accT[4] = {0.f, 0.f, 0.f, 0.f};
-          float numB[4] = {0.f, 0.f, 0.f, 0.f}, numS[4] = {0.f, 0.f, 0.f, 0.f}, numT[4] = {0.f, 0.f, 0.f, 0.f};
-          const int k0 = a.ks_lo[mt];
+        for (int nt = 0; nt < NT; ++nt) {
+          float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
+          float numH[4] = {0.f, 0.f, 0.f, 0.f}, numL[4] = {0.f, 0.f, 0.f, 0.f};
+          const int k0 = a.ks_lo[nt];
           const float* pp = prow + 8 * k0;
-          const float4* ap = reinterpret_cast<const float4*>(tab_s) + a.mel_base[mt] * 64 + lane;
+          const float4* bp = reinterpret_cast<const float4*>(tab_s) + a.mel_base[nt] * 32 + lane;
           float rb = SSC ? fmaf(p.ssc_step, (float)(8 * k0 + 2 * t), p.ssc_r0) : 0.f;  // R[k] of this lane's first bin
           // two k-steps per iteration (the band is padded to an even count with zero-weight blocks;
-          // the tile columns those read are other rows' finite values)
+          // the tile columns those read are finite)
 #pragma unroll 1
-          for (int n2 = a.ks_n2[mt]; n2 > 0; --n2) {
+          for (int n2 = a.ks_n2[nt]; n2 > 0; --n2) {
             const float2 pv0 = *reinterpret_cast<const float2*>(pp);
             const float2 pv1 = *reinterpret_cast<const float2*>(pp + 8);
-            const float4 h0 = ap[0], l0 = ap[32], h1 = ap[64], l1 = ap[96];
+            const float4 w0 = bp[0], w1 = bp[32];
             pp += 16;
-            ap += 128;
+            bp += 64;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float2 pv = h ? pv1 : pv0;
-              const float4 wh = h ? h1 : h0, wl = h ? l1 : l0;
-              uint32_t bh0, bl0, bh1, bl1;
-              split_tf32(pv.x, bh0, bl0);
-              split_tf32(pv.y, bh1, bl1);
-              mma_tf32(accB, wh, bh0, bh1);  // hi x hi
-              mma_tf32(accS, wl, bh0, bh1);  // lo x hi
-              mma_tf32(accT, wh, bl0, bl1);  // hi x lo
+              const float4 w = h ? w1 : w0;
+              uint32_t h0, l0, h2, l2;
+              split_tf32(pv.x, h0, l0);
+              split_tf32(pv.y, h2, l2);
+              const float4 av = make_float4(__uint_as_float(h0), __uint_as_float(l0), __uint_as_float(h2), __uint_as_float(l2));
+              mma_tf32(accH, av, __float_as_uint(w.x), __float_as_uint(w.y));  // [hi; lo] x hi
+              mma_tf32(accL, av, __float_as_uint(w.z), __float_as_uint(w.w));  // [hi; lo] x lo
               if (SSC) {  // numerator: the same weights against P[k] R[k]
-                split_tf32(pv.x * rb, bh0, bl0);
-                split_tf32(pv.y * (rb + p.ssc_step), bh1, bl1);
+                split_tf32(pv.x * rb, h0, l0);
+                split_tf32(pv.y * (rb + p.ssc_step), h2, l2);
                 rb = fmaf(8.0f, p.ssc_step, rb);
-                mma_tf32(numB, wh, bh0, bh1);
-                mma_tf32(numS, wl, bh0, bh1);
-                mma_tf32(numT, wh, bl0, bl1);
+                const float4 nv = make_float4(__uint_as_float(h0), __uint_as_float(l0), __uint_as_float(h2), __uint_as_float(l2));
+                mma_tf32(numH, nv, __float_as_uint(w.x), __float_as_uint(w.y));
+                mma_tf32(numL, nv, __float_as_uint(w.z), __float_as_uint(w.w));
               }
             }
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int f = 16 * mt + g + 8 * (i >> 1);  // filter; i & 1: tile row 2t / 2t + 1 = frame j0 / j0 + 2
-            const float m = zero_handling(accB[i] + (accS[i] + accT[i]));
-            const float lgv = fast_ln(m);
-            if (f < kLgRow) lgT[(j0 + 2 * (i & 1)) * kLgRow + f] = lgv;
-            if (((i & 1) ? vb : va) && f < nf) {
-              const int64_t o = ((i & 1) ? ob : oa) + f;
-              if (p.mfe) p.mfe[o] = m;
-              if (p.lmfe) p.lmfe[o] = lgv;
-              if (SSC && p.ssc) p.ssc[o] = __fdividef(numB[i] + (numS[i] + numT[i]), m);
+          const int f0 = 8 * nt + 2 * t;
+          const float m0 = zero_handling(accH[0] + (accH[2] + (accL[0] + accL[2])));
+          const float m1 = zero_handling(accH[1] + (accH[3] + (accL[1] + accL[3])));
+          const float lg0 = fast_ln(m0), lg1 = fast_ln(m1);
+          if (vg && f0 < nf) {
+            const int64_t o = og + f0;
+            const float s0 = SSC ? __fdividef(numH[0] + (numH[2] + (numL[0] + numL[2])), m0) : 0.f;
+            const float s1 = SSC ? __fdividef(numH[1] + (numH[3] + (numL[1] + numL[3])), m1) : 0.f;
+            if (a.nf_even) {  // f0 is even: 8-byte aligned pairs
+              if (p.mfe) *reinterpret_cast<float2*>(p.mfe + o) = make_float2(m0, m1);
+              if (p.lmfe) *reinterpret_cast<float2*>(p.lmfe + o) = make_float2(lg0, lg1);
+              if (SSC && p.ssc) *reinterpret_cast<float2*>(p.ssc + o) = make_float2(s0, s1);
+            } else {
+              const bool v1 = f0 + 1 < nf;
+              if (p.mfe) { p.mfe[o] = m0; if (v1) p.mfe[o + 1] = m1; }
+              if (p.lmfe) { p.lmfe[o] = lg0; if (v1) p.lmfe[o + 1] = lg1; }
+              if (SSC && p.ssc) { p.ssc[o] = s0; if (v1) p.ssc[o + 1] = s1; }
             }
+          }
+          if (p.mfcc) {
+            const float4 wh = dp[(2 * nt) * 32], wl = dp[(2 * nt + 1) * 32];
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(lg0, bh0, bl0);
+            split_tf32(lg1, bh1, bl1);
+            mma_tf32(dB, wh, bh0, bh1);
+            mma_tf32(dS, wl, bh0, bh1);
+            mma_tf32(dT, wh, bl0, bl1);
           }
         }
       }
 
-      // ---- DCT-II on the tensor cores (feature.rs:120-123), transposed as well:
-      //   ceps^T [16][8 frames] = D [16][8 NT filters] (pre-split on the host) x logmel^T.
-      // One m-tile covers all (<= 16) cepstra; the accumulator holds (cepstrum g [+ 8], frame 2t [+ 1]).
       if (p.mfcc) {
-        __syncwarp();
-        float dB[4] = {0.f, 0.f, 0.f, 0.f}, dS[4] = {0.f, 0.f, 0.f, 0.f}, dT[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* lrow = lgT + g * kLgRow + 2 * t;
-        const float4* dp = reinterpret_cast<const float4*>(tab_s + a.dct_ofs) + lane;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float2 lv = *reinterpret_cast<const float2*>(lrow + 8 * nt);
-          const float4 wh = dp[(2 * nt) * 32], wl = dp[(2 * nt + 1) * 32];
-          uint32_t bh0, bl0, bh1, bl1;
-          split_tf32(lv.x, bh0, bl0);
-          split_tf32(lv.y, bh1, bl1);
-          mma_tf32(dB, wh, bh0, bh1);
-          mma_tf32(dS, wl, bh0, bh1);
-          mma_tf32(dT, wh, bl0, bl1);
-        }
         // scale (feature.rs:126-131), c0 <- ln(energy) (feature.rs:137-146) and stores; with a
         // fused CMVN the block is normalised in place below
         const int fr_a = tile_f0 + 2 * t;
@@ -494,9 +496,9 @@ static float tf32_rna(float x) {
 }
 
 struct FragTables {
-  int NT = 0, MT = 0;
-  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
-  std::vector<float> mel, dct;  // [blocks][2][32][4], [NT][2][32][4]
+  int NT = 0;
+  int ks_lo[kNtMax] = {0}, ks_n2[kNtMax] = {0}, mel_base[kNtMax] = {0};
+  std::vector<float> mel, dct;  // [blocks][32][4], [NT][2][32][4]
 };
 
 // A fragment of mma.m16n8k8 (row-major 16 x 8) for lane (g, t): rows g, g + 8; contraction slots t, t + 4.
@@ -516,37 +518,44 @@ static bool build_frags(const Derived& d, const MelBank& mb, FragTables* ft) {
   const int nf = d.nf;
   if (mb.max_bin > 128) return false;  // only bins <= 128 are kept (always true for the reference's bank at n_fft 512)
   if (nf > 8 * kNtMax || d.nc > kNcMax || nf < 1) return false;
-  const int NT = nf <= 40 ? 5 : 8, MT = (NT + 1) / 2;
+  const int NT = nf <= 40 ? 5 : 8;
   ft->NT = NT;
-  ft->MT = MT;
   const float mscale = 0.5f * (1.0f / (float)d.W);  // the kernel keeps 2 n_fft |X| in the tile
   const int ncol = 8 * kKsTab;
-  std::vector<float> dense((size_t)16 * MT * ncol, 0.f);  // [filter][bin]
+  std::vector<float> dense((size_t)8 * NT * ncol, 0.f);  // [filter][bin]
   for (int f = 0; f < nf; ++f)
     for (int i = 0; i < mb.len[f]; ++i) dense[(size_t)f * ncol + mb.start[f] + i] = mb.w[mb.wofs[f] + i] * mscale;
   ft->mel.clear();
-  for (int mt = 0; mt < kMtMax; ++mt) { ft->ks_lo[mt] = 0; ft->ks_n2[mt] = 0; ft->mel_base[mt] = 0; }
+  for (int nt = 0; nt < kNtMax; ++nt) { ft->ks_lo[nt] = 0; ft->ks_n2[nt] = 0; ft->mel_base[nt] = 0; }
   int n_blocks = 0;
-  for (int mt = 0; mt < MT; ++mt) {
+  for (int nt = 0; nt < NT; ++nt) {
     int lo = kKs, hi = 0;
     for (int ks = 0; ks < kKs; ++ks) {
       bool any = false;
-      for (int r = 0; r < 16; ++r)
-        for (int c = 0; c < 8; ++c) any = any || dense[(size_t)(16 * mt + r) * ncol + 8 * ks + c] != 0.f;
+      for (int r = 0; r < 8; ++r)
+        for (int c = 0; c < 8; ++c) any = any || dense[(size_t)(8 * nt + r) * ncol + 8 * ks + c] != 0.f;
       if (any) { lo = std::min(lo, ks); hi = std::max(hi, ks + 1); }
     }
-    if (hi <= lo) continue;  // 16 empty filters: no k-steps
+    if (hi <= lo) continue;  // 8 empty filters: no k-steps
     const int n2 = (hi - lo + 1) / 2;  // k-step pairs; an odd band gets one zero-weight block (ks <= 17 < kKsTab)
-    ft->ks_lo[mt] = lo;
-    ft->ks_n2[mt] = n2;
-    ft->mel_base[mt] = n_blocks;
+    ft->ks_lo[nt] = lo;
+    ft->ks_n2[nt] = n2;
+    ft->mel_base[nt] = n_blocks;
     for (int ks = lo; ks < lo + 2 * n2; ++ks, ++n_blocks) {
-      // contraction slot s <-> bin 8 ks + 2 (s % 4) + s / 4 (the kernel loads bins 2t, 2t + 1 as one float2)
+      // B fragment of mma.m16n8k8 (col-major 8 bins x 8 filters) for lane (g, t): filter 8 nt + g, contraction
+      // slots t, t + 4 <-> bins 8 ks + 2t, 8 ks + 2t + 1 (the kernel loads those two P values as one float2);
+      // stored pre-split as {hi b0, hi b1, lo b0, lo b1}
       const size_t o = ft->mel.size();
-      ft->mel.resize(o + 2 * 32 * 4, 0.f);
-      for (int lane = 0; lane < 32; ++lane)
-        put_a_frag(&ft->mel[o + lane * 4], &ft->mel[o + (32 + lane) * 4], lane,
-                   [&](int r, int s) { return dense[(size_t)(16 * mt + r) * ncol + 8 * ks + 2 * (s & 3) + (s >> 2)]; });
+      ft->mel.resize(o + 32 * 4, 0.f);
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        for (int i = 0; i < 2; ++i) {
+          const float v = dense[(size_t)(8 * nt + g) * ncol + 8 * ks + 2 * t + i];
+          const float h = tf32_rna(v);
+          ft->mel[o + lane * 4 + i] = h;
+          ft->mel[o + lane * 4 + 2 + i] = v - h;
+        }
+      }
     }
   }
   std::vector<float> dct;
@@ -569,7 +578,7 @@ struct Fast512cTables {
   float* d_tab = nullptr;  // tw | mel fragments | dct fragments
   int tab_floats = 0, dct_ofs = 0;
   int NT = 0;
-  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
+  int ks_lo[kNtMax] = {0}, ks_n2[kNtMax] = {0}, mel_base[kNtMax] = {0};
 };
 
 bool fast512c_supported(const Derived& d, const MelBank& mb) {
@@ -591,7 +600,7 @@ int fast512c_build_tables(const Derived& d, const MelBank& mb, Fast512cTables** 
     }
   Fast512cTables* t = new Fast512cTables;
   t->NT = ft.NT;
-  for (int i = 0; i < kMtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_n2[i] = ft.ks_n2[i]; t->mel_base[i] = ft.mel_base[i]; }
+  for (int i = 0; i < kNtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_n2[i] = ft.ks_n2[i]; t->mel_base[i] = ft.mel_base[i]; }
   h.insert(h.end(), ft.mel.begin(), ft.mel.end());
   t->dct_ofs = (int)ft.mel.size();
   h.insert(h.end(), ft.dct.begin(), ft.dct.end());
@@ -620,7 +629,7 @@ int launch_fast512c(const FrameParams& p, const Fast512cTables* t, int sm_count,
   a.tab = t->d_tab + kTabTw;
   a.tab_floats = t->tab_floats;
   a.dct_ofs = t->dct_ofs;
-  for (int i = 0; i < kMtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
+  for (int i = 0; i < kNtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
   // as many warps as the shared memory left by the tables allows (21 for the 40-filter bank)
   const size_t fixed = (size_t)(kTabTw + t->tab_floats + kMbarFloats) * sizeof(float);
   const int n_warps = (int)std::min<size_t>(kMaxWarps, (kSmemBudget - fixed) / (kWarpFloats * sizeof(float)));

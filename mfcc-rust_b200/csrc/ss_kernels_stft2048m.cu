@@ -10,19 +10,26 @@
 //     of one row per round; every warp writes the |X|^2 row of its frame into the group's [8][520]
 //     tile (double-buffered, so one named barrier of 256 threads per round is enough; the two groups
 //     drift apart in phase and hide each other's load and barrier latency).
-//   * The tile then feeds mel^T [128 filters][8 frames] = W [128][520 bins] x P^T on
-//     mma.sync.m16n8k8 TF32 split 3-way (hi x hi + lo x hi + hi x lo): 8 m-tiles of 16 filters, one
-//     per warp of the group; a job visits only the 8-bin k-steps its 16 filters' band touches (75
-//     of 520 blocks for the 128-filter bank).  The pre-split weight
-//     fragments (77 KB) are read from global memory: they are L2-resident and every warp needs
-//     only its own m-tile's share per round.  (A per-warp |X|^2 tile as in k_fast512c would be
-//     16.6 KB for 8 frames of 513 bins; sixteen of them do not fit next to the transpose tiles.)
-//   * The accumulator fragment holds (filter g [+ 8], frames 2t, 2t + 1): neighbours along the
-//     time-minor output [row][m][t], stored straight from registers as 8-byte pairs, 32 bytes per
-//     filter and job; the first generation's [nf][32] staging tile and its copy loop are gone.
+//   * The tile then feeds mel [8 frames][128 filters] = P [8][520 bins] x W^T on mma.sync.m16n8k8 TF32 split
+//     3-way (hi x hi + lo x hi + hi x lo) in n-tiles of 8 filters: the M rows are the 8 frames' high parts
+//     and, in rows 8..15, their low parts, so two MMAs per k-step cover the three products.  An n-tile visits only
+//     the 8-bin k-steps its 8 filters' band touches (83 of 1,040 blocks for the 128-filter bank), and the
+//     bands widen with the filter index, so a warp takes n-tile w and n-tile NT - 1 - w: 8 .. 14 k-steps
+//     per warp and round.  (The first cut had the filters as M rows, one 16-filter m-tile per warp: 2 .. 22
+//     k-steps, and every round's barrier waited for the warp with the widest band; its weight fragments
+//     were also twice the bytes.)  The pre-split weight fragments (42 KB) are read from global memory:
+//     they are L2 / L1-resident and every warp needs only its own n-tiles' share per round.  (A per-warp
+//     |X|^2 tile as in k_fast512c would be 16.6 KB for 8 frames of 513 bins; sixteen of them do not fit
+//     next to the transpose tiles.)
+//   * The accumulator fragment holds (frame g, filters 2t, 2t + 1): the 8 lanes of a filter store 32
+//     consecutive bytes of the time-minor output [row][m][t] straight from registers.
+//   * The samples of a warp's next frame (8 KB, contiguous) are requested by one TMA bulk copy into the
+//     warp's transpose tile as soon as the transpose of the current frame has been read, and complete on
+//     the warp's own mbarrier.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -44,12 +51,13 @@ constexpr int kPs = 520;                   // P row: bins 0..512 + zero pad; 65 
 constexpr int kKs = kPs / 8;
 constexpr int kKsTab = kKs + 1;            // bands are padded to an even number of k-steps
 constexpr int kTileFloats = kFpr * kPs + 8;  // + slack for the padded k-step of the last row
-constexpr int kMtMax = 8;                  // nf <= 128
+constexpr int kNtMax = 16;                 // n-tiles of 8 filters: nf <= 128
 constexpr int kTwRow = 68;                 // floats per lane row of the W1024 table (32 float2 + pad)
 constexpr int kTabTw = 0;                          // [32][kTwRow]
 constexpr int kTabTw2048 = kTabTw + kR * kTwRow;   // [512] float2 W2048^k
 constexpr int kTabWin = kTabTw2048 + 2 * 512;      // [1024] float2 window pairs
 constexpr int kTabFixed = kTabWin + 2 * kM;        // 5248 floats
+constexpr int kMbarFloats = 2 * kWarps;            // one 8-byte mbarrier per warp (staged frames), after the tables
 static_assert(kTabTw2048 % 4 == 0 && kTabWin % 4 == 0 && kTabFixed % 4 == 0, "table alignment");
 
 __device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
@@ -75,13 +83,13 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float4& a, uint32_
 struct Stft2048mArgs {
   FrameParams p;
   const float* tab;        // fixed tables (twiddles, window), copied to shared memory once per CTA
-  const float4* mel_frag;  // [blocks][hi, lo][32]: A fragments of the filterbank (16 filters x 8 bins), global
+  const float4* mel_frag;  // [blocks][32] {hi b0, hi b1, lo b0, lo b1}: B fragments of the filterbank (8 bins x 8 filters), global
   int64_t n_items;         // rows * rounds_per_row
   int rounds_per_row;
   int vec2;                // frames start 8-byte aligned
-  int pair_ok;             // T_out is even and the output is 8-byte aligned: float2 stores
-  int n_mt;                // m-tiles of 16 filters
-  int ks_lo[kMtMax], ks_n2[kMtMax], mel_base[kMtMax];
+  int stage;               // vec2 and a 16-byte aligned base: the next round's frame is staged by TMA bulk copy
+  int n_nt;                // n-tiles of 8 filters
+  int ks_lo[kNtMax], ks_n2[kNtMax], mel_base[kNtMax];
 };
 
 __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
@@ -99,11 +107,20 @@ __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
 __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
-  float* warp_s = smem + kTabFixed + (threadIdx.x >> 5) * kWarpFloats;
-  float* tile0 = smem + kTabFixed + kWarps * kWarpFloats + (threadIdx.x >> 8) * 2 * kTileFloats;  // this group's 2 x [8][kPs] (+ slack)
+  float* warp_s = smem + kTabFixed + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
+  float* tile0 = smem + kTabFixed + kMbarFloats + kWarps * kWarpFloats + (threadIdx.x >> 8) * 2 * kTileFloats;  // this group's 2 x [8][kPs] (+ slack)
   const FrameParams& p = a.p;
   const int nf = p.nf;
   for (int i = threadIdx.x; i < kTabFixed; i += kThreads) tab_s[i] = __ldg(a.tab + i);
+  // the samples of a warp's next frame arrive by TMA bulk copy and complete on the warp's own mbarrier
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint64_t*>(smem + kTabFixed) + (threadIdx.x >> 5));
+  if ((threadIdx.x & 31) == 0) {
+    asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;   // parity of the mbarrier phase the next staged frame completes
+  bool staged = false;  // this round's frame sits in the transpose tile (requested during the previous round)
+  int sshift = 0;       // ... starting at this float offset (the copy starts at the 16-byte boundary below the frame)
   // the pad bins of the tile rows are never written again and must be finite
   for (int i = threadIdx.x & 255; i < 2 * kTileFloats; i += 256) tile0[i] = 0.0f;
   __syncthreads();
@@ -122,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
   const int64_t memlen = p.N - p.S;
   const int c0 = (p.n_pad + 1) * p.S - p.N;
   // this warp's job in the filterbank product: one m-tile (16 filters) of its group's 8 frames
-  const int group = warp >> 3, wg = warp & 7, mt = wg;
+  const int group = warp >> 3, wg = warp & 7;
   int buf = 0;
 
   for (int64_t item = (int64_t)blockIdx.x * kGroups + group; item < a.n_items; item += (int64_t)gridDim.x * kGroups, buf ^= 1) {
@@ -138,7 +155,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       float2 v[kR];
       {
         const int64_t o0 = t * p.S + c0;
-        if (!computed) {
+        if (staged) {
+          unsigned done;
+          do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(mbar), "r"(phase)
+                : "memory");
+          } while (!done);
+          phase ^= 1u;
+          const float* sx = warp_s + sshift + 2 * u;
+          sfor<0, kR>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            const float2 x = *reinterpret_cast<const float2*>(sx + 64 * j);
+            const float2 w = win2[32 * j];
+            v[j] = __fmul2_rn(x, w);
+          });
+          __syncwarp();  // the buffer is the transpose tile again
+        } else if (!computed) {
           sfor<0, kR>([&](auto jj) { v[decltype(jj)::value] = make_float2(0.f, 0.f); });
         } else if (o0 >= 0 && o0 + kW <= p.row_len && a.vec2) {
           const float* px = rowp + o0 + 2 * u;
@@ -183,7 +220,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
           gg[2 * i + 1] = make_float2(x.z, x.w);
         });
       }
-      __syncwarp();  // the transpose tile is rewritten in the next round
+      __syncwarp();  // the transpose tile is free until the next round
+      // ---- request this warp's frame of the group's next item (2048 contiguous samples) while the second
+      // stage, the split and the filterbank of this one run: one TMA bulk copy (UBLKCP) into the transpose
+      // tile.  Only whole interior frames are staged; a source that is 8 but not 16 bytes aligned is copied
+      // from the 16-byte boundary below it (16 bytes more).
+      {
+        const int64_t nitem = item + (int64_t)gridDim.x * kGroups;
+        staged = false;
+        if (a.stage && nitem < a.n_items) {
+          const int64_t nrow = nitem / a.rounds_per_row;
+          const int64_t nt = (nitem - nrow * a.rounds_per_row) * kFpr + wg;
+          const int64_t no0 = nt * p.S + c0;
+          if (nt < p.T && no0 >= 0 && no0 + kW + 4 <= p.row_len) {
+            const float* src = p.pcm + nrow * p.row_stride + no0;
+            sshift = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);  // 0 or 2
+            staged = true;
+            if (lane == 0) {
+              const unsigned bytes = kW * 4 + (sshift ? 16 : 0);
+              const unsigned dst = (unsigned)__cvta_generic_to_shared(warp_s);
+              // the tile was last touched through the generic proxy (ordered by the __syncwarp above)
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                           "l"(src - sshift), "r"(bytes), "r"(mbar)
+                           : "memory");
+            }
+          }
+        }
+      }
       // ---- stage 2: 32-point FFT over the lane index.  gg[k2] = Z[u + 32 k2]
       ssfft::fft_pow2<kR>(gg);
 
@@ -210,59 +275,60 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
     // the group's tile of this round is complete (the other buffer belongs to the next round)
     asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");
 
-    // ---- mel filterbank on the tensor cores (feature.rs:163-174), transposed: this warp's job is
-    //   mel^T [16 filters of m-tile mt][8 frames] = W [16][band] x P^T,
-    // contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1 (one 8-byte load).
-    if (mt < a.n_mt) {
-      float accB[4] = {0.f, 0.f, 0.f, 0.f}, accS[4] = {0.f, 0.f, 0.f, 0.f}, accT[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* pp = tile + g * kPs + 2 * t4 + 8 * a.ks_lo[mt];
-      const float4* ap = a.mel_frag + (int64_t)a.mel_base[mt] * 64 + lane;
-      int n2 = a.ks_n2[mt];
+    // ---- mel filterbank on the tensor cores (feature.rs:163-174):
+    //   mel [8 frames][8 filters of n-tile nt] = P [8][band] x W^T,
+    // contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1 (one 8-byte load of P).
+    // An n-tile visits only the 8-bin k-steps its 8 filters' band touches; the bands widen with the filter
+    // index (1 .. 13 k-steps for the 128-filter bank), so a warp takes n-tile w and, beyond the first
+    // eight, NT - 1 - w: the widest with the narrowest (8 .. 14 k-steps per warp and round; with one m-tile
+    // of 16 filters per warp it was 2 .. 22, and every round's barrier waited for the last warp).
+    // Rows 8..15 of the A operand carry the low parts of the same frames: with A = [P_hi; P_lo] one MMA
+    // against W_hi yields hi x hi (rows 0..7) and lo x hi (rows 8..15), a second one against W_lo adds
+    // hi x lo (and the negligible lo x lo): two MMAs per k-step instead of three, no idle rows, and the split
+    // results are the operand registers as they are.
+    float* const out0 = p.mel_out + row * nf * p.T_out + t_round + g;  // (frame t_round + g) of filter 0
+    const bool fr_ok = t_round + g < p.T_out;
+#pragma unroll 1
+    for (int job = 0; job < 2; ++job) {
+      const int nt = job == 0 ? wg : a.n_nt - 1 - wg;
+      if (nt >= a.n_nt || (job == 1 && nt < kGroup)) break;
+      float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* pp = tile + g * kPs + 2 * t4 + 8 * a.ks_lo[nt];
+      const float4* bp = a.mel_frag + (int64_t)a.mel_base[nt] * 32 + lane;
+      int n2 = a.ks_n2[nt];
       // two k-steps per iteration (the band is padded to an even count with zero-weight blocks), the
       // weight fragments of the next iteration are requested before the MMAs of this one
-      float4 h0, l0, h1, l1;
-      if (n2 > 0) { h0 = __ldg(ap); l0 = __ldg(ap + 32); h1 = __ldg(ap + 64); l1 = __ldg(ap + 96); }
+      float4 w0, w1;
+      if (n2 > 0) { w0 = __ldg(bp); w1 = __ldg(bp + 32); }
 #pragma unroll 1
       for (; n2 > 0; --n2) {
         const float2 pv0 = *reinterpret_cast<const float2*>(pp);
         const float2 pv1 = *reinterpret_cast<const float2*>(pp + 8);
-        const float4 ch0 = h0, cl0 = l0, ch1 = h1, cl1 = l1;
+        const float4 c0 = w0, c1 = w1;
         pp += 16;
-        ap += 128;
-        if (n2 > 1) { h0 = __ldg(ap); l0 = __ldg(ap + 32); h1 = __ldg(ap + 64); l1 = __ldg(ap + 96); }
+        bp += 64;
+        if (n2 > 1) { w0 = __ldg(bp); w1 = __ldg(bp + 32); }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const float2 pv = h ? pv1 : pv0;
-          const float4 wh = h ? ch1 : ch0, wl = h ? cl1 : cl0;
-          uint32_t bh0, bl0, bh1, bl1;
-          split_tf32(pv.x, bh0, bl0);
-          split_tf32(pv.y, bh1, bl1);
-          mma_tf32(accB, wh, bh0, bh1);  // hi x hi
-          mma_tf32(accS, wl, bh0, bh1);  // lo x hi
-          mma_tf32(accT, wh, bl0, bl1);  // hi x lo
+          const float4 w = h ? c1 : c0;
+          uint32_t ah0, al0, ah2, al2;
+          split_tf32(pv.x, ah0, al0);
+          split_tf32(pv.y, ah2, al2);
+          const float4 av = make_float4(__uint_as_float(ah0), __uint_as_float(al0), __uint_as_float(ah2), __uint_as_float(al2));
+          mma_tf32(accH, av, __float_as_uint(w.x), __float_as_uint(w.y));  // [hi; lo] x hi
+          mma_tf32(accL, av, __float_as_uint(w.z), __float_as_uint(w.w));  // [hi; lo] x lo
         }
       }
-      // accumulator: (filter 16 mt + g [+ 8], frames t_round + 2 t4 [+ 1])
-      const int64_t fa = t_round + 2 * t4;
-      const bool va = fa < p.T_out, vb = fa + 1 < p.T_out;
-      float* outp = p.mel_out + row * nf * p.T_out + fa;
+      // accumulator rows g / g + 8: (frame t_round + g, filters 8 nt + 2 t4 [+ 1]) from the high / low parts; the
+      // 8 lanes of a filter write 32 consecutive bytes of the time-minor output [row][m][t]
+      if (fr_ok) {
+        float* outp = out0 + (int64_t)(8 * nt + 2 * t4) * p.T_out;
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int f = 16 * mt + g + 8 * hh;
-        float m0 = accB[2 * hh] + (accS[2 * hh] + accT[2 * hh]);
-        float m1 = accB[2 * hh + 1] + (accS[2 * hh + 1] + accT[2 * hh + 1]);
-        if (p.log_mode) {
-          m0 = fast_ln(zero_handling(m0));
-          m1 = fast_ln(zero_handling(m1));
-        }
-        if (f < nf) {
-          float* dst = outp + (int64_t)f * p.T_out;
-          if (a.pair_ok && vb) {
-            *reinterpret_cast<float2*>(dst) = make_float2(m0, m1);
-          } else {
-            if (va) dst[0] = m0;
-            if (vb) dst[1] = m1;
-          }
+        for (int i = 0; i < 2; ++i) {
+          float m = accH[i] + (accH[i + 2] + (accL[i] + accL[i + 2]));
+          if (p.log_mode) m = fast_ln(zero_handling(m));
+          if (8 * nt + 2 * t4 + i < nf) outp[(int64_t)i * p.T_out] = m;
         }
       }
     }
@@ -280,50 +346,50 @@ static float tf32_rna(float x) {
 }
 
 struct FragTables2048 {
-  int n_mt = 0;
-  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
-  std::vector<float> mel;  // [blocks][hi, lo][32][4]
+  int n_nt = 0;
+  int ks_lo[kNtMax] = {0}, ks_n2[kNtMax] = {0}, mel_base[kNtMax] = {0};
+  std::vector<float> mel;  // [blocks][32][4]
 };
 
-// A fragments of mma.m16n8k8 (row-major 16 filters x 8 bins) for lane (g, t): rows g, g + 8;
-// contraction slot s <-> bin 8 ks + 2 (s % 4) + s / 4.  Only the k-steps inside each 16-filter
-// group's band are stored, padded to an even count.
+// B fragments of mma.m16n8k8 (col-major 8 bins x 8 filters) for lane (g, t): filter 8 nt + g, contraction
+// slots t and t + 4, i.e. bins 8 ks + 2t and 8 ks + 2t + 1, each as {hi, lo}: one float4
+// {hi b0, hi b1, lo b0, lo b1} per lane and block.  Only the k-steps inside each 8-filter group's band are
+// stored, padded to an even count.
 static bool build_frags(const Derived& d, const MelBank& mb, float pscale, FragTables2048* ft) {
   const int nf = d.nf;
-  if (mb.max_bin > 512 || nf > 16 * kMtMax || nf < 1) return false;
-  const int MT = (nf + 15) / 16, ncol = 8 * kKsTab;
-  ft->n_mt = MT;
-  std::vector<float> dense((size_t)16 * MT * ncol, 0.f);  // [filter][bin]
+  if (mb.max_bin > 512 || nf > 8 * kNtMax || nf < 1) return false;
+  const int NT = (nf + 7) / 8, ncol = 8 * kKsTab;
+  ft->n_nt = NT;
+  std::vector<float> dense((size_t)8 * NT * ncol, 0.f);  // [filter][bin]
   for (int f = 0; f < nf; ++f)
     for (int i = 0; i < mb.len[f]; ++i) dense[(size_t)f * ncol + mb.start[f] + i] = mb.w[mb.wofs[f] + i] * pscale;
   int n_blocks = 0;
   ft->mel.clear();
-  for (int mt = 0; mt < MT; ++mt) {
+  for (int nt = 0; nt < NT; ++nt) {
     int lo = kKs, hi = 0;
     for (int ks = 0; ks < kKs; ++ks) {
       bool any = false;
-      for (int r = 0; r < 16; ++r)
-        for (int c = 0; c < 8; ++c) any = any || dense[(size_t)(16 * mt + r) * ncol + 8 * ks + c] != 0.f;
+      for (int r = 0; r < 8; ++r)
+        for (int c = 0; c < 8; ++c) any = any || dense[(size_t)(8 * nt + r) * ncol + 8 * ks + c] != 0.f;
       if (any) { lo = std::min(lo, ks); hi = std::max(hi, ks + 1); }
     }
-    ft->ks_lo[mt] = 0;
-    ft->ks_n2[mt] = 0;
-    ft->mel_base[mt] = n_blocks;
-    if (hi <= lo) continue;  // 16 empty filters: no k-steps, the outputs are exact zeros
+    ft->ks_lo[nt] = 0;
+    ft->ks_n2[nt] = 0;
+    ft->mel_base[nt] = n_blocks;
+    if (hi <= lo) continue;  // 8 empty filters: no k-steps, the outputs are exact zeros
     const int n2 = (hi - lo + 1) / 2;
-    ft->ks_lo[mt] = lo;
-    ft->ks_n2[mt] = n2;
+    ft->ks_lo[nt] = lo;
+    ft->ks_n2[nt] = n2;
     for (int ks = lo; ks < lo + 2 * n2; ++ks, ++n_blocks) {
       const size_t o = ft->mel.size();
-      ft->mel.resize(o + 2 * 32 * 4, 0.f);
+      ft->mel.resize(o + 32 * 4, 0.f);
       for (int lane = 0; lane < 32; ++lane) {
         const int g = lane >> 2, t = lane & 3;
-        for (int i = 0; i < 4; ++i) {
-          const int r = g + 8 * (i & 1), s = t + 4 * (i >> 1);
-          const float v = dense[(size_t)(16 * mt + r) * ncol + 8 * ks + 2 * (s & 3) + (s >> 2)];
+        for (int i = 0; i < 2; ++i) {
+          const float v = dense[(size_t)(8 * nt + g) * ncol + 8 * ks + 2 * t + i];
           const float h = tf32_rna(v);
           ft->mel[o + lane * 4 + i] = h;
-          ft->mel[o + (32 + lane) * 4 + i] = v - h;
+          ft->mel[o + lane * 4 + 2 + i] = v - h;
         }
       }
     }
@@ -336,8 +402,8 @@ static bool build_frags(const Derived& d, const MelBank& mb, float pscale, FragT
 struct Stft2048mTables {
   float* d_tab = nullptr;
   size_t o_mel = 0;
-  int n_mt = 0;
-  int ks_lo[kMtMax] = {0}, ks_n2[kMtMax] = {0}, mel_base[kMtMax] = {0};
+  int n_nt = 0;
+  int ks_lo[kNtMax] = {0}, ks_n2[kNtMax] = {0}, mel_base[kNtMax] = {0};
 };
 
 bool stft2048m_supported(const Derived& d, const MelBank& mb) {
@@ -367,8 +433,8 @@ int stft2048m_build_tables(const Derived& d, const MelBank& mb, const std::vecto
   Stft2048mTables* t = new Stft2048mTables;
   t->o_mel = h.size();
   h.insert(h.end(), ft.mel.begin(), ft.mel.end());
-  t->n_mt = ft.n_mt;
-  for (int i = 0; i < kMtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_n2[i] = ft.ks_n2[i]; t->mel_base[i] = ft.mel_base[i]; }
+  t->n_nt = ft.n_nt;
+  for (int i = 0; i < kNtMax; ++i) { t->ks_lo[i] = ft.ks_lo[i]; t->ks_n2[i] = ft.ks_n2[i]; t->mel_base[i] = ft.mel_base[i]; }
   cudaError_t e = cudaMalloc(&t->d_tab, h.size() * sizeof(float));
   if (e != cudaSuccess) { delete t; return (int)e; }
   e = cudaMemcpy(t->d_tab, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -390,13 +456,14 @@ int launch_stft2048m(const FrameParams& p, const Stft2048mTables* t, int sm_coun
   a.p = p;
   a.tab = t->d_tab;
   a.mel_frag = reinterpret_cast<const float4*>(t->d_tab + t->o_mel);
-  a.n_mt = t->n_mt;
-  for (int i = 0; i < kMtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
+  a.n_nt = t->n_nt;
+  for (int i = 0; i < kNtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
   a.rounds_per_row = (int)((p.T_out + kFpr - 1) / kFpr);
   a.n_items = p.n_rows * (int64_t)a.rounds_per_row;
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
-  a.pair_ok = (p.T_out % 2 == 0) && (reinterpret_cast<uintptr_t>(p.mel_out) % 8 == 0);
-  const size_t smem = (size_t)(kTabFixed + kWarps * kWarpFloats + kGroups * 2 * kTileFloats) * sizeof(float);
+  static const bool no_stage = getenv("SS_STFT2048M_STAGE") && atoi(getenv("SS_STFT2048M_STAGE")) == 0;  // A/B switch
+  a.stage = a.vec2 && !no_stage && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
+  const size_t smem = (size_t)(kTabFixed + kMbarFloats + kWarps * kWarpFloats + kGroups * 2 * kTileFloats) * sizeof(float);
   const int64_t grid = std::min<int64_t>((a.n_items + kGroups - 1) / kGroups, (int64_t)sm_count);
   if (grid <= 0) return 0;
   cudaError_t e = cudaFuncSetAttribute(k_stft2048m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
