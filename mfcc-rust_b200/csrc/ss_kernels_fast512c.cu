@@ -78,6 +78,14 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
+// one 4-byte shared-memory load that the compiler must not merge with its neighbour: the two P values of a
+// lane go to slots 0 and 2 of the MMA's A register quad, and an 8-byte load would land them side by side
+// (ptxas then spends four moves per k-step on rebuilding the quad)
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 // D += A(16x8, row) * B(8x8, col), TF32 inputs, f32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float4& a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
       // log-mel values are exactly this lane's B fragment of the DCT product below (contraction slot t <->
       // filter 8 nt + 2t, slot t + 4 <-> filter 8 nt + 2t + 1; the DCT matrix fragments are permuted on the
       // host), so ln -> DCT needs no data movement.
-      // ---- DCT-II on the tensor cores (feature.rs:120-123), transposed:
+      // DCT-II (feature.rs:120-123), transposed as well:
       //   ceps^T [16][8 frames] = D [16][8 NT filters] (pre-split on the host) x logmel^T.
       // One m-tile covers all (<= 16) cepstra; the accumulator holds (cepstrum g [+ 8], frame 2t [+ 1]).
       float dB[4] = {0.f, 0.f, 0.f, 0.f}, dS[4] = {0.f, 0.f, 0.f, 0.f}, dT[4] = {0.f, 0.f, 0.f, 0.f};
@@ -351,24 +359,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
         const int fr_g = tile_f0 + g;
         const bool vg = fr_g < fend;
         const int64_t og = (obase + fr_g) * nf;
-        const float* prow = Pt + g * kPs + 2 * t;
+        const unsigned prow_a = (unsigned)__cvta_generic_to_shared(Pt + g * kPs + 2 * t);
         const float4* dp = reinterpret_cast<const float4*>(tab_s + a.dct_ofs) + lane;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
           float numH[4] = {0.f, 0.f, 0.f, 0.f}, numL[4] = {0.f, 0.f, 0.f, 0.f};
           const int k0 = a.ks_lo[nt];
-          const float* pp = prow + 8 * k0;
+          unsigned pp = prow_a + 32 * k0;  // shared-memory byte address of P[g][8 k0 + 2t]
           const float4* bp = reinterpret_cast<const float4*>(tab_s) + a.mel_base[nt] * 32 + lane;
           float rb = SSC ? fmaf(p.ssc_step, (float)(8 * k0 + 2 * t), p.ssc_r0) : 0.f;  // R[k] of this lane's first bin
           // two k-steps per iteration (the band is padded to an even count with zero-weight blocks;
           // the tile columns those read are finite)
 #pragma unroll 1
           for (int n2 = a.ks_n2[nt]; n2 > 0; --n2) {
-            const float2 pv0 = *reinterpret_cast<const float2*>(pp);
-            const float2 pv1 = *reinterpret_cast<const float2*>(pp + 8);
+            const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 4));
+            const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 36));
             const float4 w0 = bp[0], w1 = bp[32];
-            pp += 16;
+            pp += 64;
             bp += 64;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
               if (SSC && p.ssc) { p.ssc[o] = s0; if (v1) p.ssc[o + 1] = s1; }
             }
           }
+          // ---- DCT-II on the tensor cores: the k-step of this n-tile's 8 filters
           if (p.mfcc) {
             const float4 wh = dp[(2 * nt) * 32], wl = dp[(2 * nt + 1) * 32];
             uint32_t bh0, bl0, bh1, bl1;

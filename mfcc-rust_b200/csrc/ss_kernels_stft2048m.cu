@@ -71,6 +71,14 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
+// one 4-byte shared-memory load that the compiler must not merge with its neighbour: the two P values of a
+// lane go to slots 0 and 2 of the MMA's A register quad, and an 8-byte load would land them side by side
+// (ptxas then spends four moves per k-step on rebuilding the quad)
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 // D += A(16x8, row) * B(8x8, col), TF32 inputs, f32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float4& a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       const int nt = job == 0 ? wg : a.n_nt - 1 - wg;
       if (nt >= a.n_nt || (job == 1 && nt < kGroup)) break;
       float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* pp = tile + g * kPs + 2 * t4 + 8 * a.ks_lo[nt];
+      unsigned pp = (unsigned)__cvta_generic_to_shared(tile + g * kPs + 2 * t4 + 8 * a.ks_lo[nt]);
       const float4* bp = a.mel_frag + (int64_t)a.mel_base[nt] * 32 + lane;
       int n2 = a.ks_n2[nt];
       // two k-steps per iteration (the band is padded to an even count with zero-weight blocks), the
@@ -302,10 +310,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       if (n2 > 0) { w0 = __ldg(bp); w1 = __ldg(bp + 32); }
 #pragma unroll 1
       for (; n2 > 0; --n2) {
-        const float2 pv0 = *reinterpret_cast<const float2*>(pp);
-        const float2 pv1 = *reinterpret_cast<const float2*>(pp + 8);
+        const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 4));
+        const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 36));
         const float4 c0 = w0, c1 = w1;
-        pp += 16;
+        pp += 64;
         bp += 64;
         if (n2 > 1) { w0 = __ldg(bp); w1 = __ldg(bp + 32); }
 #pragma unroll
