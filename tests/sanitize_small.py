@@ -49,6 +49,8 @@ for nf, nc in ((64, 16), (41, 8), (17, 12)):
 sb.feature.features(o.synth_signal(1, 16000 * 20 + 3, 8), cfg, mfe=True, ssc=True, mfcc=True)
 k4 = sb.SpeechConfig(**C4, devices=[0])
 sb.feature.mel_spectrogram2(o.synth_signal(3, 16000 * 3, 9), k4, log=True)   # staged rounds + ring wrap-around
+# k_stft2048m with more items than resident groups: the TMA-staged frames of a group's next item, odd rows 8-byte aligned
+sb.feature.mel_spectrogram2(o.synth_signal(60, 22050, 12), sb.SpeechConfig(**C3, devices=[0]), log=True)
 for hop in (160, 100):  # librosa mode on the register-FFT kernel (full-spectrum tile; staged and per-sample rounds)
     sb.feature.melspectrogram_librosa(o.synth_signal(3, 16000 * 2 + 5, 10), sb.feature.librosa_config(16000, 400, hop, 80, devices=[0]), db=True)
 sb.feature.melspectrogram_librosa(o.synth_signal(2, 5000, 11), sb.feature.librosa_config(22050, 512, 128, 40, devices=[0]))
