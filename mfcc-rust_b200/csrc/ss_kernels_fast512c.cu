@@ -49,10 +49,11 @@ constexpr int kXs = 18;                       // transpose row stride in float2 
 constexpr int kXchFrame = 16 * kXs;           // 288 float2 per frame
 constexpr int kXchFloats = 2 * kXchFrame * 2; // 1152 floats per warp (2 frames)
 constexpr int kTileRows = 8;                  // frames per MMA tile
-constexpr int kPs = 136;                      // P row stride: 17 k-steps of 8 bins; 136 % 32 == 8 -> conflict-free LDS.64 A fragments
-constexpr int kKs = kPs / 8;                  // 17 k-steps
+constexpr int kPs = 132;                      // P row stride: bins 0..128 + 3 zero pads; 132 % 32 == 4 -> the 4-byte A-fragment loads (row g, bin t) hit 32 banks
+constexpr int kKs = 17;                       // k-steps of 8 bins; the last one runs 4 floats into the next row (finite values x zero weights)
 constexpr int kKsTab = kKs + 1;               // + one zero block: bands are padded to an even number of k-steps
-constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows;  // + 8 frame energies
+constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows + 4;  // + 8 frame energies + 4 zeros: the zero-weight
+                                                                           // block of an odd band reads bins 136..143 of row 7
 static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 constexpr int kTwRow = 36;                    // floats per lane row of the W256 table (16 float2 + pad)
 constexpr int kTabTw = 16 * kTwRow;           // CTA-shared twiddle table
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
                  "l"(a.tw), "r"(bytes), "r"(mbar_tab)
                  : "memory");
   }
-  // the tile's pad columns (bins 132..135) are never written again and must be finite
+  // the tile's pad columns and the energies behind the last row (read by the zero-weight end of the last k-step) must be finite
   for (int i = (threadIdx.x & 31); i < kWarpFloats; i += 32) warp_s[i] = 0.0f;
   // the staged samples of the next pair arrive by TMA bulk copy and complete on this warp's mbarrier
   const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_all + (threadIdx.x >> 5));
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
       // 8..15 the remainders, so A = [P_hi; P_lo] against W_hi yields hi x hi and lo x hi at once and a second
       // MMA against W_lo adds hi x lo: two MMAs per k-step (8 bins x 8 filters), one 16-byte load of weights.
       // Only the k-steps an 8-filter group's band touches are visited (22 of 85 for the 40-filter bank).
-      // Contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1, so a lane's two P values are
-      // one 8-byte load.  The accumulator rows g / g + 8 hold (frame g, filters 8 nt + 2t [+ 1]):
+      // Contraction slot t <-> bin 8 ks + t, slot t + 4 <-> bin 8 ks + 4 + t; a lane's two P values are two
+      // 4-byte loads (conflict-free: bank 4 g + t with the 132-float row stride).  The accumulator rows g / g + 8 hold (frame g, filters 8 nt + 2t [+ 1]):
       // zero_handling -> stores -> ln follow on the fragment (feature.rs:216-230, 242-245), and the two
       // log-mel values are exactly this lane's B fragment of the DCT product below (contraction slot t <->
       // filter 8 nt + 2t, slot t + 4 <-> filter 8 nt + 2t + 1; the DCT matrix fragments are permuted on the
@@ -359,22 +360,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
         const int fr_g = tile_f0 + g;
         const bool vg = fr_g < fend;
         const int64_t og = (obase + fr_g) * nf;
-        const unsigned prow_a = (unsigned)__cvta_generic_to_shared(Pt + g * kPs + 2 * t);
+        const unsigned prow_a = (unsigned)__cvta_generic_to_shared(Pt + g * kPs + t);
         const float4* dp = reinterpret_cast<const float4*>(tab_s + a.dct_ofs) + lane;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
           float numH[4] = {0.f, 0.f, 0.f, 0.f}, numL[4] = {0.f, 0.f, 0.f, 0.f};
           const int k0 = a.ks_lo[nt];
-          unsigned pp = prow_a + 32 * k0;  // shared-memory byte address of P[g][8 k0 + 2t]
+          unsigned pp = prow_a + 32 * k0;  // shared-memory byte address of P[g][8 k0 + t]
           const float4* bp = reinterpret_cast<const float4*>(tab_s) + a.mel_base[nt] * 32 + lane;
-          float rb = SSC ? fmaf(p.ssc_step, (float)(8 * k0 + 2 * t), p.ssc_r0) : 0.f;  // R[k] of this lane's first bin
+          float rb = SSC ? fmaf(p.ssc_step, (float)(8 * k0 + t), p.ssc_r0) : 0.f;  // R[k] of this lane's first bin
           // two k-steps per iteration (the band is padded to an even count with zero-weight blocks;
           // the tile columns those read are finite)
 #pragma unroll 1
           for (int n2 = a.ks_n2[nt]; n2 > 0; --n2) {
-            const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 4));
-            const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 36));
+            const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 16));        // bins 8 ks + t, 8 ks + 4 + t
+            const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 48));
             const float4 w0 = bp[0], w1 = bp[32];
             pp += 64;
             bp += 64;
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
               mma_tf32(accL, av, __float_as_uint(w.z), __float_as_uint(w.w));  // [hi; lo] x lo
               if (SSC) {  // numerator: the same weights against P[k] R[k]
                 split_tf32(pv.x * rb, h0, l0);
-                split_tf32(pv.y * (rb + p.ssc_step), h2, l2);
+                split_tf32(pv.y * fmaf(4.0f, p.ssc_step, rb), h2, l2);
                 rb = fmaf(8.0f, p.ssc_step, rb);
                 const float4 nv = make_float4(__uint_as_float(h0), __uint_as_float(l0), __uint_as_float(h2), __uint_as_float(l2));
                 mma_tf32(numH, nv, __float_as_uint(w.x), __float_as_uint(w.y));
@@ -552,14 +553,14 @@ static bool build_frags(const Derived& d, const MelBank& mb, FragTables* ft) {
     ft->mel_base[nt] = n_blocks;
     for (int ks = lo; ks < lo + 2 * n2; ++ks, ++n_blocks) {
       // B fragment of mma.m16n8k8 (col-major 8 bins x 8 filters) for lane (g, t): filter 8 nt + g, contraction
-      // slots t, t + 4 <-> bins 8 ks + 2t, 8 ks + 2t + 1 (the kernel loads those two P values as one float2);
+      // slots t, t + 4 <-> bins 8 ks + t, 8 ks + 4 + t;
       // stored pre-split as {hi b0, hi b1, lo b0, lo b1}
       const size_t o = ft->mel.size();
       ft->mel.resize(o + 32 * 4, 0.f);
       for (int lane = 0; lane < 32; ++lane) {
         const int g = lane >> 2, t = lane & 3;
         for (int i = 0; i < 2; ++i) {
-          const float v = dense[(size_t)(8 * nt + g) * ncol + 8 * ks + 2 * t + i];
+          const float v = dense[(size_t)(8 * nt + g) * ncol + 8 * ks + t + 4 * i];
           const float h = tf32_rna(v);
           ft->mel[o + lane * 4 + i] = h;
           ft->mel[o + lane * 4 + 2 + i] = v - h;

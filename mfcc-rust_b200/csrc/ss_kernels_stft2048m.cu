@@ -47,10 +47,10 @@ constexpr int kWarps = 16, kThreads = kWarps * 32;
 constexpr int kGroup = 8, kGroups = kWarps / kGroup, kFpr = kGroup;  // 8 frames per group and round
 constexpr int kXs = 34;                    // transpose row stride in float2 (272 B: 16-byte rows, conflict-free LDS.128)
 constexpr int kWarpFloats = kR * kXs * 2;  // 2176 floats per warp
-constexpr int kPs = 520;                   // P row: bins 0..512 + zero pad; 65 k-steps of 8; 520 % 32 == 8 -> conflict-free LDS.64
-constexpr int kKs = kPs / 8;
+constexpr int kPs = 516;                   // P row: bins 0..512 + 3 zero pads; 516 % 32 == 4 -> the 4-byte A-fragment loads (row g, bin t) hit 32 banks
+constexpr int kKs = 65;                    // k-steps of 8 bins; the last one runs 4 floats into the next row / the slack (finite values x zero weights)
 constexpr int kKsTab = kKs + 1;            // bands are padded to an even number of k-steps
-constexpr int kTileFloats = kFpr * kPs + 8;  // + slack for the padded k-step of the last row
+constexpr int kTileFloats = kFpr * kPs + 12;  // + slack: the zero-weight block of an odd band reads bins 520..527 of the last row
 constexpr int kNtMax = 16;                 // n-tiles of 8 filters: nf <= 128
 constexpr int kTwRow = 68;                 // floats per lane row of the W1024 table (32 float2 + pad)
 constexpr int kTabTw = 0;                          // [32][kTwRow]
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
 
     // ---- mel filterbank on the tensor cores (feature.rs:163-174):
     //   mel [8 frames][8 filters of n-tile nt] = P [8][band] x W^T,
-    // contraction slot t <-> bin 8 ks + 2t, slot t + 4 <-> bin 8 ks + 2t + 1 (one 8-byte load of P).
+    // contraction slot t <-> bin 8 ks + t, slot t + 4 <-> bin 8 ks + 4 + t (two conflict-free 4-byte loads of P).
     // An n-tile visits only the 8-bin k-steps its 8 filters' band touches; the bands widen with the filter
     // index (1 .. 13 k-steps for the 128-filter bank), so a warp takes n-tile w and, beyond the first
     // eight, NT - 1 - w: the widest with the narrowest (8 .. 14 k-steps per warp and round; with one m-tile
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       const int nt = job == 0 ? wg : a.n_nt - 1 - wg;
       if (nt >= a.n_nt || (job == 1 && nt < kGroup)) break;
       float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
-      unsigned pp = (unsigned)__cvta_generic_to_shared(tile + g * kPs + 2 * t4 + 8 * a.ks_lo[nt]);
+      unsigned pp = (unsigned)__cvta_generic_to_shared(tile + g * kPs + t4 + 8 * a.ks_lo[nt]);
       const float4* bp = a.mel_frag + (int64_t)a.mel_base[nt] * 32 + lane;
       int n2 = a.ks_n2[nt];
       // two k-steps per iteration (the band is padded to an even count with zero-weight blocks), the
@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       if (n2 > 0) { w0 = __ldg(bp); w1 = __ldg(bp + 32); }
 #pragma unroll 1
       for (; n2 > 0; --n2) {
-        const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 4));
-        const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 36));
+        const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 16));  // bins 8 ks + t, 8 ks + 4 + t
+        const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 48));
         const float4 c0 = w0, c1 = w1;
         pp += 64;
         bp += 64;
@@ -360,7 +360,7 @@ struct FragTables2048 {
 };
 
 // B fragments of mma.m16n8k8 (col-major 8 bins x 8 filters) for lane (g, t): filter 8 nt + g, contraction
-// slots t and t + 4, i.e. bins 8 ks + 2t and 8 ks + 2t + 1, each as {hi, lo}: one float4
+// slots t and t + 4, i.e. bins 8 ks + t and 8 ks + 4 + t, each as {hi, lo}: one float4
 // {hi b0, hi b1, lo b0, lo b1} per lane and block.  Only the k-steps inside each 8-filter group's band are
 // stored, padded to an even count.
 static bool build_frags(const Derived& d, const MelBank& mb, float pscale, FragTables2048* ft) {
@@ -394,7 +394,7 @@ static bool build_frags(const Derived& d, const MelBank& mb, float pscale, FragT
       for (int lane = 0; lane < 32; ++lane) {
         const int g = lane >> 2, t = lane & 3;
         for (int i = 0; i < 2; ++i) {
-          const float v = dense[(size_t)(8 * nt + g) * ncol + 8 * ks + 2 * t + i];
+          const float v = dense[(size_t)(8 * nt + g) * ncol + 8 * ks + t + 4 * i];
           const float h = tf32_rna(v);
           ft->mel[o + lane * 4 + i] = h;
           ft->mel[o + lane * 4 + 2 + i] = v - h;
