@@ -73,6 +73,47 @@ def test_filterbank_matches_oracle_on_random_parameter_sets():
         np.testing.assert_array_equal(cfg.filterbank(), fb, err_msg=str(kw))
 
 
+def test_derived_sizes_and_frame_counts_on_random_parameter_sets():
+    """1,000 seeded random (sample rate, FFT length, frame length / stride on and next to the .5 ties of
+    round(sr * length), processing.rs:77-78): frame length, step, hop (trunc, config.rs:154), freq_size, wnorm and
+    the Vorbis window equal the oracle's, an invalid combination is rejected by both, and the f32 frame-count
+    arithmetic (processing.rs:91-102, functions.rs:97) agrees on random signal lengths."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0A10))
+    for _ in range(1000):
+        sr = int(rng.choice([8000, 11025, 16000, 22050, 32000, 44100, 48000]))
+        W = int(rng.choice([64, 128, 200, 256, 400, 480, 512, 1000, 1024, 2048, 4096]))
+        L = int(rng.integers(2, W + 1))
+        S = int(rng.integers(1, L + 1))
+        fl = np.float32((L + float(rng.choice([0.0, 0.5, 0.25, -0.25, 0.4999, 0.5001]))) / sr)
+        fs = np.float32((S + float(rng.choice([0.0, 0.5, 0.25, -0.25, 0.4999, 0.5001]))) / sr)
+        nf = int(rng.integers(1, 65))
+        kw = dict(sample_rate=sr, fft_points=W, frame_length=float(fl), frame_stride=float(fs), num_cepstral=min(13, nf),
+                  num_filters=nf, low_frequency=0.0, high_frequency=sr / 2)
+        try:
+            oc = o.SpeechConfig(**kw)
+        except Exception:
+            with pytest.raises(sb.SpeechsauceError):
+                sb.SpeechConfig(**kw, devices=[])
+            continue
+        cfg = sb.SpeechConfig(**kw, devices=[])
+        assert (cfg.frame_sample_length, cfg.frame_step, cfg.frame_size, cfg.freq_size) == \
+               (oc.frame_sample_length, oc.frame_step, oc.frame_size, oc.freq_size), kw
+        assert np.float32(cfg.wnorm) == np.float32(oc.wnorm), kw
+        np.testing.assert_array_equal(cfg.window, oc.window, err_msg=str(kw))
+        Lr, Sr = oc.frame_sample_length, oc.frame_step
+        for n in (int(rng.integers(1, 10**7)), Lr, Lr + Sr * int(rng.integers(0, 1000))):
+            for zp in (0, 1):
+                try:
+                    want = o.num_frames(n, Lr, Sr, bool(zp))
+                    if not zp and want < 1:
+                        want = -1
+                except ValueError:
+                    want = -1
+                assert sb.lib.ss_num_frames(n, Lr, Sr, zp) == want, (n, Lr, Sr, zp)
+            if oc.frame_size > 0:
+                assert sb.lib.ss_stft_num_frames(n, oc.frame_size) == o.stft_num_frames(n, oc.frame_size), (n, oc.frame_size)
+
+
 def test_frame_counts_follow_reference_f32_arithmetic():
     for n, L, S in [(16000, 400, 160), (16000, 320, 160), (10**6, 320, 160), (57_600_000, 400, 160), (401, 400, 160),
                     (123457, 400, 160), (2**24 + 3, 400, 160)]:
