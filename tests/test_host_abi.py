@@ -73,6 +73,24 @@ def test_filterbank_matches_oracle_on_random_parameter_sets():
         np.testing.assert_array_equal(cfg.filterbank(), fb, err_msg=str(kw))
 
 
+def test_slaney_filterbank_matches_oracle_on_random_parameter_sets():
+    """SS_FLAG_LIBROSA plans: the host-built Slaney bank against the oracle's (itself pinned to torchaudio in
+    test_oracle_kat.py) on 200 random (sr, n_fft, n_mels, fmin, fmax).  Both are computed in f64 and stored
+    as f32; the two libms differ in the last f64 bit at a few triangle corners, so the comparison allows 1e-7 of
+    the bank's peak (most parameter sets are bit-identical)."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0A20))
+    for _ in range(200):
+        sr = int(rng.choice([8000, 16000, 22050, 44100, 48000]))
+        n_fft = int(rng.choice([128, 256, 400, 512, 1000, 1024, 2048]))
+        n_mels = int(rng.integers(4, 129))
+        fmin = float(rng.choice([0.0, 30.0, 125.5]))
+        fmax = [None, 0.45 * sr, 0.3 * sr][int(rng.integers(0, 3))]
+        cfg = sb.feature.librosa_config(sr, n_fft, max(1, n_fft // 4), n_mels, fmin, fmax, devices=[])
+        got, want = cfg.filterbank(), o.librosa_mel_filters(sr, n_fft, n_mels, fmin, fmax)
+        assert got.shape == want.shape == (n_mels, n_fft // 2 + 1)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-7 * float(want.max()), err_msg=f"{sr} {n_fft} {n_mels} {fmin} {fmax}")
+
+
 def test_derived_sizes_and_frame_counts_on_random_parameter_sets():
     """1,000 seeded random (sample rate, FFT length, frame length / stride on and next to the .5 ties of
     round(sr * length), processing.rs:77-78): frame length, step, hop (trunc, config.rs:154), freq_size, wnorm and
