@@ -51,3 +51,45 @@ def test_c_port_frame_counts():
             except ValueError:
                 want = -1
             assert L.orc_num_frames(n, Lf, S, zp) == want
+
+
+def test_c_port_matches_numpy_oracle_on_random_parameter_sets():
+    """100 + 60 seeded random parameter sets (as in the GPU sweeps): the two CPU implementations agree on every
+    output.  This pins the C port's build flags as well: with GCC's default -ffp-contract=fast and -march=native
+    the fused m0 + step * i of the mel linspace moved the last band edge by one bin on 3 % of random parameter
+    sets (rustc never fuses on its own; oracle/Makefile passes -ffp-contract=off)."""
+    rng = np.random.Generator(np.random.Philox(0x5EED0A30))
+    for i in range(100):
+        sr = int(rng.choice([8000, 11025, 16000, 22050, 44100, 48000]))
+        n_fft = int(rng.choice([64, 128, 200, 256, 384, 400, 480, 512, 640, 1000, 1024, 2048]))
+        L = int(rng.integers(max(8, n_fft // 4), n_fft + 1))
+        S = int(rng.integers(max(1, L // 5), L + 1))
+        nf = int(rng.integers(4, 81))
+        kw = dict(sample_rate=sr, fft_points=n_fft, frame_length=(L + 0.25) / sr, frame_stride=(S + 0.25) / sr,
+                  num_cepstral=int(rng.integers(1, min(nf, 24) + 1)), num_filters=nf, low_frequency=float(rng.choice([0.0, 0.0, 64.0, 133.33])),
+                  high_frequency=float(rng.choice([sr / 2, sr / 2, 0.9 * sr / 2, sr / 3])), dc_elimination=bool(rng.integers(0, 2)))
+        oc, cc = o.SpeechConfig(**kw), oracle_c.make_config(**kw)
+        n = L + S * int(rng.integers(1, 30)) + int(rng.integers(0, S))
+        x = o.synth_signal(2, n, 77 + i)
+        r = oracle_c.features(x, cc, mfe=True, energy=True, lmfe=True, mfcc=True, n_threads=2)
+        for c in range(2):
+            f, e = o.mfe(x[c], oc)
+            np.testing.assert_allclose(r["mfe"][c], f, rtol=1e-4, atol=2e-6 * f.max(), err_msg=str(kw))
+            np.testing.assert_allclose(r["energy"][c], e, rtol=1e-4, err_msg=str(kw))
+            loud = f > 1e-3 * f.max()          # entries at the f32 FFT's noise floor are compared as spectra only
+            np.testing.assert_allclose(r["lmfe"][c][loud], np.log(f)[loud], atol=1e-3, err_msg=str(kw))
+            rows = loud.all(axis=1)
+            np.testing.assert_allclose(r["mfcc"][c][rows], o.mfcc(x[c], oc)[rows], atol=1e-3 if kw["dc_elimination"] else 4e-3, err_msg=str(kw))
+    for i in range(60):
+        sr = int(rng.choice([8000, 16000, 22050, 44100]))
+        W = int(rng.choice([64, 128, 200, 256, 400, 480, 512, 1000, 1024, 2048]))
+        H = int(rng.integers(max(1, W // 16), W // 2 + 1))
+        nf = int(rng.integers(4, 129))
+        kw = dict(sample_rate=sr, fft_points=W, frame_length=(H + 0.5) / sr, frame_stride=0.01, num_cepstral=min(13, nf), num_filters=nf,
+                  low_frequency=float(rng.choice([0.0, 50.0])), high_frequency=float(rng.choice([sr / 2, 0.8 * sr / 2])))
+        ttd = int(rng.integers(1, 30)) * H + int(rng.integers(0, H)) + (W if rng.integers(0, 2) else 0)
+        y = o.synth_signal(int(rng.integers(1, 4)), ttd, 500 + i)
+        a = oracle_c.mel_spectrogram2(y, oracle_c.make_config(**kw), n_threads=2)
+        b = o.mel_spectrogram2(y, o.SpeechConfig(**kw))
+        assert a.shape == b.shape
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=2e-6 * max(float(b.max()), 1e-30), err_msg=str(kw))
