@@ -120,6 +120,34 @@ def test_librosa_mode_oracle_is_pinned_by_torchaudio():
     assert np.abs(db + 100.0).max() < 1e-4     # 10 log10(amin = 1e-10)
 
 
+def test_librosa_mode_oracle_against_torchaudio_on_random_parameter_sets():
+    """40 seeded random (sr, n_fft, hop, n_mels, fmin, fmax, length) as in the GPU sweep.  torchaudio builds its
+    Slaney bank in f32 (librosa and the oracle in f64), which shows as a few 1e-6 of the spectrogram's peak where
+    117 filters share 241 bins; hence the absolute floor of 1e-5 of the peak on top of rel 1e-4."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    rng = np.random.Generator(np.random.Philox(0x5EED0A40))
+    for i in range(40):
+        sr = int(rng.choice([8000, 16000, 22050, 44100]))
+        n_fft = int(rng.choice([128, 256, 400, 480, 512, 1000, 1024, 2048]))
+        hop = int(rng.integers(max(1, n_fft // 16), n_fft + 1))
+        n_mels = int(rng.integers(8, 129))
+        fmin = float(rng.choice([0.0, 0.0, 30.0, 125.5]))
+        fmax = [None, 0.45 * sr, 0.3 * sr][int(rng.integers(0, 3))]
+        n = n_fft // 2 + 1 + int(rng.integers(0, 40)) * hop + int(rng.integers(0, hop))
+        y = o.synth_signal(2, n, 900 + i)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")   # "some mel filterbanks are all zero": intended here
+            ms = torchaudio.transforms.MelSpectrogram(sample_rate=sr, n_fft=n_fft, hop_length=hop, f_min=fmin,
+                                                      f_max=sr / 2.0 if fmax is None else fmax, n_mels=n_mels, power=2.0,
+                                                      center=True, pad_mode="reflect", norm="slaney", mel_scale="slaney")
+            want = ms(torch.from_numpy(y)).numpy()
+        got = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, fmin, fmax)
+        assert got.shape == want.shape == (2, n_mels, 1 + n // hop)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * want.max(), err_msg=f"{sr} {n_fft} {hop} {n_mels} {fmin} {fmax} {n}")
+
+
 def test_filterbank_indices_and_peaks():
     want = [0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 18, 20, 22, 25, 27, 29, 32, 35, 38, 41, 44,
             48, 51, 55, 60, 64, 69, 74, 79, 85, 91, 98, 105, 112, 120, 129]
