@@ -182,3 +182,21 @@ def test_argument_errors_precede_device_checks():
     assert ei.value.code == _lib.SS_ERR_INVALID_ARG
     with pytest.raises(TypeError):
         sb.feature.mfcc(np.zeros(16000, np.float64), cfg)    # f32 only (README.md:17)
+
+
+def test_python_mirror_keeps_the_py_speechsauce_signatures():
+    """py-speechsauce/speechsauce/__init__.py:37-47, 85-95: `mfcc` and `mel_spectrogram` take (signal,
+    sampling_frequency, frame_length=0.020, frame_stride=0.01, num_cepstral=13, num_filters=40, fft_length=512,
+    low_frequency=0, high_frequency=None, dc_elimination=True); `cmvn` and `preemphasis` are re-exported from the
+    extension module (py-speechsauce/src/lib.rs:208-224)."""
+    import inspect
+    want = [("signal", inspect.Parameter.empty), ("sampling_frequency", inspect.Parameter.empty), ("frame_length", 0.020),
+            ("frame_stride", 0.01), ("num_cepstral", 13), ("num_filters", 40), ("fft_length", 512), ("low_frequency", 0),
+            ("high_frequency", None), ("dc_elimination", True)]
+    for fn in (sb.mfcc, sb.mel_spectrogram):
+        got = [(p.name, p.default) for p in inspect.signature(fn).parameters.values()]
+        assert got == want, fn.__name__
+    assert [p for p in inspect.signature(sb.cmvn).parameters][:2] == ["vec", "variance_normalization"]
+    assert [p for p in inspect.signature(sb.preemphasis).parameters][:3] == ["signal", "shift", "cof"]
+    assert inspect.signature(sb.preemphasis).parameters["cof"].default == 0.98      # processing.rs:31-35
+    assert set(sb.__all__) >= {"mfcc", "mel_spectrogram", "preemphasis", "cmvn"}
