@@ -7,21 +7,25 @@
 // FFT stage as in the second generation (ss_kernels_fast512b.cu): 16 lanes x 16 points per frame,
 // 256 = 16 x 16 four-step complex FFT in registers, mirror bin by warp shuffle, two frames per warp.
 // New here: everything after the magnitudes runs on the tensor cores with warp-level
-// mma.sync.m16n8k8 TF32, split 3-way (A_hi B_hi + A_lo B_hi + A_hi B_lo, ~2^-21 relative) so the
-// f32 tolerances hold:
-//   * a warp collects |X| of 8 consecutive frames (4 FFT pairs) in a private [8][136] tile and
-//     multiplies it by the banded filterbank, 8 bins x 8 filters per MMA, visiting only the blocks
-//     the band touches (28 of 85 for the 40-filter bank).  The profile of the second generation had
-//     the per-pair CUDA-core mel program at 23 % and the DCT at 11 % of all issued instructions;
-//   * the accumulator fragment of the mel product (frame g, filters 2t, 2t+1) *is* the A fragment of
-//     the DCT product once the contraction index is permuted (the DCT matrix fragments are
-//     permuted on the host instead), so ln -> DCT needs no data movement at all;
-//   * rows 8..15 of the MMA tile carry P[k] * R[k] when the spectral subband centroids are
-//     requested, so the SSC numerator costs no extra MMA;
-//   * the cepstra stay in the accumulator fragments through the c0 / scale step and the per-clip
-//     CMVN (column statistics reduced by shuffles, merged across warps with Chan's formula through
-//     96 floats of shared memory, one barrier per clip), so no [T][nc] stash exists any more.
-// Fragment tables are read through the L1 (one copy per SM, shared by the resident CTAs).
+// mma.sync.m16n8k8 TF32, split 3-way (hi x hi + lo x hi + hi x lo, ~2^-21 relative) so the f32
+// tolerances hold:
+//   * a warp collects |X| of 8 consecutive frames (4 FFT pairs) in a private [8][132] tile and
+//     multiplies it by the banded filterbank in n-tiles of 8 filters, visiting only the 8-bin k-steps
+//     the band touches (22 of 85 for the 40-filter bank).  The M rows of the MMA are the 8 frames split
+//     in place (rows 0..7 the TF32 high parts, rows 8..15 the remainders): two MMAs and one 16-byte
+//     weight load per k-step.  The profile of the second generation had the per-pair CUDA-core mel
+//     program at 23 % and the DCT at 11 % of all issued instructions;
+//   * the accumulator fragment of the mel product (frame g, filters 2t, 2t+1) *is* the B fragment of
+//     the transposed DCT product ceps^T = D x logmel^T once the contraction index is permuted (the
+//     DCT matrix fragments are permuted on the host instead), so ln -> DCT needs no data movement;
+//   * with the spectral subband centroids the same weights run against P[k] * R[k] (two more MMAs
+//     per k-step);
+//   * a clip's cepstra are normalised in place by the warp that wrote them (per-clip CMVN: column
+//     statistics over the L2-resident [T][nc] block, no block-wide barrier) when every resident warp
+//     has at least one clip.
+// The fragment tables (12 KB mel + 5 KB DCT for the 40-filter bank) and the twiddles sit in shared
+// memory once per SM (one TMA bulk copy per CTA); a warp's scratch is 8.9 KB (transpose tile 4.6 KB,
+// |X| tile 4.2 KB): 198 KB for the 20 warps of the one persistent CTA.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -42,7 +46,7 @@ using ssfft::sfor;
 #define SS_F512C_WARPS 20
 #endif
 // One persistent CTA per SM: the warps are independent after the table load, and a single CTA
-// needs only one shared-memory copy of the fragment tables (27 KB for the 40-filter bank).
+// needs only one shared-memory copy of the fragment tables (17 KB for the 40-filter bank).
 constexpr int kMaxWarps = SS_F512C_WARPS, kMaxThreads = kMaxWarps * 32;
 constexpr int kSmemBudget = 226 * 1024;       // of the 227 KB an sm_100 CTA may use
 constexpr int kXs = 18;                       // transpose row stride in float2 (144 B: conflict-free LDS.128)
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fast512c(const FastArgsC a) 
       __syncwarp();
 
       // ---- mel filterbank on the tensor cores (feature.rs:229-230):
-      //   mel [8 frames][8 filters of n-tile nt] = P [8][136 bins] x W^T (banded, pre-split on the host).
+      //   mel [8 frames][8 filters of n-tile nt] = P [8][132] x W^T (banded, pre-split on the host).
       // The M rows of the MMA are the tile's 8 frames split in place: rows 0..7 their TF32 high parts, rows
       // 8..15 the remainders, so A = [P_hi; P_lo] against W_hi yields hi x hi and lo x hi at once and a second
       // MMA against W_lo adds hi x lo: two MMAs per k-step (8 bins x 8 filters), one 16-byte load of weights.

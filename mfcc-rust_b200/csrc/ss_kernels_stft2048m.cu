@@ -7,7 +7,7 @@
 // points per lane, 1024 = 32 x 32 four-step FFT in registers (packed FFMA2 butterflies), mirror bin
 // by warp shuffle.  New here: the filterbank runs on the tensor cores.
 //   * The CTA's 16 warps form two independent groups of 8.  A group transforms 8 consecutive frames
-//     of one row per round; every warp writes the |X|^2 row of its frame into the group's [8][520]
+//     of one row per round; every warp writes the |X|^2 row of its frame into the group's [8][516]
 //     tile (double-buffered, so one named barrier of 256 threads per round is enough; the two groups
 //     drift apart in phase and hide each other's load and barrier latency).
 //   * The tile then feeds mel [8 frames][128 filters] = P [8][520 bins] x W^T on mma.sync.m16n8k8 TF32 split
