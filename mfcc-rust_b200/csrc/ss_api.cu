@@ -1147,6 +1147,7 @@ int ss_cmvnw_dev(void* stream, const float* d_in, int64_t n_mats, int64_t rows, 
 
 int ss_derivative_extraction(const float* in, int64_t rows, int64_t cols, int dw, float* out) {
   if (rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  if (dw < 1) return fail(SS_ERR_INVALID_ARG, "delta_windows must be >= 1 (zero scale in the reference, processing.rs:253)");
   return host_unary(in, (size_t)rows * cols, out, (size_t)rows * cols,
                     [&](cudaStream_t s, float* a, float* b) { return ss_derivative_extraction_dev(s, a, rows, cols, dw, b); });
 }
@@ -1157,6 +1158,7 @@ int ss_extract_derivative_feature(const float* in, int64_t rows, int64_t cols, f
 }
 int ss_cmvnw(const float* in, int64_t rows, int64_t cols, int64_t win, int varnorm, float* out) {
   if (rows < 0 || cols < 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
+  if (win < 1 || win % 2 != 1) return fail(SS_ERR_INVALID_ARG, "Windows size must be odd! (processing.rs:327)");
   return host_unary(in, (size_t)rows * cols, out, (size_t)rows * cols,
                     [&](cudaStream_t s, float* a, float* b) { return ss_cmvnw_dev(s, a, 1, rows, cols, win, varnorm, b); });
 }

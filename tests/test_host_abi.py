@@ -182,6 +182,14 @@ def test_argument_errors_precede_device_checks():
     assert ei.value.code == _lib.SS_ERR_INVALID_ARG
     with pytest.raises(TypeError):
         sb.feature.mfcc(np.zeros(16000, np.float64), cfg)    # f32 only (README.md:17)
+    v = np.zeros((10, 3), np.float32)
+    for fn in (lambda: sb.processing.cmvnw(v, 300, False),               # even window: processing.rs:327
+               lambda: sb.processing.derivative_extraction(v, 0),        # zero scale: processing.rs:253
+               lambda: sb.processing.power_spectrum(np.zeros((2, 400), np.float32), 256),
+               lambda: sb.preemphasis(np.zeros(5, np.float32), 0, 0.98)):
+        with pytest.raises(sb.SpeechsauceError) as ei:
+            fn()
+        assert ei.value.code == _lib.SS_ERR_INVALID_ARG
 
 
 def test_python_mirror_keeps_the_py_speechsauce_signatures():
