@@ -102,14 +102,29 @@ typedef struct {
 int ss_device_count(void);
 const char* ss_last_error(void);
 const char* ss_version(void);
-/* pinned host memory helpers for callers that want full PCIe rate */
+/* Host memory.  Every host entry point accepts pageable memory (what `ArrayView::as_ptr()` of an
+ * ordinary ndarray / numpy array is, py-speechsauce/src/lib.rs:167-204): chunks are staged through
+ * pinned rings by a small pool of copy threads (ss_copy_threads(), env SS_COPY_THREADS) while the
+ * neighbouring chunks are on the wire.  Pinned memory (ss_host_alloc, or a caller's own buffer
+ * registered once with ss_host_register) is DMA'd in place and skips that copy. */
 int ss_host_alloc(void** ptr, size_t bytes);
 int ss_host_free(void* ptr);
+int ss_host_register(void* ptr, size_t bytes); /* cudaHostRegister(portable): pin a caller-owned range */
+int ss_host_unregister(void* ptr);
+int ss_host_is_pinned(const void* ptr);        /* 1 when the library will DMA `ptr` in place */
+int ss_copy_threads(void);                     /* size of the staging copy pool */
+/* frees the per-(device, stream) scratch the config-less *_dev entry points keep between calls */
+int ss_release_scratch(void);
 
 /* ---- plan (replaces SpeechConfig's FFT plan / window / overlap memory, config.rs:99-185) */
 int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_plan** out);
 void ss_plan_destroy(ss_plan* plan);
 int ss_plan_get_info(const ss_plan* plan, ss_plan_info* info);
+/* Host-pipeline tuning (results never depend on it).  tile_frames: clips with more frames than this are
+ * processed in frame tiles with an L - S sample halo so that one long stream still overlaps its H2D,
+ * kernels and D2H (0 = automatic: only clips larger than 1.5 chunks).  chunk_bytes: input + output
+ * bytes per pipeline chunk (0 = keep; default 64 MiB). */
+int ss_plan_set_tuning(ss_plan* plan, int64_t tile_frames, int64_t chunk_bytes);
 /* STFT overlap memory held by the plan (config.rs:126,162): [W-H] floats.  The reference
  * never resets it (functions.rs:89-93); these two calls make the hidden state explicit. */
 int ss_plan_get_analysis_mem(const ss_plan* plan, float* out, int64_t n);

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <thread>
 
+#include "ss_host.h"
 #include "ss_internal.h"
 
 namespace ss {
@@ -45,50 +46,60 @@ static int cuda_fail(cudaError_t e, const char* what) {
 
 constexpr int kLanes = 3;  // H2D / compute / D2H of consecutive chunks overlap on 3 streams
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  int reserve(size_t bytes) {
-    if (bytes <= cap) return SS_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 8;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
-      e = cudaMalloc(&p, bytes);
-      want = bytes;
-    }
-    if (e != cudaSuccess) return fail(SS_ERR_ALLOC, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
-    cap = want;
-    return SS_OK;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
+static int reserve(DevBuf& b, size_t bytes) {
+  cudaError_t e = b.reserve_raw(bytes);
+  if (e != cudaSuccess) return fail(SS_ERR_ALLOC, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return SS_OK;
+}
+static int reserve(PinBuf& b, size_t bytes) {
+  cudaError_t e = b.reserve_raw(bytes);
+  if (e != cudaSuccess) return fail(SS_ERR_ALLOC, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return SS_OK;
+}
+
+constexpr int kMaxOuts = 5;
+struct HostOut {
+  float* host = nullptr;
+  size_t per_row = 0;  // floats per row; rows are dense in the caller's buffer
+};
+
+// what a lane still owes the caller: the rows [a, a + n) of every output sit in its pinned ring
+struct Pending {
+  bool valid = false;
+  int64_t a = 0, n = 0;
+  int n_outs = 0;
+  HostOut outs[kMaxOuts];
+  size_t off[kMaxOuts] = {0};
 };
 
 struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf in, out, scratch, mem;
+  PinBuf hin, hout, hmem;  // pinned rings for pageable caller memory (and the STFT halo)
+  Pending pending;
+  std::vector<CopyPool::TicketPtr> out_tickets;
 };
 
 struct DeviceCtx {
   int device = 0;
   int sm_count = 148;
-  DevBuf tables;  // one allocation holding every device table
+  bool ready = false;  // tables + streams are created on first use (a plan over 8 GPUs that only ever
+  std::mutex init_mu;  // sees single clips touches device 0 alone)
+  DevBuf tables;       // one allocation holding every device table
   DevTables tab;
-  Fast512bTables* fast512b = nullptr;
   Fast512cTables* fast512c = nullptr;
-  Stft400Tables* stft400 = nullptr;
   Stft400mTables* stft400m = nullptr;
   Stft2048Tables* stft2048 = nullptr;
   Stft2048mTables* stft2048m = nullptr;
   Lane lanes[kLanes];
-  DevBuf dev_scratch;  // scratch for the *_dev entry points (cmvn partials)
-  std::string err;     // worker-thread error message
+  int next_lane = 0;
+  DevBuf clip_mfcc;                       // un-normalised cepstra of a clip that is processed in frame tiles
+  cudaEvent_t lane_evt[kLanes] = {nullptr, nullptr, nullptr};
+  std::mutex scratch_mu;
+  std::map<void*, DevBuf> dev_scratch;    // cmvn partials of ss_features_dev, per caller stream
+  std::string err;                        // worker-thread error message
+  DeviceCtx() = default;
+  DeviceCtx(const DeviceCtx&) = delete;
 };
 
 }  // namespace ss
@@ -100,10 +111,11 @@ struct ss_plan {
   bool fft_ok = false;
   std::vector<float> window, dct;
   std::vector<float> analysis_mem;  // [W-H], config.rs:126,162
-  std::vector<ss::DeviceCtx> devs;
-  bool fast512b = false;
+  std::vector<std::unique_ptr<ss::DeviceCtx>> devs;
+  std::vector<std::unique_ptr<ss::DeviceWorker>> workers;  // one persistent thread per device (multi-device plans)
+  int64_t tile_frames = 0;        // 0: automatic (ss_plan_set_tuning)
+  size_t chunk_bytes = 64u << 20;  // H2D + D2H bytes per pipeline chunk
   bool fast512c = false;
-  bool stft400 = false;
   bool stft400m = false;
   bool stft2048 = false;
   bool stft2048m = false;
@@ -112,10 +124,9 @@ struct ss_plan {
 namespace ss {
 
 static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
-  SS_CUDA(cudaSetDevice(dc->device));
-  cudaDeviceProp prop;
-  SS_CUDA(cudaGetDeviceProperties(&prop, dc->device));
-  dc->sm_count = prop.multiProcessorCount;
+  int smc = 0;
+  SS_CUDA(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, dc->device));
+  dc->sm_count = smc;
   const Derived& d = pl->d;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_tw = 0;
@@ -126,7 +137,7 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   const size_t o_fw = align(o_fo + d.nf * sizeof(int));
   const size_t o_dct = align(o_fw + pl->mb.w.size() * sizeof(float));
   const size_t total = align(o_dct + std::max<size_t>(1, pl->dct.size()) * sizeof(float));
-  int rc = dc->tables.reserve(total);
+  int rc = reserve(dc->tables, total);
   if (rc) return rc;
   char* base = static_cast<char*>(dc->tables.p);
   if (pl->fft_ok)
@@ -148,17 +159,10 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   dc->tab.n_stages = pl->fft.n_stages;
   for (int i = 0; i < kMaxStages; ++i) dc->tab.radix[i] = pl->fft.radix[i];
   for (auto& ln : dc->lanes) SS_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-  if (pl->fast512b) {
-    int e = fast512b_build_tables(pl->d, pl->mb, &dc->fast512b);
-    if (e) return cuda_fail((cudaError_t)e, "fast512b_build_tables");
-  }
+  for (auto& ev : dc->lane_evt) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if (pl->fast512c) {
     int e = fast512c_build_tables(pl->d, pl->mb, &dc->fast512c);
     if (e) return cuda_fail((cudaError_t)e, "fast512c_build_tables");
-  }
-  if (pl->stft400) {
-    int e = stft400_build_tables(pl->d, pl->mb, pl->window, &dc->stft400);
-    if (e) return cuda_fail((cudaError_t)e, "stft400_build_tables");
   }
   if (pl->stft400m) {
     int e = stft400m_build_tables(pl->d, pl->mb, pl->window, &dc->stft400m);
@@ -175,9 +179,24 @@ static int upload_tables(ss_plan* pl, DeviceCtx* dc) {
   return SS_OK;
 }
 
+// Tables, streams and events of a device are created by the first call that runs on it.  The caller's
+// current device is `dc->device` (DeviceGuard or the device's worker thread).
+static int ensure_device(ss_plan* pl, DeviceCtx* dc) {
+  std::lock_guard<std::mutex> lk(dc->init_mu);
+  if (dc->ready) return SS_OK;
+  int rc = upload_tables(pl, dc);
+  if (rc) return rc;
+  dc->ready = true;
+  return SS_OK;
+}
+
 // ---- speechpy-framing features on one device, device pointers ---------------------------
+// `T_clip` / `first_tile`: when a long clip is processed in frame tiles the rows handed in are tiles of
+// one clip; the length-dependent DCT scale (feature.rs:126) uses the clip's frame count and only the
+// clip's very first frame is element [0,0] (feature.rs:128).  T_clip == 0: rows are whole clips.
 static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const float* d_pcm, int64_t n_clips,
-                        int64_t clip_len, int64_t row_stride, const ss_feature_outputs& o, DevBuf* scratch) {
+                        int64_t clip_len, int64_t row_stride, const ss_feature_outputs& o, DevBuf* scratch,
+                        int64_t T_clip = 0, bool first_tile = true) {
   const Derived& d = pl->d;
   const int64_t T = num_frames(clip_len, d.L, d.S, 0);
   FrameParams p;
@@ -196,8 +215,8 @@ static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const f
   p.mode = kModeSpeechpy;
   p.flags = d.cfg.flags;
   p.mag_scale = 1.0f / (float)d.W;  // processing.rs:180
-  const float n = (float)(T * (int64_t)d.nf);  // feature.rs:126
-  p.scale_00 = 1.0f / std::sqrt(4.0f * n);
+  const float n = (float)((T_clip > 0 ? T_clip : T) * (int64_t)d.nf);  // feature.rs:126
+  p.scale_00 = first_tile ? 1.0f / std::sqrt(4.0f * n) : 1.0f;           // D[1:,0] stays unscaled (feature.rs:128)
   p.scale_rest = 1.0f / std::sqrt(2.0f * n);
   p.dc_elim = d.cfg.dc_elimination ? 1 : 0;
   p.ssc_r0 = 1.0f;
@@ -211,13 +230,9 @@ static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const f
   p.tab = dc->tab;
   bool cmvn_done = false;
   int e;
-  const bool use_fast = (pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  // SS_FAST512_GEN=2 selects the previous generation of the n_fft = 512 kernel for A/B measurements
-  // (2: CUDA-core mel program + DCT, CTA per clip; default 3: tensor-core mel + DCT, warp per item)
-  static const int gen = getenv("SS_FAST512_GEN") ? atoi(getenv("SS_FAST512_GEN")) : 3;
+  const bool use_fast = pl->fast512c && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
   if (use_fast) {
-    if (pl->fast512c && (gen >= 3 || !pl->fast512b)) e = launch_fast512c(p, dc->fast512c, dc->sm_count, stream);
-    else e = launch_fast512b(p, dc->fast512b, dc->sm_count, stream);
+    e = launch_fast512c(p, dc->fast512c, dc->sm_count, stream);
     cmvn_done = true;  // the fast path normalises in-kernel or enqueues its own cmvn pass
     if (e == -1000) {  // the fast path declined this shape; fall through to the generic kernel
       cmvn_done = false;
@@ -231,7 +246,7 @@ static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const f
   }
   if (e) return cuda_fail((cudaError_t)e, "feature kernel launch");
   if (p.cmvn_mode && !cmvn_done) {
-    int rc = scratch->reserve(cmvn_scratch_bytes(n_clips, T, d.nc));
+    int rc = reserve(*scratch, cmvn_scratch_bytes(n_clips, T, d.nc));
     if (rc) return rc;
     e = launch_cmvn(o.mfcc, n_clips, T, d.nc, p.cmvn_mode == SS_CMVN_MEAN_VAR, o.mfcc,
                     static_cast<float*>(scratch->p), stream);
@@ -264,14 +279,8 @@ static void stft_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float*
 
 // mel_spectrogram / stft launch: a size-specialised kernel when one exists, else the generic one
 static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
-  // SS_STFT400_GEN=1 selects the first-generation fft_points = 400 kernel for A/B measurements
-  static const int gen400 = getenv("SS_STFT400_GEN") ? atoi(getenv("SS_STFT400_GEN")) : 2;
-  if (pl->stft400m && dc->stft400m && gen400 >= 2 && (p.mel_out || p.stft_out) && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+  if (pl->stft400m && dc->stft400m && (p.mel_out || p.stft_out) && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400m(p, dc->stft400m, dc->sm_count, stream);
-    if (e != -1000) return e;
-  }
-  if (pl->stft400 && dc->stft400 && p.mel_out && !p.stft_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
-    const int e = launch_stft400(p, dc->stft400, dc->sm_count, stream);
     if (e != -1000) return e;
   }
   // SS_STFT2048_GEN=1 selects the first-generation fft_points = 2048 mel kernel for A/B measurements
@@ -344,30 +353,211 @@ static void host_mem_before_row(const ss_plan* pl, const float* pcm, int64_t ttd
   }
 }
 
+static int copy_rows_h2d(float* dst, const float* src, int64_t rows, int64_t len, int64_t row_stride,
+                         cudaStream_t s);
+
+// Retire what a lane still owes the caller: wait for its stream, then move the rows parked in the pinned
+// ring to the caller's (pageable) arrays on the copy pool.  `async`: leave the copies in flight.
+static int lane_retire(Lane& ln, bool async) {
+  SS_CUDA(cudaStreamSynchronize(ln.stream));
+  if (ln.pending.valid) {
+    const Pending& pd = ln.pending;
+    for (int i = 0; i < pd.n_outs; ++i) {
+      if (!pd.outs[i].host) continue;
+      const size_t bytes = (size_t)pd.n * pd.outs[i].per_row * sizeof(float);
+      ln.out_tickets.push_back(CopyPool::instance().copy2d_async(pd.outs[i].host + (size_t)pd.a * pd.outs[i].per_row, bytes,
+                                                                static_cast<char*>(ln.hout.p) + pd.off[i], bytes, bytes, 1));
+    }
+    ln.pending.valid = false;
+  }
+  if (!async) {
+    for (auto& t : ln.out_tickets) CopyPool::instance().wait(t);
+    ln.out_tickets.clear();
+  }
+  return SS_OK;
+}
+static int drain_lanes(DeviceCtx* dc) {
+  int rc = SS_OK;
+  for (auto& ln : dc->lanes) {
+    int r = lane_retire(ln, false);
+    if (r && !rc) rc = r;
+  }
+  return rc;
+}
+// after an error: nothing may stay in flight towards caller memory
+static void abort_lanes(DeviceCtx* dc) {
+  for (auto& ln : dc->lanes) {
+    if (ln.stream) cudaStreamSynchronize(ln.stream);
+    for (auto& t : ln.out_tickets) CopyPool::instance().wait(t);
+    ln.out_tickets.clear();
+    ln.pending.valid = false;
+  }
+  cudaGetLastError();
+}
+
+// A batch of rows on the host: dense outputs, input rows `row_stride` floats apart (rows may overlap:
+// the frame tiles of one long clip are rows TtS apart and (Tt-1)S+L long).
+struct RowBatch {
+  const float* in = nullptr;
+  int64_t row_len = 0, row_stride = 0;
+  int n_outs = 0;
+  HostOut outs[kMaxOuts];
+  size_t chunk_bytes = 64u << 20;
+};
+// enqueue the kernels for rows [a, a + n) on ln.stream; d_in is [n][row_len] dense, d_outs[i] dense
+using LaunchFn = std::function<int(Lane& ln, int64_t a, int64_t n, const float* d_in, float* const* d_outs)>;
+
+// The chunked H2D -> kernels -> D2H pipeline over the device's three lanes.  Pinned caller memory is
+// DMA'd in place; pageable memory goes through the lanes' pinned rings, filled and emptied by the copy
+// pool while the neighbouring chunks are on the wire or in the kernels.
+static int pipeline_rows(DeviceCtx* dc, const RowBatch& b, int64_t c0, int64_t c1, const LaunchFn& fn, bool drain) {
+  if (c1 <= c0) return drain ? drain_lanes(dc) : SS_OK;
+  static const bool force_stage = getenv("SS_FORCE_STAGING") && atoi(getenv("SS_FORCE_STAGING"));
+  const bool in_pinned = !force_stage && host_ptr_is_pinned(b.in + c0 * b.row_stride);
+  bool out_pinned = !force_stage;
+  size_t per_out = 0;
+  for (int i = 0; i < b.n_outs; ++i) {
+    per_out += b.outs[i].per_row * sizeof(float);
+    if (b.outs[i].host && b.outs[i].per_row && !host_ptr_is_pinned(b.outs[i].host)) out_pinned = false;
+  }
+  const size_t per_in = (size_t)b.row_len * sizeof(float);
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(b.chunk_bytes / std::max<size_t>(1, per_in + per_out)));
+  chunk = std::min(chunk, c1 - c0);
+  CopyPool& pool = CopyPool::instance();
+  for (int64_t a = c0; a < c1; a += chunk) {
+    const int64_t n = std::min(chunk, c1 - a);
+    Lane& ln = dc->lanes[dc->next_lane];
+    dc->next_lane = (dc->next_lane + 1) % kLanes;
+    int r = lane_retire(ln, true);  // the lane's previous chunk: off the device, on its way to the caller
+    if (r) return r;
+    if ((r = reserve(ln.in, std::max<size_t>(16, n * per_in)))) return r;
+    size_t off[kMaxOuts], total_out = 0;
+    for (int i = 0; i < b.n_outs; ++i) {
+      off[i] = total_out;
+      if (b.outs[i].host) total_out += ((size_t)n * b.outs[i].per_row * sizeof(float) + 255) & ~(size_t)255;
+    }
+    if ((r = reserve(ln.out, std::max<size_t>(16, total_out + 5 * 256)))) return r;
+    const float* src = b.in + a * b.row_stride;
+    if (in_pinned) {
+      if ((r = copy_rows_h2d(static_cast<float*>(ln.in.p), src, n, b.row_len, b.row_stride, ln.stream))) return r;
+    } else {
+      if ((r = reserve(ln.hin, std::max<size_t>(16, n * per_in)))) return r;
+      pool.wait(pool.copy2d_async(ln.hin.p, per_in, src, (size_t)b.row_stride * sizeof(float), per_in, (size_t)n));
+      SS_CUDA(cudaMemcpyAsync(ln.in.p, ln.hin.p, n * per_in, cudaMemcpyHostToDevice, ln.stream));
+    }
+    float* d_outs[kMaxOuts];
+    for (int i = 0; i < b.n_outs; ++i)
+      d_outs[i] = b.outs[i].host ? reinterpret_cast<float*>(static_cast<char*>(ln.out.p) + off[i]) : nullptr;
+    if ((r = fn(ln, a, n, static_cast<const float*>(ln.in.p), d_outs))) return r;
+    for (auto& t : ln.out_tickets) pool.wait(t);  // the ring is about to be overwritten
+    ln.out_tickets.clear();
+    if (out_pinned) {
+      for (int i = 0; i < b.n_outs; ++i)
+        if (b.outs[i].host && b.outs[i].per_row)
+          SS_CUDA(cudaMemcpyAsync(b.outs[i].host + (size_t)a * b.outs[i].per_row, d_outs[i],
+                                  (size_t)n * b.outs[i].per_row * sizeof(float), cudaMemcpyDeviceToHost, ln.stream));
+    } else if (total_out) {
+      if ((r = reserve(ln.hout, total_out))) return r;
+      SS_CUDA(cudaMemcpyAsync(ln.hout.p, ln.out.p, total_out, cudaMemcpyDeviceToHost, ln.stream));
+      Pending& pd = ln.pending;
+      pd.valid = true;
+      pd.a = a;
+      pd.n = n;
+      pd.n_outs = b.n_outs;
+      for (int i = 0; i < b.n_outs; ++i) {
+        pd.outs[i] = b.outs[i];
+        pd.off[i] = off[i];
+      }
+    }
+  }
+  return drain ? drain_lanes(dc) : SS_OK;
+}
+
+// Shards [0, n_items) in contiguous blocks over the plan's devices and runs fn(dc, first, last) for each
+// block: on the calling thread (device guarded) when one device is enough, else on the devices'
+// persistent worker threads.  `bytes_hint` keeps small calls on the first device alone.
 template <class Fn>
-static int run_on_devices(ss_plan* pl, int64_t n_items, Fn fn) {
-  const int nd = (int)pl->devs.size();
-  if (nd == 0) return fail(SS_ERR_NO_DEVICE, "plan has no CUDA device (host-only plan); there is no CPU fallback");
+static int run_on_devices(ss_plan* pl, int64_t n_items, size_t bytes_hint, Fn fn) {
+  const int nd_all = (int)pl->devs.size();
+  if (nd_all == 0) return fail(SS_ERR_NO_DEVICE, "plan has no CUDA device (host-only plan); there is no CPU fallback");
+  const int nd = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)nd_all, n_items, (int64_t)(bytes_hint / (4u << 20)) + 1}));
+  auto body = [pl, &fn](DeviceCtx* dc, int64_t a, int64_t b) -> int {
+    int rc = ensure_device(pl, dc);
+    if (!rc) rc = fn(dc, a, b);
+    if (rc) {
+      dc->err = g_err;
+      abort_lanes(dc);
+    }
+    return rc;
+  };
   std::vector<int> rc(nd, 0);
   if (nd == 1) {
-    rc[0] = fn(&pl->devs[0], (int64_t)0, n_items);
-    if (rc[0]) pl->devs[0].err = g_err;
+    DeviceCtx* dc = pl->devs[0].get();
+    DeviceGuard guard(dc->device);
+    rc[0] = body(dc, 0, n_items);
   } else {
-    std::vector<std::thread> th;
+    if (pl->workers.empty())
+      for (auto& dc : pl->devs) pl->workers.emplace_back(new DeviceWorker(dc->device));
     for (int i = 0; i < nd; ++i) {
       const int64_t a = n_items * i / nd, b = n_items * (i + 1) / nd;
-      th.emplace_back([&, i, a, b] {
-        rc[i] = (b > a) ? fn(&pl->devs[i], a, b) : 0;
-        if (rc[i]) pl->devs[i].err = g_err;
-      });
+      DeviceCtx* dc = pl->devs[i].get();
+      pl->workers[i]->post([&body, dc, a, b] { return b > a ? body(dc, a, b) : 0; });
     }
-    for (auto& t : th) t.join();
+    for (int i = 0; i < nd; ++i) rc[i] = pl->workers[i]->wait();
   }
   for (int i = 0; i < nd; ++i)
     if (rc[i]) {
-      g_err = "device " + std::to_string(pl->devs[i].device) + ": " + pl->devs[i].err;
+      g_err = "device " + std::to_string(pl->devs[i]->device) + ": " + pl->devs[i]->err;
       return rc[i];
     }
+  return SS_OK;
+}
+
+// scratch of ss_features_dev's standalone cmvn, one buffer per caller stream
+static DevBuf* plan_stream_scratch(DeviceCtx* dc, void* stream) {
+  std::lock_guard<std::mutex> lk(dc->scratch_mu);
+  return &dc->dev_scratch[stream];
+}
+
+// ---- default context for the config-less processing functions: per (thread, device) -------------
+struct DefaultCtx {
+  cudaStream_t stream = nullptr;
+  DevBuf a, b, c;
+  int device = -1;
+};
+struct DefaultCtxSet {
+  std::map<int, DefaultCtx> by_dev;
+  ~DefaultCtxSet() {  // thread exit: give the device memory back (the runtime may already be gone at process exit)
+    for (auto& kv : by_dev) {
+      DeviceGuard g(kv.first);
+      if (kv.second.stream && cudaStreamQuery(kv.second.stream) != cudaErrorCudartUnloading) {
+        cudaStreamSynchronize(kv.second.stream);
+        kv.second.a.release();
+        kv.second.b.release();
+        kv.second.c.release();
+        cudaStreamDestroy(kv.second.stream);
+      }
+    }
+    cudaGetLastError();
+  }
+};
+static thread_local DefaultCtxSet g_ctx;
+static int default_ctx(DefaultCtx** out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(SS_ERR_NO_DEVICE, "no CUDA device visible (%s); there is no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  int dev = 0;
+  SS_CUDA(cudaGetDevice(&dev));
+  DefaultCtx& c = g_ctx.by_dev[dev];
+  if (!c.stream) {
+    SS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.device = dev;
+  }
+  *out = &c;
   return SS_OK;
 }
 
@@ -383,32 +573,6 @@ static int copy_rows_h2d(float* dst, const float* src, int64_t rows, int64_t len
   return SS_OK;
 }
 
-static int sync_lanes(DeviceCtx* dc) {
-  for (auto& ln : dc->lanes) SS_CUDA(cudaStreamSynchronize(ln.stream));
-  return SS_OK;
-}
-
-// ---- default context for the config-less processing functions ---------------------------
-struct DefaultCtx {
-  cudaStream_t stream = nullptr;
-  DevBuf a, b, c;
-  bool ready = false;
-};
-static thread_local DefaultCtx g_ctx;
-static int default_ctx(DefaultCtx** out) {
-  if (!g_ctx.ready) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0)
-      return fail(SS_ERR_NO_DEVICE, "no CUDA device visible (%s); there is no CPU fallback",
-                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    SS_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    g_ctx.ready = true;
-  }
-  *out = &g_ctx;
-  return SS_OK;
-}
-
 // host buffers -> device -> fn -> host buffers on the default context
 template <class Fn>
 static int host_unary(const float* in, size_t in_floats, float* out, size_t out_floats, Fn fn) {
@@ -416,8 +580,8 @@ static int host_unary(const float* in, size_t in_floats, float* out, size_t out_
   DefaultCtx* c;
   int rc = default_ctx(&c);
   if (rc) return rc;
-  if ((rc = c->a.reserve(std::max<size_t>(16, in_floats * 4)))) return rc;
-  if ((rc = c->b.reserve(std::max<size_t>(16, out_floats * 4)))) return rc;
+  if ((rc = reserve(c->a, std::max<size_t>(16, in_floats * 4)))) return rc;
+  if ((rc = reserve(c->b, std::max<size_t>(16, out_floats * 4)))) return rc;
   if (in_floats) SS_CUDA(cudaMemcpyAsync(c->a.p, in, in_floats * 4, cudaMemcpyHostToDevice, c->stream));
   if ((rc = fn(c->stream, static_cast<float*>(c->a.p), static_cast<float*>(c->b.p)))) return rc;
   if (out_floats) SS_CUDA(cudaMemcpyAsync(out, c->b.p, out_floats * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -457,6 +621,23 @@ int ss_host_free(void* ptr) {
   SS_CUDA(cudaFreeHost(ptr));
   return SS_OK;
 }
+int ss_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(SS_ERR_INVALID_ARG, "null / empty range");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");
+  return SS_OK;
+}
+int ss_host_unregister(void* ptr) {
+  if (!ptr) return SS_OK;
+  SS_CUDA(cudaHostUnregister(ptr));
+  return SS_OK;
+}
+int ss_host_is_pinned(const void* ptr) { return ptr && host_ptr_is_pinned(ptr) ? 1 : 0; }
+int ss_copy_threads(void) { return CopyPool::instance().threads(); }
+int ss_release_scratch(void) {
+  ScratchRegistry::instance().clear();
+  return SS_OK;
+}
 
 int64_t ss_num_frames(int64_t n, int64_t frame_len, int64_t frame_step, int zero_padding) {
   return num_frames(n, frame_len, frame_step, zero_padding);
@@ -474,9 +655,7 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
   build_dct(pl->d, &pl->dct);
   pl->fft_ok = pl->d.W <= (1 << 20) && build_fft_plan((int)pl->d.W, &pl->fft);
   if (pl->d.stft_ok) pl->analysis_mem.assign((size_t)(pl->d.W - pl->d.H), 0.f);  // config.rs:162
-  pl->fast512b = pl->fft_ok && fast512b_supported(pl->d, pl->mb);
   pl->fast512c = pl->fft_ok && fast512c_supported(pl->d, pl->mb);
-  pl->stft400 = pl->fft_ok && stft400_supported(pl->d, pl->mb);
   pl->stft400m = pl->fft_ok && stft400m_supported(pl->d, pl->mb);
   pl->stft2048 = pl->fft_ok && stft2048_supported(pl->d, pl->mb);
   pl->stft2048m = pl->fft_ok && stft2048m_supported(pl->d, pl->mb);
@@ -494,48 +673,47 @@ int ss_plan_create(const ss_config* cfg, const int* devices, int n_devices, ss_p
     for (int dv : devs)
       if (dv < 0 || dv >= n) return fail(SS_ERR_INVALID_ARG, "device %d out of range (0..%d)", dv, n - 1);
   }
-  pl->devs.resize(devs.size());
-  int prev = -1;
-  if (!devs.empty()) cudaGetDevice(&prev);
-  for (size_t i = 0; i < devs.size(); ++i) {
-    pl->devs[i].device = devs[i];
-    int rc = upload_tables(pl.get(), &pl->devs[i]);
-    if (rc) {
-      ss_plan_destroy(pl.release());
-      return rc;
-    }
+  // device state (tables, streams, pinned rings, worker threads) is created by the first call that
+  // runs on a device: creating a plan over all GPUs costs nothing on the ones a caller never reaches
+  for (int dv : devs) {
+    pl->devs.emplace_back(new DeviceCtx());
+    pl->devs.back()->device = dv;
   }
-  if (prev >= 0) cudaSetDevice(prev);
   *out = pl.release();
   return SS_OK;
 }
 
 void ss_plan_destroy(ss_plan* pl) {
   if (!pl) return;
-  int prev = -1;
-  if (!pl->devs.empty()) cudaGetDevice(&prev);
-  for (auto& dc : pl->devs) {
-    cudaSetDevice(dc.device);
+  pl->workers.clear();  // joins the worker threads
+  for (auto& dcp : pl->devs) {
+    DeviceCtx& dc = *dcp;
+    if (!dc.ready) continue;
+    DeviceGuard guard(dc.device);
     for (auto& ln : dc.lanes) {
       if (ln.stream) {
         cudaStreamSynchronize(ln.stream);
         cudaStreamDestroy(ln.stream);
       }
+      for (auto& t : ln.out_tickets) CopyPool::instance().wait(t);
       ln.in.release();
       ln.out.release();
       ln.scratch.release();
       ln.mem.release();
+      ln.hin.release();
+      ln.hout.release();
+      ln.hmem.release();
     }
+    for (auto& ev : dc.lane_evt)
+      if (ev) cudaEventDestroy(ev);
     dc.tables.release();
-    dc.dev_scratch.release();
-    if (dc.fast512b) fast512b_free_tables(dc.fast512b);
+    dc.clip_mfcc.release();
+    for (auto& kv : dc.dev_scratch) kv.second.release();
     if (dc.fast512c) fast512c_free_tables(dc.fast512c);
-    if (dc.stft400) stft400_free_tables(dc.stft400);
     if (dc.stft400m) stft400m_free_tables(dc.stft400m);
     if (dc.stft2048) stft2048_free_tables(dc.stft2048);
     if (dc.stft2048m) stft2048m_free_tables(dc.stft2048m);
   }
-  if (prev >= 0) cudaSetDevice(prev);
   delete pl;
 }
 
@@ -552,8 +730,16 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->num_cepstral = d.nc;
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
-  info->fast_path = (pl->fast512b || pl->fast512c) && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  info->fast_stft = (pl->stft400 || pl->stft400m || pl->stft2048 || pl->stft2048m) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
+  info->fast_path = pl->fast512c && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
+  info->fast_stft = (pl->stft400m || pl->stft2048 || pl->stft2048m) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
+  return SS_OK;
+}
+
+int ss_plan_set_tuning(ss_plan* pl, int64_t tile_frames, int64_t chunk_bytes) {
+  if (!pl) return fail(SS_ERR_INVALID_ARG, "null plan");
+  if (tile_frames < 0 || chunk_bytes < 0) return fail(SS_ERR_INVALID_ARG, "negative tuning value");
+  pl->tile_frames = tile_frames;
+  if (chunk_bytes > 0) pl->chunk_bytes = (size_t)chunk_bytes;
   return SS_OK;
 }
 
@@ -599,53 +785,104 @@ int ss_features(ss_plan* pl, const float* pcm, int64_t n_clips, int64_t clip_len
   if (n_clips == 0) return SS_OK;
   const Derived& d = pl->d;
   const ss_feature_outputs o = *outs;
-  const size_t per_clip_out =
-      (size_t)T * ((o.mfe ? d.nf : 0) + (o.energy ? 1 : 0) + (o.lmfe ? d.nf : 0) + (o.ssc ? d.nf : 0) + (o.mfcc ? d.nc : 0)) *
-      sizeof(float);
+  if (o.mfcc && (o.mfcc_cmvn_mode < 0 || o.mfcc_cmvn_mode > 2)) return fail(SS_ERR_INVALID_ARG, "cmvn_mode must be 0, 1 or 2");
+  const size_t per_frame_out =
+      ((o.mfe ? d.nf : 0) + (o.energy ? 1 : 0) + (o.lmfe ? d.nf : 0) + (o.ssc ? d.nf : 0) + (o.mfcc ? d.nc : 0)) * sizeof(float);
+  const size_t per_clip_out = (size_t)T * per_frame_out;
   const size_t per_clip_in = (size_t)clip_len * sizeof(float);
-  return run_on_devices(pl, n_clips, [&](DeviceCtx* dc, int64_t c0, int64_t c1) -> int {
-    SS_CUDA(cudaSetDevice(dc->device));
-    // chunk so that H2D, kernels and D2H of neighbouring chunks overlap; whole clips only
-    int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / std::max<size_t>(1, per_clip_in + per_clip_out)));
-    chunk = std::min(chunk, c1 - c0);
-    int li = 0;
-    for (int64_t a = c0; a < c1; a += chunk, li = (li + 1) % kLanes) {
-      const int64_t n = std::min(chunk, c1 - a);
-      Lane& ln = dc->lanes[li];
-      int r = ln.in.reserve(n * per_clip_in);
-      if (r) return r;
-      r = ln.out.reserve(std::max<size_t>(16, n * per_clip_out + 5 * 256));
-      if (r) return r;
-      r = copy_rows_h2d(static_cast<float*>(ln.in.p), pcm + a * row_stride, n, clip_len, row_stride, ln.stream);
-      if (r) return r;
-      ss_feature_outputs dv = o;
-      char* ob = static_cast<char*>(ln.out.p);
-      auto carve = [&](float* host, size_t elems) -> float* {
-        if (!host) return nullptr;
-        float* p = reinterpret_cast<float*>(ob);
-        ob += (elems * sizeof(float) + 255) & ~(size_t)255;
-        return p;
-      };
-      dv.mfe = carve(o.mfe, (size_t)n * T * d.nf);
-      dv.energy = carve(o.energy, (size_t)n * T);
-      dv.lmfe = carve(o.lmfe, (size_t)n * T * d.nf);
-      dv.ssc = carve(o.ssc, (size_t)n * T * d.nf);
-      dv.mfcc = carve(o.mfcc, (size_t)n * T * d.nc);
-      r = features_dev(pl, dc, ln.stream, static_cast<float*>(ln.in.p), n, clip_len, clip_len, dv, &ln.scratch);
-      if (r) return r;
-      auto back = [&](float* host, float* dev, size_t per_clip) -> int {
-        if (!host) return SS_OK;
-        SS_CUDA(cudaMemcpyAsync(host + (size_t)a * per_clip, dev, (size_t)n * per_clip * sizeof(float),
-                                cudaMemcpyDeviceToHost, ln.stream));
-        return SS_OK;
-      };
-      if ((r = back(o.mfe, dv.mfe, (size_t)T * d.nf))) return r;
-      if ((r = back(o.energy, dv.energy, (size_t)T))) return r;
-      if ((r = back(o.lmfe, dv.lmfe, (size_t)T * d.nf))) return r;
-      if ((r = back(o.ssc, dv.ssc, (size_t)T * d.nf))) return r;
-      if ((r = back(o.mfcc, dv.mfcc, (size_t)T * d.nc))) return r;
+  const size_t kChunk = pl->chunk_bytes;
+  // a clip larger than a chunk (long-form streams: 230 MB in, 135 MB out per hour) is cut into frame
+  // tiles with an L - S halo so that its own H2D, kernels and D2H overlap (long-context row)
+  const int64_t tile_env = pl->tile_frames;
+  const bool tiled = tile_env > 0 ? T > tile_env : per_clip_in + per_clip_out > kChunk + kChunk / 2;
+  return run_on_devices(pl, n_clips, (size_t)n_clips * (per_clip_in + per_clip_out), [&](DeviceCtx* dc, int64_t c0, int64_t c1) -> int {
+    if (!tiled) {
+      RowBatch b;
+      b.in = pcm;
+      b.row_len = clip_len;
+      b.row_stride = row_stride;
+      b.chunk_bytes = kChunk;
+      b.n_outs = 5;
+      b.outs[0] = {o.mfe, (size_t)T * d.nf};
+      b.outs[1] = {o.energy, (size_t)T};
+      b.outs[2] = {o.lmfe, (size_t)T * d.nf};
+      b.outs[3] = {o.ssc, (size_t)T * d.nf};
+      b.outs[4] = {o.mfcc, (size_t)T * d.nc};
+      return pipeline_rows(dc, b, c0, c1, [&](Lane& ln, int64_t, int64_t n, const float* d_in, float* const* dv) -> int {
+        ss_feature_outputs dvo = o;
+        dvo.mfe = dv[0];
+        dvo.energy = dv[1];
+        dvo.lmfe = dv[2];
+        dvo.ssc = dv[3];
+        dvo.mfcc = dv[4];
+        return features_dev(pl, dc, ln.stream, d_in, n, clip_len, clip_len, dvo, &ln.scratch);
+      }, true);
     }
-    return sync_lanes(dc);
+    // ---- frame tiles: tile j of a clip = frames [j Tt, (j+1) Tt) = samples [j Tt S, j Tt S + (Tt-1) S + L)
+    const int64_t Tt = tile_env > 0 ? tile_env : std::max<int64_t>(64, (int64_t)(kChunk / (d.S * sizeof(float) + per_frame_out)));
+    const bool cmvn = o.mfcc && o.mfcc_cmvn_mode != SS_CMVN_NONE;
+    for (int64_t c = c0; c < c1; ++c) {
+      const float* clip = pcm + c * row_stride;
+      if (cmvn) {
+        // the statistics span the whole clip: tiles park their cepstra on the device, one cmvn pass at the end
+        int r = reserve(dc->clip_mfcc, (size_t)T * d.nc * sizeof(float));
+        if (r) return r;
+        for (auto& ln : dc->lanes) SS_CUDA(cudaStreamSynchronize(ln.stream));  // previous clip's D2H of clip_mfcc
+      }
+      const int64_t n_full = T / Tt, rem = T - n_full * Tt;
+      for (int pass = 0; pass < 2; ++pass) {  // the full tiles, then the shorter last one
+        const int64_t frames = pass == 0 ? Tt : rem, j_base = pass == 0 ? 0 : n_full, n_tiles = pass == 0 ? n_full : 1;
+        if (frames == 0 || n_tiles == 0) continue;
+        const size_t f0 = (size_t)c * T + (size_t)j_base * Tt;  // first frame of the batch in the caller's arrays
+        RowBatch b;
+        b.in = clip + j_base * Tt * d.S;
+        b.row_len = (frames - 1) * d.S + d.L;
+        b.row_stride = Tt * d.S;
+        b.chunk_bytes = 1;  // one tile per chunk
+        b.n_outs = 5;
+        auto at = [&](float* host, size_t per_frame) -> HostOut {
+          HostOut h;
+          if (host) {
+            h.host = host + f0 * per_frame;
+            h.per_row = (size_t)frames * per_frame;
+          }
+          return h;
+        };
+        b.outs[0] = at(o.mfe, d.nf);
+        b.outs[1] = at(o.energy, 1);
+        b.outs[2] = at(o.lmfe, d.nf);
+        b.outs[3] = at(o.ssc, d.nf);
+        b.outs[4] = cmvn ? HostOut() : at(o.mfcc, d.nc);
+        const int64_t tile_len = b.row_len;
+        int r = pipeline_rows(dc, b, 0, n_tiles, [&](Lane& ln, int64_t j, int64_t, const float* d_in, float* const* dv) -> int {
+          ss_feature_outputs dvo = o;
+          dvo.mfe = dv[0];
+          dvo.energy = dv[1];
+          dvo.lmfe = dv[2];
+          dvo.ssc = dv[3];
+          dvo.mfcc = cmvn ? static_cast<float*>(dc->clip_mfcc.p) + (size_t)(j_base + j) * Tt * d.nc : dv[4];
+          dvo.mfcc_cmvn_mode = SS_CMVN_NONE;
+          return features_dev(pl, dc, ln.stream, d_in, 1, tile_len, tile_len, dvo, &ln.scratch, T, j_base + j == 0);
+        }, false);
+        if (r) return r;
+      }
+      if (cmvn) {
+        // every lane holds tiles of this clip: join them on lane 0, normalise, hand the block back
+        Lane& l0 = dc->lanes[0];
+        for (int i = 1; i < kLanes; ++i) {
+          SS_CUDA(cudaEventRecord(dc->lane_evt[i], dc->lanes[i].stream));
+          SS_CUDA(cudaStreamWaitEvent(l0.stream, dc->lane_evt[i], 0));
+        }
+        int r = reserve(l0.scratch, cmvn_scratch_bytes(1, T, d.nc));
+        if (r) return r;
+        float* m = static_cast<float*>(dc->clip_mfcc.p);
+        int e = launch_cmvn(m, 1, T, d.nc, o.mfcc_cmvn_mode == SS_CMVN_MEAN_VAR, m, static_cast<float*>(l0.scratch.p), l0.stream);
+        if (e) return cuda_fail((cudaError_t)e, "cmvn kernel launch");
+        // cudaMemcpyAsync stages pageable destinations itself (18.7 MB per hour of audio: not worth a ring)
+        SS_CUDA(cudaMemcpyAsync(o.mfcc + (size_t)c * T * d.nc, m, (size_t)T * d.nc * sizeof(float), cudaMemcpyDeviceToHost, l0.stream));
+      }
+    }
+    return drain_lanes(dc);
   });
 }
 
@@ -682,8 +919,11 @@ int ss_features_dev(ss_plan* pl, int dev_index, void* stream, const float* d_pcm
   int rc = check_speechpy(pl, clip_len, row_stride, &T);
   if (rc) return rc;
   if (n_clips <= 0) return n_clips == 0 ? SS_OK : fail(SS_ERR_INVALID_ARG, "n_clips < 0");
-  DeviceCtx* dc = &pl->devs[dev_index];
-  return features_dev(pl, dc, (cudaStream_t)stream, d_pcm, n_clips, clip_len, row_stride, *d_outs, &dc->dev_scratch);
+  DeviceCtx* dc = pl->devs[dev_index].get();
+  DeviceGuard guard(dc->device);
+  if ((rc = ensure_device(pl, dc))) return rc;
+  return features_dev(pl, dc, (cudaStream_t)stream, d_pcm, n_clips, clip_len, row_stride, *d_outs,
+                      plan_stream_scratch(dc, stream));
 }
 
 // ------------------------------------------------------------------------------ STFT (host)
@@ -700,39 +940,34 @@ static int stft_host(ss_plan* pl, const float* pcm, int64_t ch, int64_t ttd, int
   if (ch > 0 && Tp > 0) {
     const size_t per_row_in = (size_t)ttd * sizeof(float);
     const size_t per_row_out = (size_t)Tp * (out_ri ? (size_t)d.F * 2 : (size_t)d.nf) * sizeof(float);
-    rc = run_on_devices(pl, ch, [&](DeviceCtx* dc, int64_t c0, int64_t c1) -> int {
-      SS_CUDA(cudaSetDevice(dc->device));
-      int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / std::max<size_t>(1, per_row_in + per_row_out)));
-      chunk = std::min(chunk, c1 - c0);
-      int li = 0;
-      std::vector<float> hmem(memlen * kLanes);
-      for (int64_t a = c0; a < c1; a += chunk, li = (li + 1) % kLanes) {
-        const int64_t n = std::min(chunk, c1 - a);
-        Lane& ln = dc->lanes[li];
-        int r = ln.in.reserve(std::max<size_t>(16, n * per_row_in));
+    rc = run_on_devices(pl, ch, (size_t)ch * (per_row_in + per_row_out), [&](DeviceCtx* dc, int64_t c0, int64_t c1) -> int {
+      RowBatch b;
+      b.in = pcm;
+      b.row_len = ttd;
+      b.row_stride = row_stride;
+      b.chunk_bytes = pl->chunk_bytes;
+      b.n_outs = 1;
+      b.outs[0] = {out_ri ? out_ri : out_mel, per_row_out / sizeof(float)};
+      return pipeline_rows(dc, b, c0, c1, [&](Lane& ln, int64_t a, int64_t n, const float* d_in, float* const* dv) -> int {
+        int r = reserve(ln.mem, std::max<size_t>(16, memlen * sizeof(float)));
         if (r) return r;
-        if ((r = ln.out.reserve(n * per_row_out))) return r;
-        if ((r = ln.mem.reserve(std::max<size_t>(16, memlen * sizeof(float))))) return r;
+        if ((r = reserve(ln.hmem, std::max<size_t>(16, memlen * sizeof(float))))) return r;
         // the chunk's first row continues the stream of the row before it (Q13): restate the
-        // overlap memory on the host from the input itself -- no device collective needed
-        SS_CUDA(cudaStreamSynchronize(ln.stream));  // hmem slot reuse
-        float* hm = hmem.data() + (size_t)li * memlen;
+        // overlap memory on the host from the input itself -- no device collective needed.
+        // (the lane was retired before this chunk started, so its halo slot is free)
+        float* hm = static_cast<float*>(ln.hmem.p);
         host_mem_before_row(pl, pcm, ttd, row_stride, a, mem0.data(), hm);
         SS_CUDA(cudaMemcpyAsync(ln.mem.p, hm, memlen * sizeof(float), cudaMemcpyHostToDevice, ln.stream));
-        if ((r = copy_rows_h2d(static_cast<float*>(ln.in.p), pcm + a * row_stride, n, ttd, row_stride, ln.stream)))
-          return r;
         FrameParams p;
-        stft_params(pl, dc, &p, static_cast<float*>(ln.in.p), n, ttd, ttd);
+        stft_params(pl, dc, &p, d_in, n, ttd, ttd);
         p.mem_in = static_cast<float*>(ln.mem.p);
         p.log_mode = log_mode;
-        if (out_ri) p.stft_out = static_cast<float2*>(ln.out.p);
-        else p.mel_out = static_cast<float*>(ln.out.p);
+        if (out_ri) p.stft_out = reinterpret_cast<float2*>(dv[0]);
+        else p.mel_out = dv[0];
         int e = launch_stft_any(pl, dc, p, ln.stream);
         if (e) return cuda_fail((cudaError_t)e, "stft kernel launch");
-        float* host_out = out_ri ? out_ri + (size_t)a * Tp * d.F * 2 : out_mel + (size_t)a * d.nf * Tp;
-        SS_CUDA(cudaMemcpyAsync(host_out, ln.out.p, n * per_row_out, cudaMemcpyDeviceToHost, ln.stream));
-      }
-      return sync_lanes(dc);
+        return SS_OK;
+      }, true);
     });
     if (rc) return rc;
   }
@@ -765,15 +1000,19 @@ static int stft_dev(ss_plan* pl, int dev_index, void* stream, const float* d_pcm
   int rc = check_stft(pl, ch, ttd, row_stride);
   if (rc) return rc;
   if (d_mem_in && d_mem_in == d_mem_out) return fail(SS_ERR_INVALID_ARG, "d_mem_in and d_mem_out must not alias");
+  if (!d_pcm && ch * ttd > 0) return fail(SS_ERR_INVALID_ARG, "null pcm");
+  DeviceCtx* dc = pl->devs[dev_index].get();
+  DeviceGuard guard(dc->device);
+  if ((rc = ensure_device(pl, dc))) return rc;
   FrameParams p;
-  stft_params(pl, &pl->devs[dev_index], &p, d_pcm, ch, ttd, row_stride);
+  stft_params(pl, dc, &p, d_pcm, ch, ttd, row_stride);
   p.mem_in = d_mem_in;
   p.mem_out = d_mem_out;
   p.log_mode = log_mode;
   p.stft_out = reinterpret_cast<float2*>(d_out_ri);
   p.mel_out = d_out_mel;
   if (ch > 0 && p.Tp > 0) {
-    int e = launch_stft_any(pl, &pl->devs[dev_index], p, stream);
+    int e = launch_stft_any(pl, dc, p, stream);
     if (e) return cuda_fail((cudaError_t)e, "stft kernel launch");
   }
   int e = launch_stft_mem_update(p, stream);
@@ -850,9 +1089,13 @@ int ss_librosa_melspectrogram_dev(ss_plan* pl, int dev_index, void* stream, cons
   if (dev_index < 0 || dev_index >= (int)pl->devs.size())
     return fail(pl->devs.empty() ? SS_ERR_NO_DEVICE : SS_ERR_INVALID_ARG, "dev_index %d out of range", dev_index);
   if (ch == 0) return SS_OK;
+  if (!d_pcm) return fail(SS_ERR_INVALID_ARG, "null pcm");
+  DeviceCtx* dc = pl->devs[dev_index].get();
+  DeviceGuard guard(dc->device);
+  if ((rc = ensure_device(pl, dc))) return rc;
   FrameParams p;
-  librosa_params(pl, &pl->devs[dev_index], &p, d_pcm, ch, ttd, row_stride, d_out, db_mode);
-  int e = launch_librosa_any(pl, &pl->devs[dev_index], p, stream);
+  librosa_params(pl, dc, &p, d_pcm, ch, ttd, row_stride, d_out, db_mode);
+  int e = launch_librosa_any(pl, dc, p, stream);
   if (e) return cuda_fail((cudaError_t)e, "librosa mel kernel launch");
   return SS_OK;
 }
@@ -867,25 +1110,21 @@ int ss_librosa_melspectrogram(ss_plan* pl, const float* pcm, int64_t ch, int64_t
   const Derived& d = pl->d;
   const int64_t Tp = 1 + ttd / d.H;
   const size_t per_row_in = (size_t)ttd * sizeof(float), per_row_out = (size_t)Tp * d.nf * sizeof(float);
-  return run_on_devices(pl, ch, [&](DeviceCtx* dc, int64_t c0, int64_t c1) -> int {
-    SS_CUDA(cudaSetDevice(dc->device));
-    int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / std::max<size_t>(1, per_row_in + per_row_out)));
-    chunk = std::min(chunk, c1 - c0);
-    int li = 0;
-    for (int64_t a = c0; a < c1; a += chunk, li = (li + 1) % kLanes) {
-      const int64_t n = std::min(chunk, c1 - a);
-      Lane& ln = dc->lanes[li];
-      int r = ln.in.reserve(std::max<size_t>(16, n * per_row_in));
-      if (r) return r;
-      if ((r = ln.out.reserve(n * per_row_out))) return r;
-      if ((r = copy_rows_h2d(static_cast<float*>(ln.in.p), pcm + a * row_stride, n, ttd, row_stride, ln.stream))) return r;
+  return run_on_devices(pl, ch, (size_t)ch * (per_row_in + per_row_out), [&](DeviceCtx* dc, int64_t c0, int64_t c1) -> int {
+    RowBatch b;
+    b.in = pcm;
+    b.row_len = ttd;
+    b.row_stride = row_stride;
+    b.chunk_bytes = pl->chunk_bytes;
+    b.n_outs = 1;
+    b.outs[0] = {out, per_row_out / sizeof(float)};
+    return pipeline_rows(dc, b, c0, c1, [&](Lane& ln, int64_t, int64_t n, const float* d_in, float* const* dv) -> int {
       FrameParams p;
-      librosa_params(pl, dc, &p, static_cast<float*>(ln.in.p), n, ttd, ttd, static_cast<float*>(ln.out.p), db_mode);
+      librosa_params(pl, dc, &p, d_in, n, ttd, ttd, dv[0], db_mode);
       int e = launch_librosa_any(pl, dc, p, ln.stream);
       if (e) return cuda_fail((cudaError_t)e, "librosa mel kernel launch");
-      SS_CUDA(cudaMemcpyAsync(out + (size_t)a * d.nf * Tp, ln.out.p, n * per_row_out, cudaMemcpyDeviceToHost, ln.stream));
-    }
-    return sync_lanes(dc);
+      return SS_OK;
+    }, true);
   });
 }
 
@@ -916,8 +1155,8 @@ int ss_preemphasis_batch(const float* in, float* out, int64_t n_rows, int64_t n,
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, (256ll << 20) / (n * 4)));
   for (int64_t a = 0; a < n_rows; a += chunk) {
     const int64_t m = std::min(chunk, n_rows - a);
-    if ((rc = c->a.reserve((size_t)m * n * 4))) return rc;
-    if ((rc = c->b.reserve((size_t)m * n * 4))) return rc;
+    if ((rc = reserve(c->a, (size_t)m * n * 4))) return rc;
+    if ((rc = reserve(c->b, (size_t)m * n * 4))) return rc;
     if ((rc = copy_rows_h2d(static_cast<float*>(c->a.p), in + a * row_stride, m, n, row_stride, c->stream))) return rc;
     if ((rc = ss_preemphasis_dev(c->stream, static_cast<float*>(c->a.p), static_cast<float*>(c->b.p), m, n, n, shift, cof)))
       return rc;
@@ -960,8 +1199,8 @@ int ss_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int zero_p
   DefaultCtx* c;
   int rc = default_ctx(&c);
   if (rc) return rc;
-  if ((rc = c->a.reserve((size_t)n * 4))) return rc;
-  if ((rc = c->b.reserve((size_t)T * L * 4))) return rc;
+  if ((rc = reserve(c->a, (size_t)n * 4))) return rc;
+  if ((rc = reserve(c->b, (size_t)T * L * 4))) return rc;
   SS_CUDA(cudaMemcpyAsync(c->a.p, in, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   if ((rc = ss_stack_frames_dev(c->stream, static_cast<float*>(c->a.p), n, L, S, zero_padding, flags,
                                 static_cast<float*>(c->b.p), T)))
@@ -971,27 +1210,48 @@ int ss_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int zero_p
   return SS_OK;
 }
 
-// power_spectrum has no config either: FFT tables are cached per (thread, n_fft)
-struct PsCache {
-  int n = 0;
+// power_spectrum has no config either: FFT tables are cached per (device, n_fft), process-wide.  The
+// table is uploaded on the stream of the call that first needs it; an event orders every later stream
+// behind that upload.
+struct PsEntry {
   FftPlanHost plan;
   DevBuf tw;
+  cudaEvent_t ready = nullptr;
+  void* upload_stream = nullptr;
 };
-static thread_local PsCache g_ps;
-static int ps_tables(int64_t n_fft, DevTables* tab) {
+static std::mutex g_ps_mu;
+static std::map<std::pair<int, int>, std::unique_ptr<PsEntry>> g_ps;
+static int ps_tables(int64_t n_fft, void* stream, DevTables* tab) {
   if (n_fft < 2 || n_fft > 8192) return fail(SS_ERR_UNSUPPORTED, "n_fft=%lld outside [2, 8192]", (long long)n_fft);
-  if (g_ps.n != n_fft) {
-    if (!build_fft_plan((int)n_fft, &g_ps.plan)) return fail(SS_ERR_UNSUPPORTED, "n_fft=%lld has a prime factor > 61", (long long)n_fft);
-    int rc = g_ps.tw.reserve(g_ps.plan.tw.size() * sizeof(float));
+  int dev = 0;
+  SS_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_ps_mu);
+  auto& slot = g_ps[{dev, (int)n_fft}];
+  if (!slot) {
+    std::unique_ptr<PsEntry> e(new PsEntry());
+    if (!build_fft_plan((int)n_fft, &e->plan)) return fail(SS_ERR_UNSUPPORTED, "n_fft=%lld has a prime factor > 61", (long long)n_fft);
+    int rc = reserve(e->tw, e->plan.tw.size() * sizeof(float));
     if (rc) return rc;
-    SS_CUDA(cudaMemcpy(g_ps.tw.p, g_ps.plan.tw.data(), g_ps.plan.tw.size() * sizeof(float), cudaMemcpyHostToDevice));
-    g_ps.n = (int)n_fft;
+    SS_CUDA(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
+    SS_CUDA(cudaMemcpyAsync(e->tw.p, e->plan.tw.data(), e->plan.tw.size() * sizeof(float), cudaMemcpyHostToDevice,
+                            (cudaStream_t)stream));
+    SS_CUDA(cudaEventRecord(e->ready, (cudaStream_t)stream));
+    e->upload_stream = stream;
+    slot = std::move(e);
+  } else if (slot->upload_stream != stream) {
+    SS_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, slot->ready, 0));
   }
   *tab = DevTables();
-  tab->tw = static_cast<const float2*>(g_ps.tw.p);
-  tab->n_stages = g_ps.plan.n_stages;
-  for (int i = 0; i < kMaxStages; ++i) tab->radix[i] = g_ps.plan.radix[i];
+  tab->tw = static_cast<const float2*>(slot->tw.p);
+  tab->n_stages = slot->plan.n_stages;
+  for (int i = 0; i < kMaxStages; ++i) tab->radix[i] = slot->plan.radix[i];
   return SS_OK;
+}
+
+static StreamScratch* stream_scratch(void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return ScratchRegistry::instance().get(dev, stream);
 }
 
 int ss_power_spectrum_dev(void* stream, const float* d_frames, int64_t rows, int64_t L, int64_t n_fft, float* d_out) {
@@ -1000,7 +1260,7 @@ int ss_power_spectrum_dev(void* stream, const float* d_frames, int64_t rows, int
   if (L > n_fft) return fail(SS_ERR_INVALID_ARG, "frame_len %lld > n_fft %lld (ndrustfft panics, processing.rs:159)", (long long)L, (long long)n_fft);
   if (rows == 0) return SS_OK;
   FrameParams p;
-  int rc = ps_tables(n_fft, &p.tab);
+  int rc = ps_tables(n_fft, stream, &p.tab);
   if (rc) return rc;
   p.pcm = d_frames;
   p.n_rows = 1;
@@ -1031,8 +1291,8 @@ int ss_power_spectrum(const float* frames, int64_t rows, int64_t L, int64_t n_ff
   int rc = default_ctx(&c);
   if (rc) return rc;
   const int64_t F = n_fft / 2 + 1;
-  if ((rc = c->a.reserve((size_t)rows * L * 4))) return rc;
-  if ((rc = c->b.reserve((size_t)rows * F * 4))) return rc;
+  if ((rc = reserve(c->a, (size_t)rows * L * 4))) return rc;
+  if ((rc = reserve(c->b, (size_t)rows * F * 4))) return rc;
   SS_CUDA(cudaMemcpyAsync(c->a.p, frames, (size_t)rows * L * 4, cudaMemcpyHostToDevice, c->stream));
   if ((rc = ss_power_spectrum_dev(c->stream, static_cast<float*>(c->a.p), rows, L, n_fft, static_cast<float*>(c->b.p))))
     return rc;
@@ -1042,13 +1302,13 @@ int ss_power_spectrum(const float* frames, int64_t rows, int64_t L, int64_t n_ff
 }
 
 // processing::log_power_spectrum (processing.rs:194-214): private and unused in the reference
-static thread_local DevBuf g_logps_scratch;
 int ss_log_power_spectrum_dev(void* stream, const float* d_frames, int64_t rows, int64_t L, int64_t n_fft, int normalize,
                               float* d_out) {
   int rc = ss_power_spectrum_dev(stream, d_frames, rows, L, n_fft, d_out);
   if (rc || rows == 0) return rc;
-  if ((rc = g_logps_scratch.reserve(16))) return rc;
-  int e = launch_log_power(d_out, rows * (n_fft / 2 + 1), normalize, g_logps_scratch.p, stream);
+  DevBuf& sc = stream_scratch(stream)->logps;
+  if ((rc = reserve(sc, 16))) return rc;
+  int e = launch_log_power(d_out, rows * (n_fft / 2 + 1), normalize, sc.p, stream);
   if (e) return cuda_fail((cudaError_t)e, "log_power_spectrum launch");
   return SS_OK;
 }
@@ -1062,8 +1322,8 @@ int ss_log_power_spectrum(const float* frames, int64_t rows, int64_t L, int64_t 
   int rc = default_ctx(&c);
   if (rc) return rc;
   const int64_t F = n_fft / 2 + 1;
-  if ((rc = c->a.reserve((size_t)rows * L * 4))) return rc;
-  if ((rc = c->b.reserve((size_t)rows * F * 4))) return rc;
+  if ((rc = reserve(c->a, (size_t)rows * L * 4))) return rc;
+  if ((rc = reserve(c->b, (size_t)rows * F * 4))) return rc;
   SS_CUDA(cudaMemcpyAsync(c->a.p, frames, (size_t)rows * L * 4, cudaMemcpyHostToDevice, c->stream));
   if ((rc = ss_log_power_spectrum_dev(c->stream, static_cast<float*>(c->a.p), rows, L, n_fft, normalize, static_cast<float*>(c->b.p))))
     return rc;
@@ -1072,7 +1332,6 @@ int ss_log_power_spectrum(const float* frames, int64_t rows, int64_t L, int64_t 
   return SS_OK;
 }
 
-static thread_local DevBuf g_cmvn_scratch;
 int ss_cmvn_dev(void* stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols, int varnorm,
                 float* d_out) {
   if (!d_in || !d_out) return fail(SS_ERR_INVALID_ARG, "null argument");
@@ -1080,9 +1339,10 @@ int ss_cmvn_dev(void* stream, const float* d_in, int64_t n_mats, int64_t rows, i
   if (rows <= 0) return fail(SS_ERR_INVALID_ARG, "cmvn: zero rows (mean_axis(..).unwrap() panics, processing.rs:270)");
   if (cols > 256) return fail(SS_ERR_UNSUPPORTED, "cmvn: more than 256 columns");
   if (n_mats == 0 || cols == 0) return SS_OK;
-  int rc = g_cmvn_scratch.reserve(cmvn_scratch_bytes(n_mats, rows, cols));
+  DevBuf& sc = stream_scratch(stream)->cmvn;
+  int rc = reserve(sc, cmvn_scratch_bytes(n_mats, rows, cols));
   if (rc) return rc;
-  int e = launch_cmvn(d_in, n_mats, rows, cols, varnorm, d_out, static_cast<float*>(g_cmvn_scratch.p), stream);
+  int e = launch_cmvn(d_in, n_mats, rows, cols, varnorm, d_out, static_cast<float*>(sc.p), stream);
   if (e) return cuda_fail((cudaError_t)e, "cmvn launch");
   return SS_OK;
 }
@@ -1096,8 +1356,8 @@ int ss_cmvn_batch(const float* in, int64_t n_mats, int64_t rows, int64_t cols, i
   int rc = default_ctx(&c);
   if (rc) return rc;
   const size_t bytes = (size_t)n_mats * rows * cols * 4;
-  if ((rc = c->a.reserve(bytes))) return rc;
-  if ((rc = c->b.reserve(bytes))) return rc;
+  if ((rc = reserve(c->a, bytes))) return rc;
+  if ((rc = reserve(c->b, bytes))) return rc;
   SS_CUDA(cudaMemcpyAsync(c->a.p, in, bytes, cudaMemcpyHostToDevice, c->stream));
   if ((rc = ss_cmvn_dev(c->stream, static_cast<float*>(c->a.p), n_mats, rows, cols, varnorm, static_cast<float*>(c->b.p))))
     return rc;
@@ -1126,7 +1386,6 @@ int ss_extract_derivative_feature_dev(void* stream, const float* d_in, int64_t r
   if (e) return cuda_fail((cudaError_t)e, "derivative cube launch");
   return SS_OK;
 }
-static thread_local DevBuf g_cmvnw_scratch;
 int ss_cmvnw_dev(void* stream, const float* d_in, int64_t n_mats, int64_t rows, int64_t cols, int64_t win, int varnorm,
                  float* d_out) {
   if (!d_in || !d_out) return fail(SS_ERR_INVALID_ARG, "null argument");
@@ -1136,9 +1395,10 @@ int ss_cmvnw_dev(void* stream, const float* d_in, int64_t n_mats, int64_t rows, 
   if (n_mats == 0 || rows == 0 || cols == 0) return SS_OK;
   float* scratch = nullptr;
   if (varnorm) {
-    int rc = g_cmvnw_scratch.reserve((size_t)n_mats * rows * cols * sizeof(float));
+    DevBuf& sc = stream_scratch(stream)->cmvnw;
+    int rc = reserve(sc, (size_t)n_mats * rows * cols * sizeof(float));
     if (rc) return rc;
-    scratch = static_cast<float*>(g_cmvnw_scratch.p);
+    scratch = static_cast<float*>(sc.p);
   }
   int e = launch_cmvnw(d_in, n_mats, rows, cols, (int)win, varnorm, d_out, scratch, stream);
   if (e) return cuda_fail((cudaError_t)e, "cmvnw launch");

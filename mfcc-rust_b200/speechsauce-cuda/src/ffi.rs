@@ -64,9 +64,15 @@ extern "C" {
     pub fn ss_version() -> *const c_char;
     pub fn ss_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn ss_host_free(ptr: *mut c_void) -> c_int;
+    pub fn ss_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn ss_host_unregister(ptr: *mut c_void) -> c_int;
+    pub fn ss_host_is_pinned(ptr: *const c_void) -> c_int;
+    pub fn ss_copy_threads() -> c_int;
+    pub fn ss_release_scratch() -> c_int;
     pub fn ss_plan_create(cfg: *const ss_config, devices: *const c_int, n_devices: c_int, out: *mut *mut ss_plan) -> c_int;
     pub fn ss_plan_destroy(plan: *mut ss_plan);
     pub fn ss_plan_get_info(plan: *const ss_plan, info: *mut ss_plan_info) -> c_int;
+    pub fn ss_plan_set_tuning(plan: *mut ss_plan, tile_frames: i64, chunk_bytes: i64) -> c_int;
     pub fn ss_plan_get_analysis_mem(plan: *const ss_plan, out: *mut f32, n: i64) -> c_int;
     pub fn ss_plan_set_analysis_mem(plan: *mut ss_plan, input: *const f32, n: i64) -> c_int;
     pub fn ss_num_frames(n: i64, frame_len: i64, frame_step: i64, zero_padding: c_int) -> i64;

@@ -64,9 +64,15 @@ SYMBOLS = {
     "ss_version": (C.c_char_p, []),
     "ss_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ss_host_free": (C.c_int, [_vp]),
+    "ss_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "ss_host_unregister": (C.c_int, [_vp]),
+    "ss_host_is_pinned": (C.c_int, [_vp]),
+    "ss_copy_threads": (C.c_int, []),
+    "ss_release_scratch": (C.c_int, []),
     "ss_plan_create": (C.c_int, [C.POINTER(ss_config), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "ss_plan_destroy": (None, [_vp]),
     "ss_plan_get_info": (C.c_int, [_vp, C.POINTER(ss_plan_info)]),
+    "ss_plan_set_tuning": (C.c_int, [_vp, C.c_int64, C.c_int64]),
     "ss_plan_get_analysis_mem": (C.c_int, [_vp, _fp, _i64]),
     "ss_plan_set_analysis_mem": (C.c_int, [_vp, _fp, _i64]),
     "ss_num_frames": (_i64, [_i64, _i64, _i64, C.c_int]),

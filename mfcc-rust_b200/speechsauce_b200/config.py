@@ -77,6 +77,11 @@ class SpeechConfig:
             v = np.ascontiguousarray(value, np.float32)
             check(lib.ss_plan_set_analysis_mem(self._plan, _lib.fptr(v), v.size))
 
+    def set_tuning(self, tile_frames=0, chunk_bytes=0):
+        """ss_plan_set_tuning: host-pipeline knobs (frame tiles for long clips, bytes per chunk)."""
+        check(lib.ss_plan_set_tuning(self._plan, int(tile_frames), int(chunk_bytes)))
+        return self
+
     def filterbank(self) -> np.ndarray:
         fb = np.empty((self.num_filters, self.freq_size), np.float32)
         check(lib.ss_debug_filterbank(self._plan, _lib.fptr(fb)))

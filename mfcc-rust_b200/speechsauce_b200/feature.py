@@ -29,8 +29,9 @@ def _frames(cfg, clip_len):
     return T
 
 
-def features(signal, cfg, *, mfe=False, energy=False, lmfe=False, ssc=False, mfcc=False, cmvn_mode=0):
-    """ss_features: any subset of outputs from ONE pass over the PCM."""
+def features(signal, cfg, *, mfe=False, energy=False, lmfe=False, ssc=False, mfcc=False, cmvn_mode=0, empty=np.empty):
+    """ss_features: any subset of outputs from ONE pass over the PCM.  `empty`: the output allocator
+    (np.empty; hostmem.pinned_empty gives page-locked results that are DMA'd in place)."""
     x, one = _rows(signal)
     n, clip_len = x.shape
     T = _frames(cfg, clip_len)
@@ -38,11 +39,11 @@ def features(signal, cfg, *, mfe=False, energy=False, lmfe=False, ssc=False, mfc
         T = 0
     nf, nc = cfg.num_filters, cfg.num_cepstral
     out = {}
-    if mfe: out["mfe"] = np.empty((n, T, nf), np.float32)
-    if energy: out["energy"] = np.empty((n, T), np.float32)
-    if lmfe: out["lmfe"] = np.empty((n, T, nf), np.float32)
-    if ssc: out["ssc"] = np.empty((n, T, nf), np.float32)
-    if mfcc: out["mfcc"] = np.empty((n, T, nc), np.float32)
+    if mfe: out["mfe"] = empty((n, T, nf), np.float32)
+    if energy: out["energy"] = empty((n, T), np.float32)
+    if lmfe: out["lmfe"] = empty((n, T, nf), np.float32)
+    if ssc: out["ssc"] = empty((n, T, nf), np.float32)
+    if mfcc: out["mfcc"] = empty((n, T, nc), np.float32)
     o = _lib.ss_feature_outputs(*[_lib.fptr(out.get(k)) for k in ("mfe", "energy", "lmfe", "ssc", "mfcc")],
                                 int(cmvn_mode), 0)
     check(lib.ss_features(cfg.plan, _lib.fptr(x), n, clip_len, clip_len, C.byref(o)))

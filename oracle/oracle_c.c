@@ -63,29 +63,48 @@ static void fft_exec(const fft_plan* p, cpx* x) {
   int ns = 1;
   for (int s = 0; s < p->nfac; ++s) {
     const int R = p->fac[s], nb = n / R, tstride = n / (ns * R), rstride = n / R;
-    for (int j = 0; j < nb; ++j) {
-      const int k = j % ns, j0 = (j / ns) * ns * R + k;
-      cpx v[64];
-      for (int r = 0; r < R; ++r) {
-        cpx a = src[j + r * nb];
-        if (r > 0 && k > 0) {
-          const cpx w = p->tw[k * r * tstride];
-          const float re = a.re * w.re - a.im * w.im, im = a.re * w.im + a.im * w.re;
-          a.re = re; a.im = im;
+    /* butterfly j = jb * ns + k (k < ns) reads src[j + r * nb] and writes dst[jb * ns * R + k + q * ns] */
+    for (int jb = 0; jb < nb / ns; ++jb) {
+      if (R == 4 || R == 2) {
+        const cpx* s0 = src + jb * ns;
+        cpx* d0 = dst + jb * ns * R;
+        for (int k = 0; k < ns; ++k) {
+          cpx v[4];
+          for (int r = 0; r < R; ++r) {
+            cpx a = s0[k + r * nb];
+            if (r > 0 && k > 0) {
+              const cpx w = p->tw[k * r * tstride];
+              const float re = a.re * w.re - a.im * w.im, im = a.re * w.im + a.im * w.re;
+              a.re = re; a.im = im;
+            }
+            v[r] = a;
+          }
+          if (R == 2) {
+            d0[k].re = v[0].re + v[1].re; d0[k].im = v[0].im + v[1].im;
+            d0[k + ns].re = v[0].re - v[1].re; d0[k + ns].im = v[0].im - v[1].im;
+          } else {
+            const float ar = v[0].re + v[2].re, ai = v[0].im + v[2].im, br = v[0].re - v[2].re, bi = v[0].im - v[2].im;
+            const float cr = v[1].re + v[3].re, ci = v[1].im + v[3].im, dr = v[1].re - v[3].re, di = v[1].im - v[3].im;
+            d0[k].re = ar + cr; d0[k].im = ai + ci;
+            d0[k + ns].re = br + di; d0[k + ns].im = bi - dr;
+            d0[k + 2 * ns].re = ar - cr; d0[k + 2 * ns].im = ai - ci;
+            d0[k + 3 * ns].re = br - di; d0[k + 3 * ns].im = bi + dr;
+          }
         }
-        v[r] = a;
+        continue;
       }
-      if (R == 2) {
-        dst[j0].re = v[0].re + v[1].re; dst[j0].im = v[0].im + v[1].im;
-        dst[j0 + ns].re = v[0].re - v[1].re; dst[j0 + ns].im = v[0].im - v[1].im;
-      } else if (R == 4) {
-        const float ar = v[0].re + v[2].re, ai = v[0].im + v[2].im, br = v[0].re - v[2].re, bi = v[0].im - v[2].im;
-        const float cr = v[1].re + v[3].re, ci = v[1].im + v[3].im, dr = v[1].re - v[3].re, di = v[1].im - v[3].im;
-        dst[j0].re = ar + cr; dst[j0].im = ai + ci;
-        dst[j0 + ns].re = br + di; dst[j0 + ns].im = bi - dr;
-        dst[j0 + 2 * ns].re = ar - cr; dst[j0 + 2 * ns].im = ai - ci;
-        dst[j0 + 3 * ns].re = br - di; dst[j0 + 3 * ns].im = bi + dr;
-      } else {
+      for (int k = 0; k < ns; ++k) {
+        const int j = jb * ns + k, j0 = jb * ns * R + k;
+        cpx v[64];
+        for (int r = 0; r < R; ++r) {
+          cpx a = src[j + r * nb];
+          if (r > 0 && k > 0) {
+            const cpx w = p->tw[k * r * tstride];
+            const float re = a.re * w.re - a.im * w.im, im = a.re * w.im + a.im * w.re;
+            a.re = re; a.im = im;
+          }
+          v[r] = a;
+        }
         for (int q = 0; q < R; ++q) {
           float re = v[0].re, im = v[0].im;
           for (int r = 1; r < R; ++r) {
@@ -200,7 +219,10 @@ typedef struct {
   int L, S, W, F, H, nf, nc;
   rfft_plan rf;
   float* fb;    /* [nf][F] */
+  float* fbT;   /* [F][nf]: the same matrix transposed, so the dense product vectorises over filters while
+                   every filter still sums its bins in index order (the sequential order of a plain dot) */
   float* dct;   /* [nf][nf] full DCT-II (nddct2 transforms the whole axis, then the slice) */
+  float* dctT;  /* [nf][nf] transposed, same reason */
   float* window;
   float* frame; /* [W] */
   cpx* spec;    /* [F] */
@@ -219,11 +241,16 @@ static int plan_init(orc_plan* p, const orc_config* c) {
   if (rfft_init(&p->rf, p->W)) return -1;
   p->fb = (float*)malloc(sizeof(float) * p->nf * p->F);
   filterbanks(c, p->F, p->fb);
+  p->fbT = (float*)malloc(sizeof(float) * p->nf * p->F);
+  for (int i = 0; i < p->nf; ++i)
+    for (int k = 0; k < p->F; ++k) p->fbT[(size_t)k * p->nf + i] = p->fb[(size_t)i * p->F + k];
   p->dct = (float*)malloc(sizeof(float) * p->nf * p->nf);
+  p->dctT = (float*)malloc(sizeof(float) * p->nf * p->nf);
   const double pi = 3.14159265358979323846;
   const double sc = c->dct2_scale != 0.f ? c->dct2_scale : 2.0;
   for (int k = 0; k < p->nf; ++k)
-    for (int n = 0; n < p->nf; ++n) p->dct[k * p->nf + n] = (float)(sc * cos(pi * k * (2.0 * n + 1.0) / (2.0 * p->nf)));
+    for (int n = 0; n < p->nf; ++n)
+      p->dctT[n * p->nf + k] = p->dct[k * p->nf + n] = (float)(sc * cos(pi * k * (2.0 * n + 1.0) / (2.0 * p->nf)));
   p->window = (float*)malloc(sizeof(float) * p->W);
   for (int i = 0; i < p->W; ++i) {
     const double s = sin(0.5 * pi * (i + 0.5) / (double)(p->W / 2));
@@ -238,12 +265,12 @@ static int plan_init(orc_plan* p, const orc_config* c) {
 }
 static void plan_free(orc_plan* p) {
   rfft_free(&p->rf);
-  free(p->fb); free(p->dct); free(p->window); free(p->frame); free(p->spec); free(p->P); free(p->feat); free(p->full);
+  free(p->fb); free(p->fbT); free(p->dct); free(p->dctT); free(p->window); free(p->frame); free(p->spec); free(p->P); free(p->feat); free(p->full);
 }
 
 /* one clip: mfe (+ energy), optional lmfe, mfcc, cmvn.  Outputs may be NULL. */
 static void clip_features(orc_plan* p, const float* x, int64_t T, float* mfe, float* energy, float* lmfe, float* mfcc,
-                          int cmvn_mode) {
+                          float* ssc, int cmvn_mode) {
   const int L = p->L, S = p->S, W = p->W, F = p->F, nf = p->nf, nc = p->nc;
   const float inv = 1.0f / (float)W;
   const float n = (float)(T * nf);
@@ -258,11 +285,22 @@ static void clip_features(orc_plan* p, const float* x, int64_t T, float* mfe, fl
       e += p->P[k];
     }
     if (e == 0.f) e = ORC_EPS;
-    for (int i = 0; i < nf; ++i) {                            /* dense GEMM row, feature.rs:229 */
-      const float* w = p->fb + (size_t)i * F;
-      float acc = 0.f;
-      for (int k = 0; k < F; ++k) acc += p->P[k] * w[k];
-      p->feat[i] = acc == 0.f ? ORC_EPS : acc;
+    for (int i = 0; i < nf; ++i) p->feat[i] = 0.f;          /* dense GEMM row, feature.rs:229 */
+    for (int k = 0; k < F; ++k) {
+      const float pk = p->P[k];
+      const float* w = p->fbT + (size_t)k * nf;
+      for (int i = 0; i < nf; ++i) p->feat[i] += pk * w[i];
+    }
+    for (int i = 0; i < nf; ++i) p->feat[i] = p->feat[i] == 0.f ? ORC_EPS : p->feat[i];
+    if (ssc) {  /* (P o R) fb^T / mfe with R = linspace(1, sr/2, F) */
+      const float step = F > 1 ? ((float)p->c.sample_rate / 2.0f - 1.0f) / (float)(F - 1) : 0.f;
+      for (int i = 0; i < nf; ++i) p->full[i] = 0.f;
+      for (int k = 0; k < F; ++k) {
+        const float pr = p->P[k] * (1.0f + (float)k * step);
+        const float* w = p->fbT + (size_t)k * nf;
+        for (int i = 0; i < nf; ++i) p->full[i] += pr * w[i];
+      }
+      for (int i = 0; i < nf; ++i) ssc[t * nf + i] = p->full[i] / p->feat[i];
     }
     if (mfe) memcpy(mfe + t * nf, p->feat, sizeof(float) * nf);
     if (energy) energy[t] = e;
@@ -270,11 +308,11 @@ static void clip_features(orc_plan* p, const float* x, int64_t T, float* mfe, fl
       for (int i = 0; i < nf; ++i) p->feat[i] = logf(p->feat[i]);
     if (lmfe) memcpy(lmfe + t * nf, p->feat, sizeof(float) * nf);
     if (mfcc) {
-      for (int k = 0; k < nf; ++k) {                          /* nddct2 over the whole axis */
-        const float* d = p->dct + (size_t)k * nf;
-        float acc = 0.f;
-        for (int i = 0; i < nf; ++i) acc += p->feat[i] * d[i];
-        p->full[k] = acc;
+      for (int k = 0; k < nf; ++k) p->full[k] = 0.f;          /* nddct2 over the whole axis */
+      for (int i = 0; i < nf; ++i) {
+        const float fi = p->feat[i];
+        const float* d = p->dctT + (size_t)i * nf;
+        for (int k = 0; k < nf; ++k) p->full[k] += fi * d[k];
       }
       float* o = mfcc + t * nc;
       for (int k = 0; k < nc; ++k) o[k] = k == 0 ? (t == 0 ? p->full[0] * s00 : p->full[0]) : p->full[k] * srest;
@@ -304,7 +342,7 @@ static void clip_features(orc_plan* p, const float* x, int64_t T, float* mfe, fl
 
 /* pcm [n_clips][clip_len] -> any of mfe [n][T][nf], energy [n][T], lmfe [n][T][nf], mfcc [n][T][nc] */
 int orc_features(const orc_config* c, const float* pcm, int64_t n_clips, int64_t clip_len, float* mfe, float* energy,
-                 float* lmfe, float* mfcc, int cmvn_mode, int n_threads) {
+                 float* lmfe, float* mfcc, float* ssc, int cmvn_mode, int n_threads) {
   orc_plan probe;
   if (plan_init(&probe, c)) return -1;
   const int64_t T = orc_num_frames(clip_len, probe.L, probe.S, 0);
@@ -322,7 +360,8 @@ int orc_features(const orc_config* c, const float* pcm, int64_t n_clips, int64_t
 #pragma omp for schedule(dynamic, 8)
     for (int64_t i = 0; i < n_clips; ++i)
       clip_features(&p, pcm + i * clip_len, T, mfe ? mfe + i * T * nf : NULL, energy ? energy + i * T : NULL,
-                    lmfe ? lmfe + i * T * nf : NULL, mfcc ? mfcc + i * T * nc : NULL, cmvn_mode);
+                    lmfe ? lmfe + i * T * nf : NULL, mfcc ? mfcc + i * T * nc : NULL, ssc ? ssc + i * T * nf : NULL,
+                    cmvn_mode);
     plan_free(&p);
   }
   return 0;
@@ -375,14 +414,17 @@ int orc_mel_spectrogram2(const orc_config* c, const float* pcm, int64_t ch, int6
           dst[k] = a * a;
         }
       }
-      for (int m = 0; m < nf; ++m) {                          /* dense einsum ntf,mf->nmt */
-        const float* w = p.fb + (size_t)m * F;
-        float* o = out + (r * nf + m) * Tp;
-        for (int64_t t = 0; t < Tp; ++t) {
-          const float* pr = pw + t * F;
-          float acc = 0.f;
-          for (int k = 0; k < F; ++k) acc += pr[k] * w[k];
-          o[t] = log_mode ? logf(acc == 0.f ? ORC_EPS : acc) : acc;
+      for (int64_t t = 0; t < Tp; ++t) {                      /* dense einsum ntf,mf->nmt: every (m, t) sums */
+        const float* pr = pw + t * F;                         /* its bins in index order; vectorised over m   */
+        for (int m = 0; m < nf; ++m) p.feat[m] = 0.f;
+        for (int k = 0; k < F; ++k) {
+          const float pk = pr[k];
+          const float* w = p.fbT + (size_t)k * nf;
+          for (int m = 0; m < nf; ++m) p.feat[m] += pk * w[m];
+        }
+        for (int m = 0; m < nf; ++m) {
+          const float acc = p.feat[m];
+          out[(r * nf + m) * Tp + t] = log_mode ? logf(acc == 0.f ? ORC_EPS : acc) : acc;
         }
       }
     }

@@ -27,7 +27,7 @@ def _load():
     lib.orc_num_frames.restype = C.c_int64
     lib.orc_num_frames.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int]
     vp = C.c_void_p
-    lib.orc_features.argtypes = [C.POINTER(orc_config), vp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.c_int, C.c_int]
+    lib.orc_features.argtypes = [C.POINTER(orc_config), vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, C.c_int, C.c_int]
     lib.orc_mel_spectrogram2.argtypes = [C.POINTER(orc_config), vp, C.c_int64, C.c_int64, vp, vp, C.c_int, C.c_int]
     return lib
 
@@ -57,7 +57,7 @@ def max_threads():
     return lib().orc_max_threads()
 
 
-def features(x, cfg, *, mfe=False, energy=False, lmfe=False, mfcc=False, cmvn_mode=0, n_threads=0):
+def features(x, cfg, *, mfe=False, energy=False, lmfe=False, mfcc=False, ssc=False, cmvn_mode=0, n_threads=0):
     x = np.ascontiguousarray(x, np.float32)
     n, clip_len = x.shape
     L = int(np.floor(float(np.float32(cfg.sample_rate) * np.float32(cfg.frame_length)) + 0.5))
@@ -70,8 +70,9 @@ def features(x, cfg, *, mfe=False, energy=False, lmfe=False, mfcc=False, cmvn_mo
     if energy: out["energy"] = np.empty((n, T), np.float32)
     if lmfe: out["lmfe"] = np.empty((n, T, cfg.num_filters), np.float32)
     if mfcc: out["mfcc"] = np.empty((n, T, cfg.num_cepstral), np.float32)
+    if ssc: out["ssc"] = np.empty((n, T, cfg.num_filters), np.float32)
     rc = lib().orc_features(C.byref(cfg), _p(x), n, clip_len, _p(out.get("mfe")), _p(out.get("energy")),
-                            _p(out.get("lmfe")), _p(out.get("mfcc")), cmvn_mode, n_threads)
+                            _p(out.get("lmfe")), _p(out.get("mfcc")), _p(out.get("ssc")), cmvn_mode, n_threads)
     if rc:
         raise ValueError("orc_features failed")
     return out

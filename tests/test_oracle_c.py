@@ -15,9 +15,10 @@ def test_c_port_features_match_numpy_oracle(cname):
     x = o.synth_signal(6, oc.sample_rate, 17)
     x[1] = 0.0                      # zero_handling path
     x[2, :4000] = 0.0               # silence next to sound
-    r = oracle_c.features(x, cc, mfe=True, energy=True, lmfe=True, mfcc=True, cmvn_mode=0, n_threads=2)
+    r = oracle_c.features(x, cc, mfe=True, energy=True, lmfe=True, mfcc=True, ssc=True, cmvn_mode=0, n_threads=2)
     for i in range(6):
         f, e = o.mfe(x[i], oc)
+        np.testing.assert_allclose(r["ssc"][i], o.ssc(x[i], oc), rtol=2e-4, atol=1e-3)
         np.testing.assert_allclose(r["mfe"][i], f, rtol=1e-4, atol=2e-6 * f.max())
         np.testing.assert_allclose(r["energy"][i], e, rtol=1e-5)
         np.testing.assert_allclose(r["lmfe"][i], np.log(f), atol=1e-3)
