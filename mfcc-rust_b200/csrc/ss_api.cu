@@ -194,11 +194,12 @@ static int ensure_device(ss_plan* pl, DeviceCtx* dc) {
 // `T_clip` / `first_tile`: when a long clip is processed in frame tiles the rows handed in are tiles of
 // one clip; the length-dependent DCT scale (feature.rs:126) uses the clip's frame count and only the
 // clip's very first frame is element [0,0] (feature.rs:128).  T_clip == 0: rows are whole clips.
+// `T_rows`: frames per row when it is not the reference's count for `clip_len` samples (tiles).
 static int features_dev(ss_plan* pl, DeviceCtx* dc, cudaStream_t stream, const float* d_pcm, int64_t n_clips,
                         int64_t clip_len, int64_t row_stride, const ss_feature_outputs& o, DevBuf* scratch,
-                        int64_t T_clip = 0, bool first_tile = true) {
+                        int64_t T_clip = 0, bool first_tile = true, int64_t T_rows = 0) {
   const Derived& d = pl->d;
-  const int64_t T = num_frames(clip_len, d.L, d.S, 0);
+  const int64_t T = T_rows > 0 ? T_rows : num_frames(clip_len, d.L, d.S, 0);
   FrameParams p;
   p.pcm = d_pcm;
   p.n_rows = n_clips;
@@ -818,7 +819,9 @@ int ss_features(ss_plan* pl, const float* pcm, int64_t n_clips, int64_t clip_len
         return features_dev(pl, dc, ln.stream, d_in, n, clip_len, clip_len, dvo, &ln.scratch);
       }, true);
     }
-    // ---- frame tiles: tile j of a clip = frames [j Tt, (j+1) Tt) = samples [j Tt S, j Tt S + (Tt-1) S + L)
+    // ---- frame tiles: tile j of a clip = frames [j Tt, (j+1) Tt) = samples [j Tt S, j Tt S + (Tt-1) S + L).
+    // The frame count of a tile is handed to the kernels explicitly: the reference's own count has no "+1"
+    // (floor((N - L) / S), processing.rs:101) and would give Tt - 1 for exactly these samples.
     const int64_t Tt = tile_env > 0 ? tile_env : std::max<int64_t>(64, (int64_t)(kChunk / (d.S * sizeof(float) + per_frame_out)));
     const bool cmvn = o.mfcc && o.mfcc_cmvn_mode != SS_CMVN_NONE;
     for (int64_t c = c0; c < c1; ++c) {
@@ -862,7 +865,7 @@ int ss_features(ss_plan* pl, const float* pcm, int64_t n_clips, int64_t clip_len
           dvo.ssc = dv[3];
           dvo.mfcc = cmvn ? static_cast<float*>(dc->clip_mfcc.p) + (size_t)(j_base + j) * Tt * d.nc : dv[4];
           dvo.mfcc_cmvn_mode = SS_CMVN_NONE;
-          return features_dev(pl, dc, ln.stream, d_in, 1, tile_len, tile_len, dvo, &ln.scratch, T, j_base + j == 0);
+          return features_dev(pl, dc, ln.stream, d_in, 1, tile_len, tile_len, dvo, &ln.scratch, T, j_base + j == 0, frames);
         }, false);
         if (r) return r;
       }

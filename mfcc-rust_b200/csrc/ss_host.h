@@ -3,6 +3,7 @@
 // memory through pinned rings, and the (device, stream)-keyed scratch registry of the *_dev entry points.
 #pragma once
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -101,6 +102,37 @@ inline bool host_ptr_is_pinned(const void* ptr) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
+// memcpy with non-temporal stores: a staging copy never re-reads its destination, so the lines should
+// not be read for ownership nor evict the rest of the cache (3 -> 2 memory passes per byte moved)
+inline void stream_copy(char* dst, const char* src, size_t n) {
+  if (n < (64u << 10)) {
+    std::memcpy(dst, src, n);
+    return;
+  }
+  const size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
+  if (head) {
+    std::memcpy(dst, src, head);
+    dst += head;
+    src += head;
+    n -= head;
+  }
+  const size_t blocks = n / 64;
+  for (size_t i = 0; i < blocks; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 0);
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 1);
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 2);
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 3);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 0, a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 1, b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 2, c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 3, d);
+    src += 64;
+    dst += 64;
+  }
+  _mm_sfence();
+  if (n & 63) std::memcpy(dst, src, n & 63);
+}
+
 // ---- staging copy pool ------------------------------------------------------------------------
 // A caller's pageable ndarray cannot be DMA'd; cudaMemcpyAsync on it degrades to a synchronous,
 // single-threaded bounce through the driver.  Instead the chunks are memcpy'd into / out of the lanes'
@@ -167,7 +199,7 @@ class CopyPool {
   };
   CopyPool() {
     unsigned hw = std::thread::hardware_concurrency();
-    int n = (int)std::min(12u, std::max(2u, hw / 2));
+    int n = (int)std::min(16u, std::max(2u, hw - 1));
     if (const char* e = getenv("SS_COPY_THREADS")) n = std::max(0, atoi(e));
     for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); });
     for (auto& t : th_) t.detach();
@@ -180,7 +212,11 @@ class CopyPool {
     return true;
   }
   static void run(const Task& k) {
-    for (size_t r = 0; r < k.rows; ++r) std::memcpy(k.dst + r * k.dpitch, k.src + r * k.spitch, k.bytes);
+    static const bool nt = !(getenv("SS_COPY_NT") && atoi(getenv("SS_COPY_NT")) == 0);
+    for (size_t r = 0; r < k.rows; ++r) {
+      if (nt) stream_copy(k.dst + r * k.dpitch, k.src + r * k.spitch, k.bytes);
+      else std::memcpy(k.dst + r * k.dpitch, k.src + r * k.spitch, k.bytes);
+    }
     if (k.t->left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
       std::lock_guard<std::mutex> lk(k.t->m);
       k.t->cv.notify_all();

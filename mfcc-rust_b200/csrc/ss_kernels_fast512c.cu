@@ -53,11 +53,13 @@ constexpr int kXs = 18;                       // transpose row stride in float2 
 constexpr int kXchFrame = 16 * kXs;           // 288 float2 per frame
 constexpr int kXchFloats = 2 * kXchFrame * 2; // 1152 floats per warp (2 frames)
 constexpr int kTileRows = 8;                  // frames per MMA tile
-constexpr int kPs = 132;                      // P row stride: bins 0..128 + 3 zero pads; 132 % 32 == 4 -> the 4-byte A-fragment loads (row g, bin t) hit 32 banks
-constexpr int kKs = 17;                       // k-steps of 8 bins; the last one runs 4 floats into the next row (finite values x zero weights)
+constexpr int kPs = 148;                      // P row stride: bins 0..128 + 19 zero pads, so that the last k-step (bins 128..135) and the
+                                              // zero-weight block of an odd band (bins 136..143) stay inside the row: a NaN / Inf frame
+                                              // cannot reach its neighbours through 0 x Inf.  148 % 32 == 20 -> the 4-byte A-fragment
+                                              // loads (row g, bin t) still hit 32 distinct banks
+constexpr int kKs = 17;                       // k-steps of 8 bins
 constexpr int kKsTab = kKs + 1;               // + one zero block: bands are padded to an even number of k-steps
-constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows + 4;  // + 8 frame energies + 4 zeros: the zero-weight
-                                                                           // block of an odd band reads bins 136..143 of row 7
+constexpr int kWarpFloats = kXchFloats + kTileRows * kPs + kTileRows + 4;  // + 8 frame energies (+ 4: 16-byte granularity)
 static_assert(kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 constexpr int kTwRow = 36;                    // floats per lane row of the W256 table (16 float2 + pad)
 constexpr int kTabTw = 16 * kTwRow;           // CTA-shared twiddle table
