@@ -1262,6 +1262,12 @@ int ss_power_spectrum_dev(void* stream, const float* d_frames, int64_t rows, int
   if (rows < 0 || L <= 0) return fail(SS_ERR_INVALID_ARG, "bad shape");
   if (L > n_fft) return fail(SS_ERR_INVALID_ARG, "frame_len %lld > n_fft %lld (ndrustfft panics, processing.rs:159)", (long long)L, (long long)n_fft);
   if (rows == 0) return SS_OK;
+  static const bool no_fast = getenv("SS_PSPEC_GENERIC") && atoi(getenv("SS_PSPEC_GENERIC"));  // A/B switch
+  if (!no_fast && pspec512_supported(L, n_fft)) {
+    const int e = launch_pspec512(d_frames, rows, L, d_out, stream);
+    if (e) return cuda_fail((cudaError_t)e, "power_spectrum launch");
+    return SS_OK;
+  }
   FrameParams p;
   int rc = ps_tables(n_fft, stream, &p.tab);
   if (rc) return rc;

@@ -154,6 +154,10 @@ int stft2048m_build_tables(const Derived& d, const MelBank& mb, const std::vecto
 void stft2048m_free_tables(Stft2048mTables* t);
 int launch_stft2048m(const FrameParams& p, const Stft2048mTables* t, int sm_count, void* stream);
 
+// processing::power_spectrum for n_fft == 512: the register FFT of the fused path without its epilogue (ss_kernels_pspec512.cu)
+bool pspec512_supported(int64_t L, int64_t n_fft);
+int launch_pspec512(const float* frames, int64_t rows, int64_t L, float* out, void* stream);
+
 int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
                        int64_t shift, float cof, void* stream);
 int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,

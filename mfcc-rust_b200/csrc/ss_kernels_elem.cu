@@ -84,7 +84,94 @@ __global__ void __launch_bounds__(256) k_stack_frames(const float* __restrict__ 
   }
 }
 
+// 16-byte path: L, S multiples of 4 and 16-byte aligned bases.  A block copies kSfFrames consecutive frames;
+// thread i moves float4 i of the block's [frames][L / 4] slab (the overlapping part of neighbouring frames is
+// re-read through L1 / L2: DRAM sees every sample once).
+constexpr int kSfFrames = 16;
+__global__ void __launch_bounds__(256) k_stack_frames_v4(const float4* __restrict__ in, float4* __restrict__ out, int64_t n4,
+                                                         int L4, int S4, int64_t T) {
+  for (int64_t f0 = (int64_t)blockIdx.x * kSfFrames; f0 < T; f0 += (int64_t)gridDim.x * kSfFrames) {
+    const int frames = (int)min((int64_t)kSfFrames, T - f0);
+    const int total = frames * L4;
+    const float4* src = in + f0 * S4;
+    float4* dst = out + f0 * L4;
+    const int64_t left = n4 - f0 * S4;  // float4s of the signal from this slab's first sample on (zero padding beyond)
+#pragma unroll 4
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int f = i / L4, j = i - f * L4;
+      const int o = f * S4 + j;
+      dst[i] = o < left ? __ldg(src + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- cmvn
+// Small matrices (the per-clip cepstra: 97 x 13): one warp per matrix, the matrix parked in shared memory between
+// the statistics and the normalisation -> one DRAM read and one write, no scratch.  Columns are summed down the
+// rows in order (ndarray's mean_axis(0) is a sequential row accumulation, processing.rs:270), by 32 / cols row
+// groups side by side; the variance is the two-pass form of std_axis(0, ddof 0) (processing.rs:283).
+constexpr int kCmvnSmallWarps = 8;
+__global__ void __launch_bounds__(kCmvnSmallWarps * 32) k_cmvn_small(const float* __restrict__ in, float* __restrict__ out,
+                                                                     int64_t n_mats, int rows, int cols, int varnorm,
+                                                                     int warp_floats) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* x = sm + (size_t)warp * warp_floats;  // [rows * cols] then [R][cols] partials, [cols] mean, [cols] denominator
+  const int n = rows * cols;
+  const int R = cols <= 16 ? 32 / cols : 1;    // row groups working side by side
+  float* part = x + ((n + 3) & ~3);
+  float* mean_s = part + R * cols;
+  float* den_s = mean_s + cols;
+  const int rg = lane / cols, c0 = lane - rg * cols;
+  const int rpg = (rows + R - 1) / R;
+  for (int64_t m = (int64_t)blockIdx.x * kCmvnSmallWarps + warp; m < n_mats; m += (int64_t)gridDim.x * kCmvnSmallWarps) {
+    const float* src = in + m * n;
+    float* dst = out + m * n;
+    for (int i = lane; i < n; i += 32) x[i] = __ldg(src + i);
+    __syncwarp();
+    // pass A: column sums -> mean
+    for (int pass = 0; pass < (varnorm ? 3 : 1); ++pass) {
+      if (cols <= 16) {
+        if (rg < R) {
+          const int r0 = rg * rpg, r1 = min(rows, r0 + rpg);
+          const float mu = pass ? mean_s[c0] : 0.f, mu2 = pass == 2 ? den_s[c0] : 0.f;
+          float acc = 0.f;
+          for (int r = r0; r < r1; ++r) {
+            const float v = x[r * cols + c0] - mu;
+            acc += pass == 2 ? (v - mu2) * (v - mu2) : v;
+          }
+          part[rg * cols + c0] = acc;
+        }
+      } else {
+        for (int c = lane; c < cols; c += 32) {
+          const float mu = pass ? mean_s[c] : 0.f, mu2 = pass == 2 ? den_s[c] : 0.f;
+          float acc = 0.f;
+          for (int r = 0; r < rows; ++r) {
+            const float v = x[r * cols + c] - mu;
+            acc += pass == 2 ? (v - mu2) * (v - mu2) : v;
+          }
+          part[c] = acc;
+        }
+      }
+      __syncwarp();
+      for (int c = lane; c < cols; c += 32) {
+        float t = part[c];
+        for (int g = 1; g < R; ++g) t += part[g * cols + c];
+        if (pass == 0) mean_s[c] = t / (float)rows;                  // mean of x
+        else if (pass == 1) den_s[c] = t / (float)rows;              // mean of y = x - mean (std_axis subtracts it again)
+        else den_s[c] = sqrtf(t / (float)rows) + kCmvnEps;           // processing.rs:283-292
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < n; i += 32) {
+      const int c = i % cols;
+      const float d = x[i] - mean_s[c];
+      dst[i] = varnorm ? d / den_s[c] : d;
+    }
+    __syncwarp();
+  }
+}
+
 // Pass 1: per (matrix, row block) Welford statistics per column, merged across the block's
 // threads with Chan's formula.  Pass 2: merge the row blocks of the matrix, then normalise.
 // partial layout: [n_mats][nblk][cols][3] = (count, mean, M2)
@@ -112,27 +199,44 @@ __global__ void __launch_bounds__(256) k_cmvn_partial(const float* __restrict__ 
   const float* x = in + mat * rows * cols;
   const int64_t r0 = blk * rows_per_blk;
   const int64_t r1 = min(rows, r0 + rows_per_blk);
-  Wf w = {0.f, 0.f, 0.f};
-  if (lane < lanes) {
-    for (int64_t r = r0 + lane; r < r1; r += lanes) {
-      const float v = __ldg(x + r * cols + c);  // consecutive threads -> consecutive addresses
-      w.n += 1.f;
-      const float d = v - w.mean;
-      w.mean += d / w.n;
-      w.m2 += d * (v - w.mean);
+  // sums of (v - pivot) and (v - pivot)^2 with the block's first row as the pivot of every column: three
+  // operations per element and no division (a per-element Welford update made this pass compute-bound);
+  // the pivot keeps the squares small, and the row blocks are merged with Chan's formula as before
+  float n_t = 0.f, s1 = 0.f, s2 = 0.f;
+  if (lane < lanes && r0 < r1) {
+    const float pivot = __ldg(x + r0 * cols + c);
+    int64_t r = r0 + lane;
+    for (; r + 3 * lanes < r1; r += 4 * lanes) {  // four independent loads in flight
+      const float v0 = __ldg(x + r * cols + c) - pivot, v1 = __ldg(x + (r + lanes) * cols + c) - pivot;
+      const float v2 = __ldg(x + (r + 2 * lanes) * cols + c) - pivot, v3 = __ldg(x + (r + 3 * lanes) * cols + c) - pivot;
+      s1 += (v0 + v1) + (v2 + v3);
+      s2 += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+      n_t += 4.f;
+    }
+    for (; r < r1; r += lanes) {
+      const float v = __ldg(x + r * cols + c) - pivot;
+      s1 += v;
+      s2 += v * v;
+      n_t += 1.f;
     }
     float* s = sm + ((size_t)lane * cols + c) * 3;
-    s[0] = w.n; s[1] = w.mean; s[2] = w.m2;
+    s[0] = n_t; s[1] = s1; s[2] = s2;
+  } else if (lane < lanes) {
+    float* s = sm + ((size_t)lane * cols + c) * 3;
+    s[0] = 0.f; s[1] = 0.f; s[2] = 0.f;
   }
   __syncthreads();
   if (threadIdx.x < cols) {
-    Wf acc = {0.f, 0.f, 0.f};
+    float N = 0.f, S1 = 0.f, S2 = 0.f;
     for (int l = 0; l < lanes; ++l) {
       const float* s = sm + ((size_t)l * cols + threadIdx.x) * 3;
-      acc = wf_merge(acc, Wf{s[0], s[1], s[2]});
+      N += s[0]; S1 += s[1]; S2 += s[2];
     }
     float* o = partial + (((size_t)mat * nblk + blk) * cols + threadIdx.x) * 3;
-    o[0] = acc.n; o[1] = acc.mean; o[2] = acc.m2;
+    const float pivot = r0 < r1 ? __ldg(x + r0 * cols + threadIdx.x) : 0.f;
+    o[0] = N;
+    o[1] = N > 0.f ? pivot + S1 / N : 0.f;
+    o[2] = N > 0.f ? fmaxf(S2 - S1 * (S1 / N), 0.f) : 0.f;
   }
 }
 
@@ -157,10 +261,18 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
   float* y = out + mat * rows * cols;
   const int64_t e0 = blk * rows_per_blk * cols;
   const int64_t e1 = min(rows, (blk + 1) * rows_per_blk) * cols;
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-    const int c = (int)(e % cols);
-    const float d = x[e] - sm[2 * c];  // plain load: the host layer runs this pass in place (in == out)
-    y[e] = varnorm ? d * sm[2 * c + 1] : d;
+  x += e0;
+  y += e0;
+  // the slab is walked in chunks of 2^20 elements so that the column of an element is 32-bit arithmetic
+  for (int64_t base = 0; base < e1 - e0; base += (1 << 20)) {
+    const int n = (int)min((int64_t)(1 << 20), e1 - e0 - base);
+    const int cb = (int)(base % cols);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = (cb + i) % cols;
+      const float d = x[base + i] - sm[2 * c];  // plain load: the host layer runs this pass in place (in == out)
+      y[base + i] = varnorm ? d * sm[2 * c + 1] : d;
+    }
   }
 }
 
@@ -293,6 +405,15 @@ int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, i
 int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,
                         float* out, void* stream) {
   if (T <= 0) return 0;
+  const bool v4 = !(flags & SS_FLAG_FRAMING_LITERAL) && L % 4 == 0 && S % 4 == 0 && n % 4 == 0 && L / 4 < (1 << 20) && S / 4 < (1 << 20) &&
+                  reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  if (v4) {
+    const int64_t blocks = std::min<int64_t>((T + kSfFrames - 1) / kSfFrames, 32LL * kSmCountGuess);
+    k_stack_frames_v4<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                                                                        n / 4, (int)(L / 4), (int)(S / 4), T);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   int64_t blocks = (T * L + 255) / 256;
   if (blocks > 16LL * kSmCountGuess) blocks = 16LL * kSmCountGuess;
   k_stack_frames<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, L, S, T, flags);
@@ -386,13 +507,43 @@ int launch_cmvnw(const float* in, int64_t n_mats, int64_t rows, int64_t cols, in
 size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols) {
   const int64_t rpb = cmvn_rows_per_blk(n_mats, rows);
   const int64_t nblk = (rows + rpb - 1) / rpb;
-  return (size_t)n_mats * nblk * cols * 3 * sizeof(float);
+  // + the shape of an L2-sized batch of the same matrices (launch_cmvn): at most 8 x 148 + n_mats row blocks
+  return (size_t)(n_mats * nblk + 8 * kSmCountGuess + n_mats) * cols * 3 * sizeof(float);
 }
 
 int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int varnorm, float* out,
                 float* scratch, void* stream) {
   if (n_mats <= 0 || rows <= 0 || cols <= 0) return 0;
   if (cols > 256 || n_mats > 2147483647LL) return (int)cudaErrorInvalidValue;
+  // matrices that fit a warp's slice of shared memory: the fused one-read / one-write kernel
+  if (rows * cols <= 5120 && n_mats >= 64) {
+    const int n = (int)(rows * cols), R = cols <= 16 ? 32 / (int)cols : 1;
+    const int warp_floats = ((n + 3) & ~3) + (R + 2) * (int)cols + 4;
+    const size_t smem = (size_t)kCmvnSmallWarps * warp_floats * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_cmvn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    const int64_t blocks = std::min<int64_t>((n_mats + kCmvnSmallWarps - 1) / kCmvnSmallWarps, 8LL * kSmCountGuess);
+    k_cmvn_small<<<(unsigned)blocks, kCmvnSmallWarps * 32, smem, (cudaStream_t)stream>>>(in, out, n_mats, (int)rows, (int)cols, varnorm,
+                                                                                         warp_floats);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  // large matrices in batches of at most ~48 MB: the normalising pass then finds its batch in L2
+  {
+    const int64_t per_mat = rows * cols * (int64_t)sizeof(float);
+    const int64_t batch = std::max<int64_t>(1, (48LL << 20) / per_mat);
+    if (n_mats > batch) {
+      for (int64_t m0 = 0; m0 < n_mats; m0 += batch) {
+        const int64_t nm = std::min(batch, n_mats - m0);
+        const int e = launch_cmvn(in + m0 * rows * cols, nm, rows, cols, varnorm, out + m0 * rows * cols, scratch, stream);
+        if (e) return e;
+      }
+      return 0;
+    }
+  }
   const int64_t rpb = cmvn_rows_per_blk(n_mats, rows);
   const int nblk = (int)((rows + rpb - 1) / rpb);
   if (nblk > 65535) return (int)cudaErrorInvalidValue;

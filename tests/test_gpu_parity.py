@@ -361,6 +361,16 @@ def test_preemphasis():
         sb.preemphasis(x, 0, 0.98)
 
 
+def test_stack_frames_vector_path():
+    """L, S multiples of 4: the 16-byte kernel, including the zero-padded tail and a long signal"""
+    rng = np.random.default_rng(21)
+    for n, L, S, zp in [(16000, 400, 160, False), (16000, 400, 160, True), (1_000_004, 512, 256, True), (1_000_003, 512, 256, True), (5000, 64, 4, False), (776, 400, 160, True)]:
+        x = rng.standard_normal(n).astype(np.float32)
+        got = sb.processing.stack_frames(x, 16000, L / 16000, S / 16000, None, zp)
+        want = o.stack_frames(x, 16000, L / 16000, S / 16000, zp)
+        np.testing.assert_array_equal(got, want)
+
+
 def test_stack_frames():
     x = o.synth_signal(1, 100_000, 4)[0]
     for fl, fs, zp in [(0.02, 0.02, True), (0.025, 0.01, False), (0.025, 0.01, True), (0.02, 0.01, False)]:
@@ -383,6 +393,12 @@ def test_power_spectrum():
     fr = o.synth_signal(33, 400, 8)
     for nfft in (512, 400, 1024, 2048, 480):
         assert_spec_close(sb.processing.power_spectrum(fr, nfft), o.power_spectrum(fr, nfft), what=f"power_spectrum {nfft}")
+    # n_fft = 512 runs on the register-FFT kernel (k_pspec512): every pruning case of the frame length, odd row counts
+    for L in (1, 2, 31, 32, 33, 257, 320, 399, 400, 401, 511, 512):
+        f = o.synth_signal(7, L, 100 + L)
+        f[3] = 0.0
+        assert_spec_close(sb.processing.power_spectrum(f, 512), o.power_spectrum(f, 512), what=f"power_spectrum L={L}")
+    assert sb.lib.ss_last_kernel_name() == b"k_pspec512"
     with pytest.raises(sb.SpeechsauceError):
         sb.processing.power_spectrum(fr, 256)  # frame longer than the FFT: ndrustfft panics
 
@@ -475,6 +491,18 @@ def test_cmvn():
     got = sb.cmvn(batch, True)
     for i in (0, 13, 39):
         np.testing.assert_allclose(got[i], o.cmvn(batch[i], True), atol=2e-5)
+    # many small matrices: the fused one-warp-per-matrix kernel (13 columns: two row groups; 100 columns: one)
+    for shape in [(300, 97, 13), (200, 50, 100), (129, 1, 7), (70, 31, 16), (64, 300, 17)]:
+        xb = (rng.standard_normal(shape) * 2 + 1).astype(np.float32)
+        for vn in (True, False):
+            got = sb.cmvn(xb, vn)
+            for i in (0, shape[0] // 2, shape[0] - 1):
+                np.testing.assert_allclose(got[i], o.cmvn(xb[i], vn), atol=2e-5, err_msg=f"{shape} {vn} {i}")
+    # several long matrices: L2-sized batches, shifted-sum statistics (a large offset must not hurt the variance)
+    long_ = (rng.standard_normal((5, 300_000, 13)) * 0.5 + 40).astype(np.float32)
+    got = sb.cmvn(long_, True)
+    for i in (0, 4):
+        np.testing.assert_allclose(got[i], o.cmvn(long_[i], True, np.float64), atol=2e-4)
     with pytest.raises(sb.SpeechsauceError):
         sb.cmvn(np.zeros((0, 4), np.float32))
 
