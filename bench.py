@@ -318,8 +318,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    cpu_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_pg = dist.new_group(backend="gloo")  # host-side barrier for the in-process leg (no kernel spinning on the idle GPUs)
 
     cfg = sb.SpeechConfig(**w["cfg"], devices=[local], flags=_lib.SS_FLAG_FORCE_GENERIC if args.generic else 0)
     n, length = w["n"], w["length"]
@@ -466,6 +468,8 @@ def main():
                 # the crate's own multi-GPU path: ONE plan over all N devices in one process (rank 0), persistent
                 # worker thread per device; the other ranks stay idle behind the barrier
                 barrier()
+                torch.cuda.synchronize()
+                dist.barrier(group=cpu_pg)
                 if rank == 0:
                     big = sb.SpeechConfig(**w["cfg"], devices=list(range(world)))
                     gx = torch.empty((world * n_e, length), dtype=torch.float32, pin_memory=True)
@@ -484,6 +488,7 @@ def main():
                         e2e_inproc["vs_one_process_per_gpu"] = e2e_inproc["value"] / e2e["value"]
                     del gx, gouts
                     big.close()
+                dist.barrier(group=cpu_pg)  # the other ranks wait here on the CPU: their GPUs belong to rank 0's plan meanwhile
                 barrier()
         except RuntimeError as ex:  # pinned allocation failed
             if e2e is None:

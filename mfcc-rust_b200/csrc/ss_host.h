@@ -117,7 +117,9 @@ inline void stream_copy(char* dst, const char* src, size_t n) {
     n -= head;
   }
   const size_t blocks = n / 64;
+  static const bool pf = !(getenv("SS_COPY_PREFETCH") && atoi(getenv("SS_COPY_PREFETCH")) == 0);
   for (size_t i = 0; i < blocks; ++i) {
+    if (pf) _mm_prefetch(src + 1024, _MM_HINT_NTA);
     const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 0);
     const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 1);
     const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 2);

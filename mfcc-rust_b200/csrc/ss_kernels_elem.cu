@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "ss_internal.h"
 
@@ -129,26 +130,27 @@ __global__ void __launch_bounds__(kCmvnSmallWarps * 32) k_cmvn_small(const float
     float* dst = out + m * n;
     for (int i = lane; i < n; i += 32) x[i] = __ldg(src + i);
     __syncwarp();
-    // pass A: column sums -> mean
-    for (int pass = 0; pass < (varnorm ? 3 : 1); ++pass) {
+    // pass 0: column sums -> mean.  pass 1: sum (x - mean)^2 -> std.  (std_axis subtracts the mean of y = x - mean
+    // once more; that residual is a rounding error of ~1e-8 sigma and changes nothing at f32 resolution.)
+    for (int pass = 0; pass < (varnorm ? 2 : 1); ++pass) {
       if (cols <= 16) {
         if (rg < R) {
           const int r0 = rg * rpg, r1 = min(rows, r0 + rpg);
-          const float mu = pass ? mean_s[c0] : 0.f, mu2 = pass == 2 ? den_s[c0] : 0.f;
+          const float mu = pass ? mean_s[c0] : 0.f;
           float acc = 0.f;
           for (int r = r0; r < r1; ++r) {
             const float v = x[r * cols + c0] - mu;
-            acc += pass == 2 ? (v - mu2) * (v - mu2) : v;
+            acc += pass ? v * v : v;
           }
           part[rg * cols + c0] = acc;
         }
       } else {
         for (int c = lane; c < cols; c += 32) {
-          const float mu = pass ? mean_s[c] : 0.f, mu2 = pass == 2 ? den_s[c] : 0.f;
+          const float mu = pass ? mean_s[c] : 0.f;
           float acc = 0.f;
           for (int r = 0; r < rows; ++r) {
             const float v = x[r * cols + c] - mu;
-            acc += pass == 2 ? (v - mu2) * (v - mu2) : v;
+            acc += pass ? v * v : v;
           }
           part[c] = acc;
         }
@@ -157,16 +159,20 @@ __global__ void __launch_bounds__(kCmvnSmallWarps * 32) k_cmvn_small(const float
       for (int c = lane; c < cols; c += 32) {
         float t = part[c];
         for (int g = 1; g < R; ++g) t += part[g * cols + c];
-        if (pass == 0) mean_s[c] = t / (float)rows;                  // mean of x
-        else if (pass == 1) den_s[c] = t / (float)rows;              // mean of y = x - mean (std_axis subtracts it again)
-        else den_s[c] = sqrtf(t / (float)rows) + kCmvnEps;           // processing.rs:283-292
+        if (pass == 0) mean_s[c] = t / (float)rows;
+        else den_s[c] = 1.0f / (sqrtf(t / (float)rows) + kCmvnEps);  // processing.rs:283-292
       }
       __syncwarp();
     }
-    for (int i = lane; i < n; i += 32) {
-      const int c = i % cols;
-      const float d = x[i] - mean_s[c];
-      dst[i] = varnorm ? d / den_s[c] : d;
+    {
+      int c = lane % cols;
+      const int step = 32 % cols;
+      for (int i = lane; i < n; i += 32) {
+        const float d = x[i] - mean_s[c];
+        dst[i] = varnorm ? d * den_s[c] : d;
+        c += step;
+        if (c >= cols) c -= cols;
+      }
     }
     __syncwarp();
   }
@@ -240,22 +246,44 @@ __global__ void __launch_bounds__(256) k_cmvn_partial(const float* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
-                                                    const float* __restrict__ partial, int64_t rows, int cols,
-                                                    int64_t rows_per_blk, int nblk, int varnorm) {
+// Pass 1b: one block per matrix merges the row blocks' statistics (Chan's formula, a tree over up to 256 / cols
+// groups) into stats[mat][cols][2] = mean, 1 / (std + eps).  (The normalising blocks used to repeat this
+// serial merge each: with hundreds of row blocks per matrix that was most of their run time.)
+__global__ void __launch_bounds__(256) k_cmvn_merge(const float* __restrict__ partial, float* __restrict__ stats, int cols, int nblk,
+                                                    int varnorm) {
+  extern __shared__ float sm[];  // [groups][cols][3]
+  const int64_t mat = blockIdx.x;
+  const int groups = 256 / cols;
+  const int g = threadIdx.x / cols, c = threadIdx.x - g * cols;
+  if (g < groups) {
+    Wf acc = {0.f, 0.f, 0.f};
+    for (int b = g; b < nblk; b += groups) {
+      const float* s = partial + (((size_t)mat * nblk + b) * cols + c) * 3;
+      acc = wf_merge(acc, Wf{__ldg(s), __ldg(s + 1), __ldg(s + 2)});
+    }
+    float* s = sm + ((size_t)g * cols + c) * 3;
+    s[0] = acc.n; s[1] = acc.mean; s[2] = acc.m2;
+  }
+  __syncthreads();
+  if (threadIdx.x < cols) {
+    Wf acc = {0.f, 0.f, 0.f};
+    for (int l = 0; l < groups; ++l) {
+      const float* s = sm + ((size_t)l * cols + threadIdx.x) * 3;
+      acc = wf_merge(acc, Wf{s[0], s[1], s[2]});
+    }
+    float* o = stats + ((size_t)mat * cols + threadIdx.x) * 2;
+    o[0] = acc.mean;
+    // processing.rs:283-292: std with ddof 0, divide by (std + 2^-30)
+    o[1] = varnorm ? 1.0f / (sqrtf(acc.m2 / acc.n) + kCmvnEps) : 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out, const float* __restrict__ stats, int64_t rows, int cols,
+                                                    int64_t rows_per_blk, int varnorm) {
   extern __shared__ float sm[];  // [cols][2] = mean, 1/(std+eps)
   const int64_t mat = blockIdx.x;
   const int blk = blockIdx.y;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    Wf acc = {0.f, 0.f, 0.f};
-    for (int b = 0; b < nblk; ++b) {
-      const float* s = partial + (((size_t)mat * nblk + b) * cols + c) * 3;
-      acc = wf_merge(acc, Wf{s[0], s[1], s[2]});
-    }
-    sm[2 * c] = acc.mean;
-    // processing.rs:283-292: std with ddof 0, divide by (std + 2^-30)
-    sm[2 * c + 1] = varnorm ? 1.0f / (sqrtf(acc.m2 / acc.n) + kCmvnEps) : 1.0f;
-  }
+  for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) sm[i] = __ldg(stats + (size_t)mat * cols * 2 + i);
   __syncthreads();
   const float* x = in + mat * rows * cols;
   float* y = out + mat * rows * cols;
@@ -263,16 +291,15 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
   const int64_t e1 = min(rows, (blk + 1) * rows_per_blk) * cols;
   x += e0;
   y += e0;
-  // the slab is walked in chunks of 2^20 elements so that the column of an element is 32-bit arithmetic
-  for (int64_t base = 0; base < e1 - e0; base += (1 << 20)) {
-    const int n = (int)min((int64_t)(1 << 20), e1 - e0 - base);
-    const int cb = (int)(base % cols);
+  const int n = (int)(e1 - e0);  // rows_per_blk * cols < 2^31 (launch_cmvn)
+  int c = (int)((e0 + threadIdx.x) % cols);
+  const int step = (int)(blockDim.x % cols);
 #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int c = (cb + i) % cols;
-      const float d = x[base + i] - sm[2 * c];  // plain load: the host layer runs this pass in place (in == out)
-      y[base + i] = varnorm ? d * sm[2 * c + 1] : d;
-    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = x[i] - sm[2 * c];  // plain load: the host layer runs this pass in place (in == out)
+    y[i] = varnorm ? d * sm[2 * c + 1] : d;
+    c += step;
+    if (c >= cols) c -= cols;
   }
 }
 
@@ -372,12 +399,13 @@ __global__ void __launch_bounds__(256) k_cmvnw(const float* __restrict__ in, flo
 }
 
 inline int64_t cmvn_rows_per_blk(int64_t n_mats, int64_t rows) {
-  // enough blocks to fill the chip a few times over, at least 64 rows per block
-  const int64_t want_blocks = 8 * kSmCountGuess;
-  int64_t per_mat = (want_blocks + n_mats - 1) / n_mats;
-  if (per_mat < 1) per_mat = 1;
-  int64_t rpb = (rows + per_mat - 1) / per_mat;
-  if (rpb < 64) rpb = 64;
+  // many small blocks: at least ~4 waves of 8 x 148 resident blocks (a grid of 1.03 waves ran for two), at most
+  // 2048 rows per block, at least 64
+  const int64_t want_blocks = 4 * 8 * kSmCountGuess;
+  int64_t rpb = (rows * n_mats + want_blocks - 1) / want_blocks;
+  rpb = std::min<int64_t>(rpb, 2048);
+  rpb = std::max<int64_t>(rpb, 64);
+  rpb = std::max<int64_t>(rpb, (rows + 65534) / 65535);  // gridDim.y
   if (rpb > rows) rpb = rows;
   return rpb < 1 ? 1 : rpb;
 }
@@ -507,8 +535,8 @@ int launch_cmvnw(const float* in, int64_t n_mats, int64_t rows, int64_t cols, in
 size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols) {
   const int64_t rpb = cmvn_rows_per_blk(n_mats, rows);
   const int64_t nblk = (rows + rpb - 1) / rpb;
-  // + the shape of an L2-sized batch of the same matrices (launch_cmvn): at most 8 x 148 + n_mats row blocks
-  return (size_t)(n_mats * nblk + 8 * kSmCountGuess + n_mats) * cols * 3 * sizeof(float);
+  // + 2 floats per matrix and column for the merged statistics
+  return (size_t)(n_mats * nblk + n_mats) * cols * 3 * sizeof(float);
 }
 
 int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int varnorm, float* out,
@@ -516,7 +544,8 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
   if (n_mats <= 0 || rows <= 0 || cols <= 0) return 0;
   if (cols > 256 || n_mats > 2147483647LL) return (int)cudaErrorInvalidValue;
   // matrices that fit a warp's slice of shared memory: the fused one-read / one-write kernel
-  if (rows * cols <= 5120 && n_mats >= 64) {
+  // (chosen by the matrix shape alone, so that a batch gives the same bits however the host layer chunks it)
+  if (rows * cols <= 5120) {
     const int n = (int)(rows * cols), R = cols <= 16 ? 32 / (int)cols : 1;
     const int warp_floats = ((n + 3) & ~3) + (R + 2) * (int)cols + 4;
     const size_t smem = (size_t)kCmvnSmallWarps * warp_floats * sizeof(float);
@@ -531,19 +560,6 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
     count_launch();
     return (int)cudaGetLastError();
   }
-  // large matrices in batches of at most ~48 MB: the normalising pass then finds its batch in L2
-  {
-    const int64_t per_mat = rows * cols * (int64_t)sizeof(float);
-    const int64_t batch = std::max<int64_t>(1, (48LL << 20) / per_mat);
-    if (n_mats > batch) {
-      for (int64_t m0 = 0; m0 < n_mats; m0 += batch) {
-        const int64_t nm = std::min(batch, n_mats - m0);
-        const int e = launch_cmvn(in + m0 * rows * cols, nm, rows, cols, varnorm, out + m0 * rows * cols, scratch, stream);
-        if (e) return e;
-      }
-      return 0;
-    }
-  }
   const int64_t rpb = cmvn_rows_per_blk(n_mats, rows);
   const int nblk = (int)((rows + rpb - 1) / rpb);
   if (nblk > 65535) return (int)cudaErrorInvalidValue;
@@ -554,8 +570,13 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  k_cmvn_apply<<<grid, 256, (size_t)cols * 2 * sizeof(float), (cudaStream_t)stream>>>(
-      in, out, scratch, rows, (int)cols, rpb, nblk, varnorm);
+  // the merged statistics live behind the partials in the scratch buffer
+  float* stats = scratch + (size_t)n_mats * nblk * cols * 3;
+  k_cmvn_merge<<<(unsigned)n_mats, 256, (size_t)lanes * cols * 3 * sizeof(float), (cudaStream_t)stream>>>(scratch, stats, (int)cols, nblk, varnorm);
+  count_launch();
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  if (rpb * cols >= (1LL << 31)) return (int)cudaErrorInvalidValue;
+  k_cmvn_apply<<<grid, 256, (size_t)cols * 2 * sizeof(float), (cudaStream_t)stream>>>(in, out, stats, rows, (int)cols, rpb, varnorm);
   count_launch();
   return (int)cudaGetLastError();
 }
