@@ -2,6 +2,7 @@
 //! window, DCT handler and STFT overlap memory of the reference struct live in the device-side
 //! `ss_plan`; the public scalar fields are kept so existing callers compile unchanged.
 use crate::ffi;
+use std::cell::RefCell;
 use std::ptr;
 
 pub(crate) fn check(code: i32) {
@@ -71,6 +72,12 @@ pub struct SpeechConfig {
     pub frame_size: usize,
     pub dc_elimination: bool,
     pub wnorm: f32,
+    /// the analysis window (reference config.rs:125,151-160), read back from the plan's tables
+    pub window: Vec<f32>,
+    /// the STFT overlap memory, `window_size - frame_size` samples (reference config.rs:126,162).  As in the
+    /// reference it is the state itself: `stft1/2` and `mel_spectrogram1/2` read it before the first row and leave
+    /// the memory after the last row in it; it is never reset behind the caller's back.
+    pub analysis_mem: RefCell<Vec<f32>>,
     pub(crate) plan: *mut ffi::ss_plan,
     /// frame length / step as `stack_frames` derives them (round, processing.rs:77-78)
     pub(crate) frame_len: usize,
@@ -88,14 +95,7 @@ impl Clone for SpeechConfig {
     /// a clone owns its own plan (and its own STFT overlap memory, copied like the RefCell clone)
     fn clone(&self) -> Self {
         let c = SpeechConfig::from_raw(self.raw);
-        let n = self.window_size.saturating_sub(self.frame_size);
-        if n > 0 && self.frame_size > 0 && 2 * self.frame_size <= self.window_size {
-            let mut mem = vec![0f32; n];
-            unsafe {
-                check(ffi::ss_plan_get_analysis_mem(self.plan, mem.as_mut_ptr(), n as i64));
-                check(ffi::ss_plan_set_analysis_mem(c.plan, mem.as_ptr(), n as i64));
-            }
-        }
+        *c.analysis_mem.borrow_mut() = self.analysis_mem.borrow().clone();
         c
     }
 }
@@ -163,6 +163,13 @@ impl SpeechConfig {
             frame_size: info.hop as usize,
             dc_elimination: raw.dc_elimination != 0,
             wnorm: info.wnorm,
+            window: {
+                let mut w = vec![0f32; raw.fft_points.max(0) as usize];
+                unsafe { check(ffi::ss_debug_window(plan, w.as_mut_ptr())) };
+                w
+            },
+            // config.rs:162: vec![0.0; window_size - frame_size] (empty where the reference's subtraction underflows)
+            analysis_mem: RefCell::new(vec![0f32; (raw.fft_points.max(0) as usize).saturating_sub(info.hop.max(0) as usize)]),
             plan,
             frame_len: info.frame_len as usize,
             frame_step: info.frame_step as usize,
@@ -173,5 +180,13 @@ impl SpeechConfig {
     pub fn builder() -> SpeechConfigBuilder { SpeechConfigBuilder::default() }
 
     /// explicit form of the hidden STFT state (reference: `analysis_mem`, never reset)
-    pub fn reset_analysis_mem(&self) { unsafe { check(ffi::ss_plan_set_analysis_mem(self.plan, ptr::null(), 0)) } }
+    pub fn reset_analysis_mem(&self) { self.analysis_mem.borrow_mut().iter_mut().for_each(|v| *v = 0.0) }
+
+    /// pointer handed to the C ABI as `analysis_mem_inout` (null when the STFT is undefined for this config, so that
+    /// the library reports the reference's panic condition itself)
+    pub(crate) fn analysis_mem_ptr(&self) -> *mut f32 {
+        let mut m = self.analysis_mem.borrow_mut();
+        let ok = self.frame_size > 0 && 2 * self.frame_size <= self.window_size && m.len() == self.window_size - self.frame_size;
+        if ok { m.as_mut_ptr() } else { ptr::null_mut() }
+    }
 }

@@ -2,7 +2,6 @@
 use crate::config::{check, SpeechConfig};
 use crate::ffi;
 use ndarray::{Array1, Array2, Array3, ArrayView1, ArrayView2};
-use std::ptr;
 
 fn frames(cfg: &SpeechConfig, n: usize) -> usize {
     let t = unsafe { ffi::ss_num_frames(n as i64, cfg.frame_len as i64, cfg.frame_step as i64, 0) };
@@ -64,7 +63,7 @@ pub fn mel_spectrogram2(signal: ArrayView2<f32>, cfg: &SpeechConfig) -> Array3<f
     let (ch, ttd) = x.dim();
     let tp = unsafe { ffi::ss_stft_num_frames(ttd as i64, cfg.frame_size as i64) }.max(0) as usize;
     let mut out = Array3::<f32>::zeros((ch, cfg.num_filters, tp));
-    unsafe { check(ffi::ss_mel_spectrogram(cfg.plan, x.as_ptr(), ch as i64, ttd as i64, ttd as i64, out.as_mut_ptr(), ptr::null_mut(), 0)) };
+    unsafe { check(ffi::ss_mel_spectrogram(cfg.plan, x.as_ptr(), ch as i64, ttd as i64, ttd as i64, out.as_mut_ptr(), cfg.analysis_mem_ptr(), 0)) };
     out
 }
 
@@ -87,7 +86,7 @@ pub fn mel_spectrogram1(signal: ArrayView1<f32>, cfg: &SpeechConfig) -> Array2<f
     let ttd = x.len();
     let tp = unsafe { ffi::ss_stft_num_frames(ttd as i64, cfg.frame_size as i64) }.max(0) as usize;
     let mut out = Array2::<f32>::zeros((cfg.num_filters, tp));
-    unsafe { check(ffi::ss_mel_spectrogram(cfg.plan, x.as_ptr(), 1, ttd as i64, ttd as i64, out.as_mut_ptr(), ptr::null_mut(), 0)) };
+    unsafe { check(ffi::ss_mel_spectrogram(cfg.plan, x.as_ptr(), 1, ttd as i64, ttd as i64, out.as_mut_ptr(), cfg.analysis_mem_ptr(), 0)) };
     out
 }
 

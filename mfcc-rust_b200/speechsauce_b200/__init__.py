@@ -8,7 +8,7 @@ from functools import lru_cache
 
 import numpy as np
 
-from . import config, feature, functions, hostmem, processing  # noqa: F401
+from . import config, device, feature, functions, hostmem, processing  # noqa: F401
 from ._lib import LIB_PATH, SpeechsauceError, lib  # noqa: F401
 from .config import SpeechConfig, SpeechConfigBuilder  # noqa: F401
 from .processing import cmvn, preemphasis  # noqa: F401

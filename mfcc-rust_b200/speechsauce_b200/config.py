@@ -33,6 +33,7 @@ class SpeechConfig:
                                    self.num_cepstral, self.num_filters, self.low_frequency,
                                    self.high_frequency, int(self.dc_elimination), int(flags), float(dct2_scale))
         self._plan = C.c_void_p()
+        self.devices = None if devices is None else [int(d) for d in devices]
         if devices is None:          # every visible device (fails loudly when there is none)
             dev_arr, n = None, -1
         else:                        # explicit list; [] = host-only plan (tables / frame counts only)

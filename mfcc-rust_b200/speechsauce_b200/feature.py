@@ -24,6 +24,18 @@ def _rows(signal):
     return np.ascontiguousarray(x), one  # as_standard_layout(), SURVEY 8(b)
 
 
+def _mem(analysis_mem, cfg):
+    """the caller-held STFT overlap memory (config.rs:126): exactly W - H float32, C-contiguous; the library reads
+    and writes that many floats through the pointer, so anything else is refused here"""
+    if analysis_mem is None:
+        return None
+    m = analysis_mem
+    want = cfg.window_size - cfg.frame_size
+    if not isinstance(m, np.ndarray) or m.dtype != np.float32 or not m.flags.c_contiguous or not m.flags.writeable or m.size != want:
+        raise ValueError(f"analysis_mem must be a writable C-contiguous float32 array of window_size - frame_size = {want} elements")
+    return m
+
+
 def _frames(cfg, clip_len):
     T = lib.ss_num_frames(clip_len, cfg.frame_sample_length, cfg.frame_step, 0)
     return T
@@ -100,7 +112,7 @@ def mel_spectrogram2(signal, cfg, *, log=False, analysis_mem=None):
     Tp = max(0, lib.ss_stft_num_frames(ttd, max(cfg.frame_size, 1)))
     out = np.empty((ch, cfg.num_filters, Tp), np.float32)
     check(lib.ss_mel_spectrogram(cfg.plan, _lib.fptr(x), ch, ttd, ttd, _lib.fptr(out),
-                                 _lib.fptr(analysis_mem), int(log)))
+                                 _lib.fptr(_mem(analysis_mem, cfg)), int(log)))
     return out
 
 

@@ -18,7 +18,8 @@ def stft2(signal, cfg, *, analysis_mem=None):
     ch, ttd = x.shape
     Tp = max(0, lib.ss_stft_num_frames(ttd, max(cfg.frame_size, 1)))
     out = np.empty((ch, Tp, cfg.freq_size), np.complex64)
-    check(lib.ss_stft(cfg.plan, _lib.fptr(x), ch, ttd, ttd, _lib.fptr(out), _lib.fptr(analysis_mem)))
+    from .feature import _mem
+    check(lib.ss_stft(cfg.plan, _lib.fptr(x), ch, ttd, ttd, _lib.fptr(out), _lib.fptr(_mem(analysis_mem, cfg))))
     return out
 
 

@@ -187,3 +187,57 @@ def test_dev_entry_points_on_two_streams_do_not_share_scratch():
     assert torch.equal(ps[0], ps[1])
     np.testing.assert_allclose(ps[0][5].cpu().numpy(), o.power_spectrum(fr[5:6].cpu().numpy(), 600)[0], rtol=1e-4, atol=1e-6)
     assert sb.lib.ss_release_scratch() == 0
+
+
+def test_device_arrays_in_and_out_without_a_host_round_trip():
+    """`__cuda_array_interface__` inputs and outputs (torch tensors here, and a bare object
+    that carries nothing but the interface dict, standing in for cupy / numba)"""
+    torch = pytest.importorskip("torch")
+    x = o.synth_signal(9, 16000, 510)
+    xd = torch.from_numpy(x).cuda()
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], devices=[0])
+    host = sb.feature.features(x, cfg, cmvn_mode=2, **ALL)
+    dev = sb.device.features(xd, cfg, cmvn_mode=2, **ALL)
+    torch.cuda.synchronize()
+    for k in host:
+        assert dev[k].is_cuda and dev[k].__cuda_array_interface__["data"][0] == dev[k].data_ptr()
+        np.testing.assert_array_equal(host[k], dev[k].cpu().numpy(), err_msg=k)
+
+    class Bare:  # only the protocol
+        def __init__(self, t):
+            self._t = t
+            self.__cuda_array_interface__ = dict(t.__cuda_array_interface__)
+
+    s = torch.cuda.Stream()
+    one = sb.device.mfcc(Bare(xd[3]), cfg, stream=s)
+    s.synchronize()
+    np.testing.assert_array_equal(one.cpu().numpy(), sb.feature.mfcc(x[3], cfg))
+    y = o.synth_signal(3, 8000, 511)
+    c4 = sb.SpeechConfig(**CONFIGS["c4"], devices=[0])
+    m = sb.device.mel_spectrogram2(torch.from_numpy(y).cuda(), c4, log=True)
+    st = sb.device.stft2(torch.from_numpy(y).cuda(), c4)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(m.cpu().numpy(), sb.feature.mel_spectrogram2(y, sb.SpeechConfig(**CONFIGS["c4"], devices=[0]), log=True))
+    np.testing.assert_array_equal(torch.view_as_complex(st).cpu().numpy(), sb.functions.stft2(y, sb.SpeechConfig(**CONFIGS["c4"], devices=[0])))
+    f = torch.randn(5, 97, 13, device="cuda")
+    np.testing.assert_allclose(sb.device.cmvn(f, True).cpu().numpy()[2], o.cmvn(f[2].cpu().numpy(), True), atol=2e-5)
+    p = sb.device.preemphasis(xd[0])
+    np.testing.assert_array_equal(p.cpu().numpy(), o.preemphasis(x[0], 1, 0.98))
+    with pytest.raises(ValueError):
+        sb.device.features(xd.t(), cfg, mfcc=True)          # not C-contiguous
+    with pytest.raises(TypeError):
+        sb.device.features(xd.double(), cfg, mfcc=True)     # f32 only
+    with pytest.raises(TypeError):
+        sb.device.features(x, cfg, mfcc=True)               # a host array
+
+
+def test_analysis_mem_arguments_are_validated():
+    y = o.synth_signal(2, 8000, 512)
+    c4 = sb.SpeechConfig(**CONFIGS["c4"], devices=[0])
+    good = np.zeros(240, np.float32)
+    sb.functions.stft2(y, c4, analysis_mem=good)
+    for bad in (np.zeros(240, np.float64), np.zeros(239, np.float32), np.zeros(480, np.float32)[::2], [0.0] * 240):
+        with pytest.raises(ValueError):
+            sb.functions.stft2(y, c4, analysis_mem=bad)
+        with pytest.raises(ValueError):
+            sb.feature.mel_spectrogram2(y, c4, analysis_mem=bad)
