@@ -506,7 +506,7 @@ def main():
             xs = orc.synth_signal(cs, cl, 1)
             kw = {k: True for k in w["outs"]}
             cores = min(cores, cs)            # one clip (c1) is one thread's work: `cores` = the threads actually used
-            reps = 1 if cs >= 64 else 200     # the latency case is a millisecond of work: repeat it
+            reps = 200 if cs * cl <= 16000 * 64 else 1     # the latency case is a millisecond of work: repeat it
             oracle_c.features(xs[: max(1, cs // 8)], ccfg, cmvn_mode=w["cmvn"], n_threads=cores, **kw)
             t0 = time.perf_counter()
             for _ in range(reps):

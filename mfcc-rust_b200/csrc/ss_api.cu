@@ -567,6 +567,9 @@ static int copy_rows_h2d(float* dst, const float* src, int64_t rows, int64_t len
   if (rows == 0 || len == 0) return SS_OK;
   if (row_stride == len) {
     SS_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * len * sizeof(float), cudaMemcpyHostToDevice, s));
+  } else if (row_stride < len || rows == 1) {  // overlapping rows (the frame tiles of one long clip): a 2-D copy needs pitch >= width
+    for (int64_t r = 0; r < rows; ++r)
+      SS_CUDA(cudaMemcpyAsync(dst + r * len, src + r * row_stride, (size_t)len * sizeof(float), cudaMemcpyHostToDevice, s));
   } else {
     SS_CUDA(cudaMemcpy2DAsync(dst, len * sizeof(float), src, row_stride * sizeof(float), len * sizeof(float),
                               rows, cudaMemcpyHostToDevice, s));

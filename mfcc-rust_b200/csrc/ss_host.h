@@ -159,12 +159,20 @@ class CopyPool {
   TicketPtr copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows) {
     auto t = std::make_shared<Ticket>();
     if (rows == 0 || row_bytes == 0) return t;
+    if (rows * row_bytes <= (256u << 10)) {  // single clips: waking the pool costs more than the copy
+      for (size_t r = 0; r < rows; ++r) std::memcpy((char*)dst + r * dst_pitch, (const char*)src + r * src_pitch, row_bytes);
+      return t;
+    }
     std::vector<Task> tasks;
     const size_t piece = 2u << 20;
-    if (dst_pitch == row_bytes && src_pitch == row_bytes) {
+    if ((dst_pitch == row_bytes && src_pitch == row_bytes) || rows == 1) {
       const size_t total = rows * row_bytes;
       for (size_t o = 0; o < total; o += piece)
         tasks.push_back({(char*)dst + o, (const char*)src + o, std::min(piece, total - o), 1, 0, 0, t});
+    } else if (row_bytes >= piece) {  // long rows (the frame tiles of one stream): every row in pieces
+      for (size_t r = 0; r < rows; ++r)
+        for (size_t o = 0; o < row_bytes; o += piece)
+          tasks.push_back({(char*)dst + r * dst_pitch + o, (const char*)src + r * src_pitch + o, std::min(piece, row_bytes - o), 1, 0, 0, t});
     } else {
       const size_t rows_per = std::max<size_t>(1, piece / row_bytes);
       for (size_t r = 0; r < rows; r += rows_per)

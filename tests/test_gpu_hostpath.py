@@ -95,6 +95,12 @@ def test_frame_tiles_of_a_long_clip_match_the_whole_clip(cmvn_mode):
             np.testing.assert_array_equal(ref["mfcc"], got["mfcc"], err_msg=f"tile={tile}")
         else:
             np.testing.assert_allclose(got["mfcc"], ref["mfcc"], rtol=0, atol=2e-5, err_msg=f"tile={tile}")
+    # pinned input and outputs: the tiles (overlapping rows) are DMA'd in place
+    cfg = sb.SpeechConfig(**CONFIGS["c1"], devices=[0]).set_tuning(tile_frames=300)
+    got = sb.feature.features(_pinned_copy(x), cfg, cmvn_mode=cmvn_mode, empty=hostmem.pinned_empty, **ALL)
+    for k in ("mfe", "energy", "lmfe", "ssc"):
+        np.testing.assert_array_equal(ref[k], got[k], err_msg=f"{k} pinned tiles")
+    np.testing.assert_allclose(got["mfcc"], ref["mfcc"], rtol=0, atol=2e-5 if cmvn_mode else 0)
     # dc_elimination off: column 0 keeps the reference's frame-0-only scale across tiles
     kw = dict(CONFIGS["c1"], dc_elimination=False)
     ref = sb.feature.features(x, sb.SpeechConfig(**kw, devices=[0]), mfcc=True)["mfcc"]
