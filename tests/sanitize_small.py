@@ -60,4 +60,24 @@ sb.processing.stack_frames(x[0], 16000, 0.025, 0.01, None, True)
 sb.processing.power_spectrum(o.synth_signal(9, 400, 4), 512)
 sb.processing.cmvn(o.synth_signal(300, 13, 5), True)
 sb.processing.cmvn(o.synth_signal(4, 97 * 13, 6).reshape(4, 97, 13), True)
+# round 2: k_pspec512 (every pruning class), 16-byte stack_frames, one-warp cmvn, long cmvn with the merge kernel,
+# pinned buffers, frame tiles, the device-array API
+for L in (1, 33, 320, 400, 512):
+    sb.processing.power_spectrum(o.synth_signal(5, L, 20 + L), 512)
+sb.processing.stack_frames(o.synth_signal(1, 16000, 30)[0], 16000, 0.025, 0.01, None, False)
+sb.processing.stack_frames(o.synth_signal(1, 1003, 31)[0], 16000, 0.025, 0.01, None, True)
+sb.processing.cmvn(o.synth_signal(70, 97 * 13, 32).reshape(70, 97, 13), True)
+sb.processing.cmvn(o.synth_signal(3, 50 * 100, 33).reshape(3, 50, 100), False)
+sb.processing.cmvn(o.synth_signal(2, 20000 * 13, 34).reshape(2, 20000, 13), True)
+from speechsauce_b200 import hostmem  # noqa: E402
+xp = hostmem.pinned_empty(x.shape)
+xp[...] = x
+sb.feature.features(xp, cfg, lmfe=True, mfcc=True, cmvn_mode=2, empty=hostmem.pinned_empty)
+tiled = sb.SpeechConfig(**C1, devices=[0]).set_tuning(tile_frames=150, chunk_bytes=1 << 20)
+long_x = o.synth_signal(2, 16000 * 6 + 7, 35)
+for mode in (0, 2):
+    sb.feature.features(long_x, tiled, mfe=True, energy=True, lmfe=True, ssc=True, mfcc=True, cmvn_mode=mode)
+sb.device.features(dx[:40], cfg, lmfe=True, mfcc=True, cmvn_mode=1)
+sb.device.mel_spectrogram2(torch.from_numpy(o.synth_signal(2, 4001, 36)).cuda(), k4, log=True)
+torch.cuda.synchronize()
 print("sanitize_small: all kernels ran")
