@@ -113,6 +113,10 @@ int ss_host_register(void* ptr, size_t bytes); /* cudaHostRegister(portable): pi
 int ss_host_unregister(void* ptr);
 int ss_host_is_pinned(const void* ptr);        /* 1 when the library will DMA `ptr` in place */
 int ss_copy_threads(void);                     /* size of the staging copy pool */
+/* the staging pool's 2-D copy on its own (host memory only, usable without a device): `rows` rows of `row_bytes`,
+ * source rows `src_pitch` bytes apart (they may overlap: the frame tiles of a long clip), destination rows
+ * `dst_pitch` >= row_bytes apart; blocks until done */
+int ss_debug_copy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows);
 /* frees the per-(device, stream) scratch the config-less *_dev entry points keep between calls */
 int ss_release_scratch(void);
 

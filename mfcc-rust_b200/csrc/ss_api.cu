@@ -638,6 +638,13 @@ int ss_host_unregister(void* ptr) {
 }
 int ss_host_is_pinned(const void* ptr) { return ptr && host_ptr_is_pinned(ptr) ? 1 : 0; }
 int ss_copy_threads(void) { return CopyPool::instance().threads(); }
+int ss_debug_copy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows) {
+  if ((!dst || !src) && rows > 0 && row_bytes > 0) return fail(SS_ERR_INVALID_ARG, "null argument");
+  if (rows > 1 && (dst_pitch < row_bytes)) return fail(SS_ERR_INVALID_ARG, "destination rows overlap");
+  CopyPool& pool = CopyPool::instance();
+  pool.wait(pool.copy2d_async(dst, dst_pitch, src, src_pitch, row_bytes, rows));
+  return SS_OK;
+}
 int ss_release_scratch(void) {
   ScratchRegistry::instance().clear();
   return SS_OK;

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <map>
 #include <memory>
@@ -218,7 +219,7 @@ class CopyPool {
     std::lock_guard<std::mutex> lk(m_);
     if (q_.empty()) return false;
     *k = std::move(q_.front());
-    q_.erase(q_.begin());
+    q_.pop_front();
     return true;
   }
   static void run(const Task& k) {
@@ -239,14 +240,14 @@ class CopyPool {
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [&] { return !q_.empty(); });
         k = std::move(q_.front());
-        q_.erase(q_.begin());
+        q_.pop_front();
       }
       run(k);
     }
   }
   std::mutex m_;
   std::condition_variable cv_;
-  std::vector<Task> q_;
+  std::deque<Task> q_;
   std::vector<std::thread> th_;
 };
 

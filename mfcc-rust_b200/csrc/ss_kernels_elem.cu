@@ -549,10 +549,9 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
     const int n = (int)(rows * cols), R = cols <= 16 ? 32 / (int)cols : 1;
     const int warp_floats = ((n + 3) & ~3) + (R + 2) * (int)cols + 4;
     const size_t smem = (size_t)kCmvnSmallWarps * warp_floats * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_cmvn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
+    if (smem > 48 * 1024) {  // per device, so not cached in a static
+      cudaError_t ea = cudaFuncSetAttribute(k_cmvn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (ea != cudaSuccess) return (int)ea;
     }
     // more blocks than resident slots: the hardware scheduler balances the tail (exactly one wave measured 11 % slower)
     const int64_t blocks = std::min<int64_t>((n_mats + kCmvnSmallWarps - 1) / kCmvnSmallWarps, 8LL * kSmCountGuess);

@@ -68,6 +68,7 @@ extern "C" {
     pub fn ss_host_unregister(ptr: *mut c_void) -> c_int;
     pub fn ss_host_is_pinned(ptr: *const c_void) -> c_int;
     pub fn ss_copy_threads() -> c_int;
+    pub fn ss_debug_copy2d(dst: *mut c_void, dst_pitch: usize, src: *const c_void, src_pitch: usize, row_bytes: usize, rows: usize) -> c_int;
     pub fn ss_release_scratch() -> c_int;
     pub fn ss_plan_create(cfg: *const ss_config, devices: *const c_int, n_devices: c_int, out: *mut *mut ss_plan) -> c_int;
     pub fn ss_plan_destroy(plan: *mut ss_plan);

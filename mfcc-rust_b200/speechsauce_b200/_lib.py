@@ -68,6 +68,7 @@ SYMBOLS = {
     "ss_host_unregister": (C.c_int, [_vp]),
     "ss_host_is_pinned": (C.c_int, [_vp]),
     "ss_copy_threads": (C.c_int, []),
+    "ss_debug_copy2d": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t]),
     "ss_release_scratch": (C.c_int, []),
     "ss_plan_create": (C.c_int, [C.POINTER(ss_config), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "ss_plan_destroy": (None, [_vp]),

@@ -208,3 +208,35 @@ def test_python_mirror_keeps_the_py_speechsauce_signatures():
     assert [p for p in inspect.signature(sb.preemphasis).parameters][:3] == ["signal", "shift", "cof"]
     assert inspect.signature(sb.preemphasis).parameters["cof"].default == 0.98      # processing.rs:31-35
     assert set(sb.__all__) >= {"mfcc", "mel_spectrogram", "preemphasis", "cmvn"}
+
+
+def test_staging_copy_pool_matches_numpy_on_contiguous_strided_and_overlapping_rows():
+    """the copy pool that stages pageable caller memory (csrc/ss_host.h): runs without a device"""
+    import ctypes as C
+    import threading
+    rng = np.random.default_rng(5)
+    assert sb.lib.ss_copy_threads() >= 0
+    cases = [(1, 37, 37, 37), (1, 5_000_003, 5_000_003, 5_000_003),        # one short / one long row (pieces)
+             (300, 64000, 64000, 64000),                                  # dense rows (one flat copy)
+             (257, 64000, 64148, 64000), (13, 3_000_000, 3_000_016, 3_000_004),  # strided source / destination
+             (9, 400_000, 160_000, 400_000),                              # overlapping source rows: frame tiles with a halo
+             (1000, 52, 64, 52), (0, 10, 10, 10)]
+    for rows, row_bytes, spitch, dpitch in cases:
+        src = rng.integers(0, 256, max(1, (rows - 1) * spitch + row_bytes if rows else 1), dtype=np.uint8)
+        dst = np.zeros(max(1, (rows - 1) * dpitch + row_bytes if rows else 1), np.uint8)
+        _lib.check(sb.lib.ss_debug_copy2d(C.c_void_p(dst.ctypes.data), dpitch, C.c_void_p(src.ctypes.data), spitch, row_bytes, rows))
+        for r in (0, rows // 2, rows - 1) if rows else ():
+            np.testing.assert_array_equal(dst[r * dpitch:r * dpitch + row_bytes], src[r * spitch:r * spitch + row_bytes])
+        if rows and dpitch > row_bytes:
+            assert not dst[row_bytes:dpitch].any()        # the gaps between destination rows stay untouched
+    # several callers at once (the device workers of a multi-GPU plan share the pool)
+    big = [rng.integers(0, 256, 20_000_000, dtype=np.uint8) for _ in range(4)]
+    outs = [np.zeros_like(b) for b in big]
+    th = [threading.Thread(target=lambda b=b, o_=o_: _lib.check(sb.lib.ss_debug_copy2d(C.c_void_p(o_.ctypes.data), b.size, C.c_void_p(b.ctypes.data), b.size, b.size, 1)))
+          for b, o_ in zip(big, outs)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for b, o_ in zip(big, outs):
+        np.testing.assert_array_equal(b, o_)
+    with pytest.raises(sb.SpeechsauceError):
+        _lib.check(sb.lib.ss_debug_copy2d(C.c_void_p(outs[0].ctypes.data), 10, C.c_void_p(big[0].ctypes.data), 100, 100, 2))
