@@ -278,8 +278,26 @@ static void stft_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float*
   p->tab = dc->tab;
 }
 
+static DevBuf* plan_stream_scratch(DeviceCtx* dc, void* stream);
+
+// fft_points = 512: the register-FFT kernel + the banded mel kernel; the |X|^2 scratch lives per caller stream
+static int launch_stft512_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
+  if (pl->d.W != 512 || (pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC) || !(p.mel_out || p.stft_out)) return -1000;
+  float* scratch = nullptr;
+  if (p.mel_out) {
+    DevBuf* sb = plan_stream_scratch(dc, stream);
+    if (reserve(*sb, stft512_scratch_bytes(p, nullptr))) return (int)cudaErrorMemoryAllocation;
+    scratch = static_cast<float*>(sb->p);
+  }
+  return launch_stft512(p, scratch, dc->sm_count, stream);
+}
+
 // mel_spectrogram / stft launch: a size-specialised kernel when one exists, else the generic one
 static int launch_stft_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
+  {
+    const int e = launch_stft512_any(pl, dc, p, stream);
+    if (e != -1000) return e;
+  }
   if (pl->stft400m && dc->stft400m && (p.mel_out || p.stft_out) && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400m(p, dc->stft400m, dc->sm_count, stream);
     if (e != -1000) return e;
@@ -742,7 +760,7 @@ int ss_plan_get_info(const ss_plan* pl, ss_plan_info* info) {
   info->wnorm = d.wnorm;
   info->n_devices = (int32_t)pl->devs.size();
   info->fast_path = pl->fast512c && !(d.cfg.flags & (SS_FLAG_FORCE_GENERIC | SS_FLAG_FRAMING_LITERAL));
-  info->fast_stft = (pl->stft400m || pl->stft2048 || pl->stft2048m) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
+  info->fast_stft = (pl->stft400m || pl->stft2048 || pl->stft2048m || stft512_supported(d)) && !(d.cfg.flags & SS_FLAG_FORCE_GENERIC);
   return SS_OK;
 }
 
@@ -1085,6 +1103,10 @@ static void librosa_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const flo
 
 // the register-FFT kernel when n_fft = 400 (Whisper's front end), else the generic one
 static int launch_librosa_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
+  {
+    const int e = launch_stft512_any(pl, dc, p, stream);
+    if (e != -1000) return e;
+  }
   if (pl->stft400m && dc->stft400m && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400m(p, dc->stft400m, dc->sm_count, stream);
     if (e != -1000) return e;

@@ -158,6 +158,11 @@ int launch_stft2048m(const FrameParams& p, const Stft2048mTables* t, int sm_coun
 bool pspec512_supported(int64_t L, int64_t n_fft);
 int launch_pspec512(const float* frames, int64_t rows, int64_t L, float* out, void* stream);
 
+// fft_points == 512 on the STFT / librosa paths: register FFT + a banded mel kernel over a |X|^2 scratch (ss_kernels_stft512.cu)
+bool stft512_supported(const Derived& d);
+size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch);
+int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* stream);
+
 int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
                        int64_t shift, float cof, void* stream);
 int launch_stack_frames(const float* in, int64_t n, int64_t L, int64_t S, int64_t T, uint32_t flags,

@@ -1,0 +1,281 @@
+// fft_points = 512 on the STFT / librosa paths: functions::stft1/2 (functions.rs:86-233), feature::mel_spectrogram1/2
+// (feature.rs:151-174) and the librosa-compatible mel spectrogram for n_fft = 512.
+//
+// Two kernels instead of one fused one (the fused MMA epilogue of k_fast512c is tied to speechpy framing):
+//   k_stft512        one half-warp per frame: window, the 16 x 16 four-step register FFT of k_fast512c / k_pspec512,
+//                    real-FFT split; writes X wnorm (complex STFT output) and / or |X wnorm|^2 rows into a scratch.
+//                    Frames inside their row are loaded as float2; frames that touch the overlap memory, the previous
+//                    row, the zero padding (stream model, functions.rs:99-121) or the reflected edges (librosa mode)
+//                    fetch per sample through the same index formulas as k_frames_generic.
+//   k_mel_from_power banded mel reduction of 32 frames x all filters per block from those rows, time-minor store
+//                    [row][m][t] (feature.rs:173), ln(zero_handling) / power_to_db on request.
+// The |X|^2 scratch costs one extra write and read of 1 KB per frame; both kernels are HBM-bound, ~6 x the rate of the
+// any-length kernel.  Each filter sums its bins in index order, as the reference's einsum does.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "fft_ct.cuh"
+#include "ss_internal.h"
+
+namespace ss {
+
+namespace {
+
+using ssfft::sfor;
+
+constexpr int kWarps = 8;
+constexpr int kXs = 18;                       // transpose row stride in float2 (144 B: conflict-free LDS.128)
+constexpr int kXchFrame = 16 * kXs;
+constexpr int kWarpFloats = 2 * kXchFrame * 2;
+constexpr int kTwRow = 36;
+constexpr int kTabTw = 16 * kTwRow;
+constexpr int kW = 512, kF = 257;
+
+__device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
+
+// STFT stream model (functions.rs:86-170), as in k_frames_generic
+__device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
+  const int64_t memlen = p.N - p.S;
+  if (q < 0) return 0.f;
+  if (q < memlen) return p.mem_in ? p.mem_in[q] : 0.0f;
+  q -= memlen;
+  const int64_t span = p.Tp * (int64_t)p.S;
+  const int64_t r = q / span;
+  const int64_t o = q - r * span;
+  if (r >= p.n_rows || o >= p.row_len) return 0.0f;
+  return p.pcm[r * p.row_stride + o];
+}
+
+template <bool LIBROSA>
+__global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, const float* __restrict__ tw_tab, float* __restrict__ power,
+                                                          int64_t row0, int64_t n_rows) {
+  __shared__ __align__(16) float tw_s[kTabTw];
+  __shared__ __align__(16) float win_s[kW];
+  __shared__ __align__(16) float xch_s[kWarps * kWarpFloats];
+  for (int i = threadIdx.x; i < kTabTw; i += kWarps * 32) tw_s[i] = __ldg(tw_tab + i);
+  for (int i = threadIdx.x; i < kW; i += kWarps * 32) win_s[i] = __ldg(p.tab.window + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fi = lane >> 4, u = lane & 15;
+  const bool isz = (u == 0);
+  const int partner = (lane & 16) | ((16 - u) & 15);
+  const float4* twrow = reinterpret_cast<const float4*>(tw_s + u * kTwRow);
+  float2 wu;  // W512^u
+  sincospif(-(float)u / 256.0f, &wu.y, &wu.x);
+  float2* xch = reinterpret_cast<float2*>(xch_s + warp * kWarpFloats) + fi * kXchFrame;
+  const float2* win2 = reinterpret_cast<const float2*>(win_s) + u;  // window pairs (2m, 2m+1), m = u + 16 j
+
+  const int64_t T = p.T, T_out = p.T_out;
+  const int H = p.S;
+  const int64_t span = p.Tp * (int64_t)H;
+  const int64_t memlen = kW - H;
+  const int c0 = LIBROSA ? -kW / 2 : (p.n_pad + 1) * H - kW;  // first sample of frame 0 relative to its row
+  const float scale = 0.5f * p.wnorm;                           // the 1/2 of E', O' and functions.rs:166-169
+  const bool vec_ok = (H % 2 == 0) && (c0 % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
+  // frames of rows [row0, row0 + n_rows); the frames [T, T_out) of a row are the reference's zero tail
+  const int64_t pairs_per_row = (T_out + 1) >> 1;
+  const int64_t n_pairs = n_rows * pairs_per_row;
+  for (int64_t pr = (int64_t)blockIdx.x * kWarps + warp; pr < n_pairs; pr += (int64_t)gridDim.x * kWarps) {
+    const int64_t rl = pr / pairs_per_row;               // row within this launch
+    const int64_t row = row0 + rl;
+    const int64_t t = 2 * (pr - rl * pairs_per_row) + fi;
+    const bool stored = t < T_out;                        // an odd T_out leaves the last half-warp idle
+    const bool computed = t < T;
+    const float* rowp = p.pcm + row * p.row_stride;
+    const int64_t o0 = t * H + c0;
+    // ---- framing + window: v[j] = (x w)[2m] + i (x w)[2m+1], m = u + 16 j
+    float2 v[16];
+    if (!computed) {
+      sfor<0, 16>([&](auto jj) { v[decltype(jj)::value] = make_float2(0.f, 0.f); });
+    } else if (o0 >= 0 && o0 + kW <= p.row_len && vec_ok) {
+      const float* px = rowp + o0 + 2 * u;
+      sfor<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        v[j] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(px + 32 * j)), win2[16 * j]);
+      });
+    } else {
+      sfor<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float2 w = win2[16 * j];
+        float xs[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int64_t o = o0 + 2 * u + 32 * j + e;
+          if (LIBROSA) {  // librosa.stft(center=True, pad_mode="reflect")
+            if (o < 0) o = -o;
+            if (o >= p.row_len) o = 2 * (p.row_len - 1) - o;
+            xs[e] = rowp[o];
+          } else {
+            xs[e] = o >= 0 ? (o < p.row_len ? rowp[o] : 0.f) : stream_at(p, memlen + row * span + o);
+          }
+        }
+        v[j] = make_float2(xs[0] * w.x, xs[1] * w.y);
+      });
+    }
+    // ---- 256-point complex FFT: 16-point FFT over j, twiddle W256^{u k1}, transpose, 16-point FFT over the lanes
+    ssfft::fft_pow2<16>(v);
+    sfor<0, 8>([&](auto kk) {
+      constexpr int k1 = 2 * decltype(kk)::value;
+      const float4 w = twrow[k1 / 2];
+      float2 y0 = v[k1], y1 = v[k1 + 1];
+      if constexpr (k1 > 0) y0 = ssfft::cmulf(y0, make_float2(w.x, w.y));
+      y1 = ssfft::cmulf(y1, make_float2(w.z, w.w));
+      xch[k1 * kXs + u] = y0;
+      xch[(k1 + 1) * kXs + u] = y1;
+    });
+    __syncwarp();
+    float2 gg[16];
+    {
+      const float4* r4 = reinterpret_cast<const float4*>(xch + u * kXs);
+      sfor<0, 8>([&](auto tt) {
+        constexpr int i = decltype(tt)::value;
+        const float4 x = r4[i];
+        gg[2 * i] = make_float2(x.x, x.y);
+        gg[2 * i + 1] = make_float2(x.z, x.w);
+      });
+    }
+    __syncwarp();
+    ssfft::fft_pow2<16>(gg);
+    // ---- real-FFT split: X[k] = xa / 2, X[256 - k] = conj(xb) / 2 for k = u + 16 k2
+    float2* srow = (p.stft_out && stored) ? p.stft_out + (row * T_out + t) * kF : nullptr;
+    float* prow = (power && computed) ? power + (rl * T + t) * kF : nullptr;
+    sfor<0, 8>([&](auto kk) {
+      constexpr int k2 = decltype(kk)::value;
+      float2 zb;
+      zb.x = __shfl_sync(0xffffffffu, gg[15 - k2].x, partner);
+      zb.y = __shfl_sync(0xffffffffu, gg[15 - k2].y, partner);
+      if (isz) zb = gg[(16 - k2) & 15];
+      const float2 za = gg[k2];
+      const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
+      const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
+      const float2 tt = ssfft::cmulf(ssfft::twmul<32, k2>(od), wu);
+      const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
+      const float2 Xa = make_float2(scale * xa.x, scale * xa.y), Xb = make_float2(scale * xb.x, -scale * xb.y);
+      const int ka = u + 16 * k2, kb = 256 - ka;
+      if (srow) {
+        srow[ka] = Xa;
+        srow[kb] = Xb;
+      }
+      if (prow) {
+        prow[ka] = fmaf(Xa.x, Xa.x, Xa.y * Xa.y);  // feature.rs:164: |X|^2
+        prow[kb] = fmaf(Xb.x, Xb.x, Xb.y * Xb.y);
+      }
+    });
+    if (isz) {  // X[128] = conj Z[128]
+      const float2 X = make_float2(2.0f * scale * gg[8].x, -2.0f * scale * gg[8].y);
+      if (srow) srow[128] = X;
+      if (prow) prow[128] = fmaf(X.x, X.x, X.y * X.y);
+    }
+  }
+}
+
+// mel[row][m][t] = sum_k P[row][t][k] fb[m][k] for 32 frames x all filters per block
+constexpr int kMelFrames = 32;
+__global__ void __launch_bounds__(256) k_mel_from_power(const float* __restrict__ power, const FrameParams p, int64_t row0, int F) {
+  extern __shared__ float tile[];  // [32][F | 1]: an odd row stride keeps the column walks conflict-free
+  const int Fs = F | 1;
+  const int64_t rl = blockIdx.y;                           // row within this launch
+  const int64_t row = row0 + rl;
+  const int64_t t0 = (int64_t)blockIdx.x * kMelFrames;
+  const int nfr = (int)min((int64_t)kMelFrames, p.T - t0);  // computed frames in this tile (may be <= 0)
+  const float* src = power + (rl * p.T + t0) * F;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int f = warp; f < kMelFrames; f += 8) {  // a warp per frame row: coalesced, no index division
+    const float* s = src + (int64_t)f * F;
+    float* d = tile + f * Fs;
+    if (f < nfr)
+      for (int k = lane; k < F; k += 32) d[k] = __ldg(s + k);
+    else
+      for (int k = lane; k < F; k += 32) d[k] = 0.f;
+  }
+  __syncthreads();
+  const int64_t t = t0 + lane;
+  const float* trow = tile + lane * Fs;
+  for (int m = warp; m < p.nf; m += 8) {
+    const int b0 = __ldg(&p.tab.fstart[m]), len = __ldg(&p.tab.flen[m]);
+    const float* w = p.tab.fw + __ldg(&p.tab.fwofs[m]);
+    float acc = 0.f;
+    for (int q = 0; q < len; ++q) acc += trow[b0 + q] * __ldg(&w[q]);
+    float v;
+    if (t < p.T) {
+      if (p.log_mode == 2) v = 10.0f * log10f(fmaxf(acc, 1e-10f));  // librosa.power_to_db(ref=1, amin=1e-10, top_db=None)
+      else v = p.log_mode ? logf(zero_handling(acc)) : acc;
+    } else {
+      v = p.log_mode ? logf(kEps) : 0.f;  // the reference's zero tail
+    }
+    if (t < p.T_out) p.mel_out[(row * p.nf + m) * p.T_out + t] = v;
+  }
+}
+
+std::mutex g_mu;
+std::map<int, float*> g_tw;  // W256 table per device
+
+}  // namespace
+
+bool stft512_supported(const Derived& d) { return d.W == 512 && d.stft_ok; }
+
+// scratch: power rows of the rows of one launch; sized by stft512_scratch_bytes for `rows_per_launch` rows
+size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch) {
+  const int64_t per_row = std::max<int64_t>(1, p.T) * kF * (int64_t)sizeof(float);
+  int64_t rpl = std::max<int64_t>(1, (256LL << 20) / per_row);
+  rpl = std::min<int64_t>(rpl, std::max<int64_t>(1, p.n_rows));
+  rpl = std::min<int64_t>(rpl, 65535);  // gridDim.y of the mel kernel
+  if (rows_per_launch) *rows_per_launch = rpl;
+  return (size_t)(rpl * per_row);
+}
+
+int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* stream) {
+  if (p.N != kW || p.n_rows <= 0 || p.T_out <= 0) return p.N != kW ? -1000 : 0;
+  if (p.mel_out && !scratch) return -1000;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  const float* tw = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    float*& t = g_tw[dev];
+    if (!t) {
+      std::vector<float> h(kTabTw, 0.f);
+      const double pi = 3.14159265358979323846264338327950288;
+      for (int u = 0; u < 16; ++u)
+        for (int k1 = 0; k1 < 16; ++k1) {
+          const double ang = -2.0 * pi * (double)(u * k1) / 256.0;
+          h[u * kTwRow + 2 * k1] = (float)std::cos(ang);
+          h[u * kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
+        }
+      if ((e = cudaMalloc(&t, kTabTw * sizeof(float))) != cudaSuccess) return (int)e;
+      if ((e = cudaMemcpy(t, h.data(), kTabTw * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    }
+    tw = t;
+  }
+  const bool librosa = p.mode == kModeLibrosa;
+  int64_t rpl = p.n_rows;
+  if (p.mel_out) stft512_scratch_bytes(p, &rpl);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t mel_smem = (size_t)kMelFrames * (kF | 1) * sizeof(float);
+  for (int64_t r0 = 0; r0 < p.n_rows; r0 += rpl) {
+    const int64_t nr = std::min(rpl, p.n_rows - r0);
+    const int64_t pairs = nr * ((p.T_out + 1) / 2);
+    const int64_t grid = std::min<int64_t>((pairs + kWarps - 1) / kWarps, 16LL * sm_count);
+    float* pw = p.mel_out ? scratch : nullptr;
+    if (librosa) k_stft512<true><<<(unsigned)grid, kWarps * 32, 0, s>>>(p, tw, pw, r0, nr);
+    else k_stft512<false><<<(unsigned)grid, kWarps * 32, 0, s>>>(p, tw, pw, r0, nr);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    if (p.mel_out) {
+      dim3 g((unsigned)((p.T_out + kMelFrames - 1) / kMelFrames), (unsigned)nr);
+      k_mel_from_power<<<g, 256, mel_smem, s>>>(scratch, p, r0, kF);
+      count_launch();
+      if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    }
+  }
+  note_kernel("k_stft512");
+  return 0;
+}
+
+}  // namespace ss

@@ -19,7 +19,7 @@ fn main() {
         println!("cargo:rustc-link-search=native={}", dir);
     } else {
         let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-        let sources = ["ss_api.cu", "ss_tables.cpp", "ss_kernels_generic.cu", "ss_kernels_elem.cu", "ss_kernels_fast512c.cu", "ss_kernels_pspec512.cu", "ss_kernels_stft400m.cu",
+        let sources = ["ss_api.cu", "ss_tables.cpp", "ss_kernels_generic.cu", "ss_kernels_elem.cu", "ss_kernels_fast512c.cu", "ss_kernels_pspec512.cu", "ss_kernels_stft512.cu", "ss_kernels_stft400m.cu",
                        "ss_kernels_stft2048.cu", "ss_kernels_stft2048m.cu"];
         let mut cmd = Command::new(&nvcc);
         cmd.args(["-O3", "-std=c++17", "-arch=sm_100a", "-lineinfo", "--expt-relaxed-constexpr", "-shared",

@@ -79,5 +79,12 @@ for mode in (0, 2):
     sb.feature.features(long_x, tiled, mfe=True, energy=True, lmfe=True, ssc=True, mfcc=True, cmvn_mode=mode)
 sb.device.features(dx[:40], cfg, lmfe=True, mfcc=True, cmvn_mode=1)
 sb.device.mel_spectrogram2(torch.from_numpy(o.synth_signal(2, 4001, 36)).cuda(), k4, log=True)
+# fft_points = 512 on the STFT / librosa paths (k_stft512 + k_mel_from_power): vector and per-sample frames, odd frame counts
+for H in (256, 160, 101):
+    k5 = sb.SpeechConfig(16000, 512, (H + 0.5) / 16000, 0.01, 13, 40, 0.0, 8000.0, devices=[0])
+    y5 = o.synth_signal(3, 4001, 37)
+    sb.functions.stft2(y5, k5)
+    sb.feature.mel_spectrogram2(y5, k5, log=True)
+sb.feature.melspectrogram_librosa(o.synth_signal(2, 5000, 38), sb.feature.librosa_config(16000, 512, 160, 80, devices=[0]), db=True)
 torch.cuda.synchronize()
 print("sanitize_small: all kernels ran")
