@@ -1107,6 +1107,12 @@ static int launch_librosa_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, 
     const int e = launch_stft512_any(pl, dc, p, stream);
     if (e != -1000) return e;
   }
+  if (pl->stft2048 && dc->stft2048 && pl->d.librosa && p.mel_out && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
+    DevBuf* sb = plan_stream_scratch(dc, stream);
+    if (reserve(*sb, stft2048_power_scratch_bytes(p, nullptr))) return (int)cudaErrorMemoryAllocation;
+    const int e = launch_stft2048_power(p, dc->stft2048, static_cast<float*>(sb->p), dc->sm_count, stream);
+    if (e != -1000) return e;
+  }
   if (pl->stft400m && dc->stft400m && !(pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC)) {
     const int e = launch_stft400m(p, dc->stft400m, dc->sm_count, stream);
     if (e != -1000) return e;

@@ -146,6 +146,9 @@ struct Stft2048Tables;
 int stft2048_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft2048Tables** out);
 void stft2048_free_tables(Stft2048Tables* t);
 int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count, void* stream);
+// librosa mode for n_fft == 2048: |X|^2 rows (all 1025 bins) + the banded mel kernel
+size_t stft2048_power_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch);
+int launch_stft2048_power(const FrameParams& p, const Stft2048Tables* t, float* scratch, int sm_count, void* stream);
 
 // second-generation fft_points == 2048 mel kernel: CTA-shared |X|^2 tile, mel on mma.sync TF32x3 (ss_kernels_stft2048m.cu)
 bool stft2048m_supported(const Derived& d, const MelBank& mb);
@@ -162,6 +165,7 @@ int launch_pspec512(const float* frames, int64_t rows, int64_t L, float* out, vo
 bool stft512_supported(const Derived& d);
 size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch);
 int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* stream);
+int launch_mel_from_power(const float* power, const FrameParams& p, int64_t row0, int64_t n_rows, int F, void* stream);
 
 int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
                        int64_t shift, float cof, void* stream);

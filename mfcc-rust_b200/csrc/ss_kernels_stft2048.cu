@@ -51,6 +51,8 @@ struct Stft2048Args {
   int rounds_per_row;
   int nit, tab_floats;
   int vec2;
+  int64_t row0 = 0;        // first row of this launch (MODE 2 runs in slabs of rows)
+  float* power = nullptr;  // MODE 2: [rows of the slab][T][1025]
 };
 
 __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
@@ -65,8 +67,12 @@ __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
   return p.pcm[r * p.row_stride + o];
 }
 
-template <bool STFT>  // STFT: complex output of functions::stft1/2 instead of the mel spectrogram
+// MODE 0: fused banded mel (first generation; serves shapes k_stft2048m declines).  MODE 1: complex output of
+// functions::stft1/2.  MODE 2: |X wnorm|^2 rows of all 1025 bins into a scratch for k_mel_from_power (the librosa-
+// compatible mode, whose Slaney bank spans the whole spectrum); framing by p.mode: stream model or centred / reflected.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) {
+  constexpr bool STFT = MODE != 0;
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
   float* warp_s = smem + a.tab_floats + (threadIdx.x >> 5) * kWarpFloats;
@@ -90,12 +96,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
 
   const int64_t span = p.Tp * (int64_t)p.S;
   const int64_t memlen = p.N - p.S;
-  const int c0 = (p.n_pad + 1) * p.S - p.N;
+  const bool librosa = p.mode == kModeLibrosa;
+  const int c0 = librosa ? -kW / 2 : (p.n_pad + 1) * p.S - p.N;
   float* stash = stash0;
 
   for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-    const int64_t row = item / a.rounds_per_row;
-    const int64_t t_round = (item - row * a.rounds_per_row) * kFpr;
+    const int64_t row = a.row0 + item / a.rounds_per_row;
+    const int64_t t_round = (item - (row - a.row0) * a.rounds_per_row) * kFpr;
     const float* rowp = p.pcm + row * p.row_stride;
 
 #pragma unroll 1
@@ -123,8 +130,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
             constexpr int j = decltype(jj)::value;
             const float2 w = win2[32 * j];
             const int64_t o = o0 + 2 * u + 64 * j;
-            const float xa = o >= 0 ? (o < p.row_len ? rowp[o] : 0.f) : stream_at(p, q0 + 64 * j);
-            const float xb = o + 1 >= 0 ? (o + 1 < p.row_len ? rowp[o + 1] : 0.f) : stream_at(p, q0 + 64 * j + 1);
+            float xa, xb;
+            if (librosa) {  // librosa.stft(center=True, pad_mode="reflect")
+              int64_t oa = o, ob = o + 1;
+              if (oa < 0) oa = -oa;
+              if (ob < 0) ob = -ob;
+              if (oa >= p.row_len) oa = 2 * (p.row_len - 1) - oa;
+              if (ob >= p.row_len) ob = 2 * (p.row_len - 1) - ob;
+              xa = rowp[oa];
+              xb = rowp[ob];
+            } else {
+              xa = o >= 0 ? (o < p.row_len ? rowp[o] : 0.f) : stream_at(p, q0 + 64 * j);
+              xb = o + 1 >= 0 ? (o + 1 < p.row_len ? rowp[o + 1] : 0.f) : stream_at(p, q0 + 64 * j + 1);
+            }
             v[j] = make_float2(xa * w.x, xb * w.y);
           });
         }
@@ -171,7 +189,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
         const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
         const float2 tt = ssfft::cmulf(od, w);
         const float2 xa = ssfft::cadd(e, tt);  // 2 X[k]
-        if constexpr (STFT) {
+        if constexpr (MODE == 2) {
+          if (computed) {
+            float* po = a.power + ((row - a.row0) * p.T + t) * (int64_t)(kM + 1);
+            const float2 xb = ssfft::csub(e, tt);
+            const float hs2 = 0.25f * p.wnorm * p.wnorm;
+            po[u + 32 * k2] = hs2 * fmaf(xa.x, xa.x, xa.y * xa.y);
+            po[kM - (u + 32 * k2)] = hs2 * fmaf(xb.x, xb.x, xb.y * xb.y);
+          }
+        } else if constexpr (STFT) {
           // [row][T_out][1025] (re, im): X wnorm (functions.rs:166-169); zeros in the reference's zero tail (v = 0)
           if (t < p.T_out) {
             float2* so = p.stft_out + (row * p.T_out + t) * (int64_t)(kM + 1);
@@ -184,7 +210,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048(const Stft2048Args a) 
           pA[32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
         }
       });
-      if constexpr (STFT) {
+      if constexpr (MODE == 2) {
+        if (isz && computed)  // X[512] = conj Z[512]
+          a.power[((row - a.row0) * p.T + t) * (int64_t)(kM + 1) + 512] = p.wnorm * p.wnorm * fmaf(g[16].x, g[16].x, g[16].y * g[16].y);
+        continue;
+      }
+      if constexpr (MODE == 1) {
         if (isz && t < p.T_out)  // X[512] = conj Z[512]
           p.stft_out[(row * p.T_out + t) * (int64_t)(kM + 1) + 512] = make_float2(g[16].x * p.wnorm, -g[16].y * p.wnorm);
         continue;
@@ -284,7 +315,9 @@ struct Stft2048Tables {
 };
 
 bool stft2048_supported(const Derived& d, const MelBank& mb) {
-  if (d.librosa || d.W != kW || !d.stft_ok || d.nf > kNfMax) return false;
+  if (d.W != kW || !d.stft_ok) return false;
+  if (d.librosa) return true;  // |X|^2 rows + k_mel_from_power: no mel program needed
+  if (d.nf > kNfMax) return false;
   MelProgram2048 mp;
   return build_program(d, mb, 1.0f, &mp);
 }
@@ -292,7 +325,11 @@ bool stft2048_supported(const Derived& d, const MelBank& mb) {
 int stft2048_build_tables(const Derived& d, const MelBank& mb, const std::vector<float>& window, Stft2048Tables** out) {
   MelProgram2048 mp;
   const float pscale = 0.25f * d.wnorm * d.wnorm;  // (1/2)^2 of E, O and wnorm^2 (functions.rs:166-169)
-  if (!build_program(d, mb, pscale, &mp)) return (int)cudaErrorInvalidValue;
+  if (d.librosa) {
+    mp = MelProgram2048();
+  } else if (!build_program(d, mb, pscale, &mp)) {
+    return (int)cudaErrorInvalidValue;
+  }
   std::vector<float> h(kTabFixed + (size_t)mp.nit * 32 * 6, 0.f);
   const double pi = 3.14159265358979323846264338327950288;
   for (int u = 0; u < kR; ++u)
@@ -329,6 +366,7 @@ void stft2048_free_tables(Stft2048Tables* t) {
 }
 
 int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count, void* stream) {
+  if (p.mode == kModeLibrosa) return -1000;                                     // launch_stft2048_power serves that mode
   if (p.N != kW || (!p.mel_out == !p.stft_out) || p.T_out < 1) return -1000;  // exactly one of the two outputs
   Stft2048Args a;
   a.p = p;
@@ -344,17 +382,59 @@ int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count,
   if (grid <= 0) return 0;
   cudaError_t e;
   if (p.stft_out) {
-    e = cudaFuncSetAttribute(k_stft2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(k_stft2048<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    k_stft2048<true><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
+    k_stft2048<1><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
   } else {
-    e = cudaFuncSetAttribute(k_stft2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(k_stft2048<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    k_stft2048<false><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
+    k_stft2048<0><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
   }
   count_launch();
   note_kernel("k_stft2048");
   return (int)cudaGetLastError();
+}
+
+// the librosa-compatible mel spectrogram for n_fft = 2048 (librosa's default): |X|^2 rows of a slab of rows into
+// `scratch` (stft2048_power_scratch_bytes), then k_mel_from_power (ss_kernels_stft512.cu) over the Slaney bank
+size_t stft2048_power_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch) {
+  const int64_t per_row = std::max<int64_t>(1, p.T) * (kM + 1) * (int64_t)sizeof(float);
+  int64_t rpl = std::max<int64_t>(1, (256LL << 20) / per_row);
+  rpl = std::min<int64_t>(rpl, std::max<int64_t>(1, p.n_rows));
+  rpl = std::min<int64_t>(rpl, 65535);
+  if (rows_per_launch) *rows_per_launch = rpl;
+  return (size_t)(rpl * per_row);
+}
+
+int launch_stft2048_power(const FrameParams& p, const Stft2048Tables* t, float* scratch, int sm_count, void* stream) {
+  if (p.N != kW || !p.mel_out || !scratch || p.T_out < 1 || p.n_rows <= 0) return -1000;
+  int64_t rpl = 1;
+  stft2048_power_scratch_bytes(p, &rpl);
+  Stft2048Args a;
+  a.p = p;
+  a.tab = t->d_tab;
+  a.nit = 0;
+  a.tab_floats = kTabFixed;  // no mel program behind the fixed tables
+  a.rounds_per_row = (int)((p.T_out + kFpr - 1) / kFpr);
+  a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0) &&
+           (p.mode != kModeLibrosa || (kW / 2) % 2 == 0);
+  a.power = scratch;
+  const size_t smem = (size_t)(a.tab_floats + kWarps * kWarpFloats) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(k_stft2048<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  for (int64_t r0 = 0; r0 < p.n_rows; r0 += rpl) {
+    const int64_t nr = std::min(rpl, p.n_rows - r0);
+    a.row0 = r0;
+    a.n_items = nr * (int64_t)a.rounds_per_row;
+    const int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sm_count);
+    k_stft2048<2><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(a);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    const int me = launch_mel_from_power(scratch, p, r0, nr, kM + 1, stream);
+    if (me) return me;
+  }
+  note_kernel("k_stft2048");
+  return 0;
 }
 
 }  // namespace ss

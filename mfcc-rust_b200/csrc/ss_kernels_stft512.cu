@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -174,18 +175,21 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
   }
 }
 
-// mel[row][m][t] = sum_k P[row][t][k] fb[m][k] for 32 frames x all filters per block
+// mel[row][m][t] = sum_k P[row][t][k] fb[m][k] for TF frames x all filters per block.  TF = 32 for F = 257 (33 KB tile);
+// TF = 16 for wide spectra (F = 1025: 66 KB, three blocks per SM), the two half-warps then taking alternate filters
 constexpr int kMelFrames = 32;
+template <int TF>
 __global__ void __launch_bounds__(256) k_mel_from_power(const float* __restrict__ power, const FrameParams p, int64_t row0, int F) {
-  extern __shared__ float tile[];  // [32][F | 1]: an odd row stride keeps the column walks conflict-free
+  extern __shared__ float tile[];  // [TF][F | 1]: an odd row stride keeps the column walks conflict-free
+  constexpr int kSub = 32 / TF;    // filters in flight per warp
   const int Fs = F | 1;
   const int64_t rl = blockIdx.y;                           // row within this launch
   const int64_t row = row0 + rl;
-  const int64_t t0 = (int64_t)blockIdx.x * kMelFrames;
-  const int nfr = (int)min((int64_t)kMelFrames, p.T - t0);  // computed frames in this tile (may be <= 0)
+  const int64_t t0 = (int64_t)blockIdx.x * TF;
+  const int nfr = (int)min((int64_t)TF, p.T - t0);  // computed frames in this tile (may be <= 0)
   const float* src = power + (rl * p.T + t0) * F;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int f = warp; f < kMelFrames; f += 8) {  // a warp per frame row: coalesced, no index division
+  for (int f = warp; f < TF; f += 8) {  // a warp per frame row: coalesced, no index division
     const float* s = src + (int64_t)f * F;
     float* d = tile + f * Fs;
     if (f < nfr)
@@ -194,9 +198,10 @@ __global__ void __launch_bounds__(256) k_mel_from_power(const float* __restrict_
       for (int k = lane; k < F; k += 32) d[k] = 0.f;
   }
   __syncthreads();
-  const int64_t t = t0 + lane;
-  const float* trow = tile + lane * Fs;
-  for (int m = warp; m < p.nf; m += 8) {
+  const int fl = lane % TF;
+  const int64_t t = t0 + fl;
+  const float* trow = tile + fl * Fs;
+  for (int m = warp * kSub + lane / TF; m < p.nf; m += 8 * kSub) {
     const int b0 = __ldg(&p.tab.fstart[m]), len = __ldg(&p.tab.flen[m]);
     const float* w = p.tab.fw + __ldg(&p.tab.fwofs[m]);
     float acc = 0.f;
@@ -216,6 +221,28 @@ std::mutex g_mu;
 std::map<int, float*> g_tw;  // W256 table per device
 
 }  // namespace
+
+template <int TF>
+static int launch_mel_tf(const float* power, const FrameParams& p, int64_t row0, int64_t n_rows, int F, void* stream) {
+  const size_t smem = (size_t)TF * (F | 1) * sizeof(float);
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_mel_from_power<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 g((unsigned)((p.T_out + TF - 1) / TF), (unsigned)n_rows);
+  k_mel_from_power<TF><<<g, 256, smem, (cudaStream_t)stream>>>(power, p, row0, F);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// banded mel reduction of `n_rows` rows of |X|^2 ([n_rows][p.T][F], rows row0.. of the call) into p.mel_out
+int launch_mel_from_power(const float* power, const FrameParams& p, int64_t row0, int64_t n_rows, int F, void* stream) {
+  if (n_rows <= 0 || p.T_out <= 0) return 0;
+  static const int tf_env = getenv("SS_MEL_TF") ? atoi(getenv("SS_MEL_TF")) : 0;  // A/B switch for measurements
+  const int tf = tf_env ? tf_env : (F > 512 ? 16 : kMelFrames);
+  return tf == 16 ? launch_mel_tf<16>(power, p, row0, n_rows, F, stream) : launch_mel_tf<kMelFrames>(power, p, row0, n_rows, F, stream);
+}
 
 bool stft512_supported(const Derived& d) { return d.W == 512 && d.stft_ok; }
 
@@ -257,7 +284,6 @@ int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* str
   int64_t rpl = p.n_rows;
   if (p.mel_out) stft512_scratch_bytes(p, &rpl);
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t mel_smem = (size_t)kMelFrames * (kF | 1) * sizeof(float);
   for (int64_t r0 = 0; r0 < p.n_rows; r0 += rpl) {
     const int64_t nr = std::min(rpl, p.n_rows - r0);
     const int64_t pairs = nr * ((p.T_out + 1) / 2);
@@ -268,10 +294,8 @@ int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* str
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     if (p.mel_out) {
-      dim3 g((unsigned)((p.T_out + kMelFrames - 1) / kMelFrames), (unsigned)nr);
-      k_mel_from_power<<<g, 256, mel_smem, s>>>(scratch, p, r0, kF);
-      count_launch();
-      if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+      const int me = launch_mel_from_power(scratch, p, r0, nr, kF, stream);
+      if (me) return me;
     }
   }
   note_kernel("k_stft512");

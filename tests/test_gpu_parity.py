@@ -627,6 +627,26 @@ def test_librosa_mode_n_fft_512_register_fft_kernel():
         assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what="librosa 512 power_to_db")
 
 
+def test_librosa_mode_n_fft_2048_register_fft_kernel():
+    """librosa's default n_fft: k_stft2048<power> -> |X|^2 rows of all 1025 bins -> k_mel_from_power over the Slaney bank."""
+    for sr, hop, n_mels, n, rows in [(22050, 512, 128, 22050 * 2 + 3, 3), (16000, 160, 80, 16000, 2), (44100, 1024, 64, 30001, 2),
+                                     (16000, 250, 40, 1100, 4), (22050, 512, 128, 2048, 1)]:
+        cfg = sb.feature.librosa_config(sr, 2048, hop, n_mels, 0.0, None)
+        assert cfg.info.fast_stft == 1
+        y = o.synth_signal(rows, n, 0x5EED2048 + hop)
+        got = sb.feature.melspectrogram_librosa(y, cfg)
+        assert sb.lib.ss_last_kernel_name() == b"k_stft2048"
+        want = o.librosa_melspectrogram(y, sr, 2048, hop, n_mels, 0.0, None)
+        assert got.shape == want.shape == (rows, n_mels, 1 + n // hop)
+        assert_spec_close(got, want, what=f"librosa 2048 mel hop {hop}")
+        gen = sb.feature.librosa_config(sr, 2048, hop, n_mels, 0.0, None, flags=_lib.SS_FLAG_FORCE_GENERIC)
+        assert_spec_close(got, sb.feature.melspectrogram_librosa(y, gen), what=f"librosa 2048 fast vs generic hop {hop}")
+        gdb = sb.feature.melspectrogram_librosa(y, cfg, db=True)
+        wdb = o.librosa_melspectrogram(y, sr, 2048, hop, n_mels, 0.0, None, db=True)
+        loud = want > 1e-6 * want.max()
+        assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what="librosa 2048 power_to_db")
+
+
 def test_stft_explicit_memory_equals_plan_memory_and_sharding_halo():
     kw = CONFIGS["c4"]
     x = o.synth_signal(8, 3200, 77)
