@@ -57,7 +57,8 @@ constexpr int kTabTw = 0;                          // [32][kTwRow]
 constexpr int kTabTw2048 = kTabTw + kR * kTwRow;   // [512] float2 W2048^k
 constexpr int kTabWin = kTabTw2048 + 2 * 512;      // [1024] float2 window pairs
 constexpr int kTabFixed = kTabWin + 2 * kM;        // 5248 floats
-constexpr int kMbarFloats = 2 * kWarps;            // one 8-byte mbarrier per warp (staged frames), after the tables
+constexpr int kMbarFloats = 2 * (kWarps + kGroups);  // one 8-byte mbarrier per warp (staged frames) and per group (tile complete), after the tables
+static_assert((kTabFixed + kMbarFloats) % 4 == 0, "the transpose tiles start 16-byte aligned");
 static_assert(kTabTw2048 % 4 == 0 && kTabWin % 4 == 0 && kTabFixed % 4 == 0, "table alignment");
 
 __device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
@@ -112,6 +113,24 @@ __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
   return p.pcm[r * p.row_stride + o];
 }
 
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned phase) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(phase)
+        : "memory");
+  } while (!done);
+}
+
+// The filterbank product of round r runs in the middle of round r + 1's FFT, at the one point where the
+// transform lives in shared memory (the transpose tile) and the registers are free.  A warp announces its tile
+// row on the group's mbarrier and carries on with the next frame's load, window and first FFT stage; only then
+// does it wait for the other seven rows, so the group tolerates ~40 % of a round of skew between its warps
+// instead of stalling all eight at a bar.sync per round.
 __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* tab_s = smem;
@@ -126,6 +145,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
     asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const unsigned gbar = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint64_t*>(smem + kTabFixed) + kWarps + (threadIdx.x >> 8));
+  if ((threadIdx.x & 255) == 0) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(gbar), "r"(kGroup) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned gphase = 0;  // parity of the group barrier phase the pending tile completes
   unsigned phase = 0;   // parity of the mbarrier phase the next staged frame completes
   bool staged = false;  // this round's frame sits in the transpose tile (requested during the previous round)
   int sshift = 0;       // ... starting at this float offset (the copy starts at the 16-byte boundary below the frame)
@@ -150,10 +175,92 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
   const int group = warp >> 3, wg = warp & 7;
   int buf = 0;
 
-  for (int64_t item = (int64_t)blockIdx.x * kGroups + group; item < a.n_items; item += (int64_t)gridDim.x * kGroups, buf ^= 1) {
-    const int64_t row = item / a.rounds_per_row;
-    const int64_t t_round = (item - row * a.rounds_per_row) * kFpr;
-    const float* rowp = p.pcm + row * p.row_stride;
+  // ---- mel filterbank on the tensor cores (feature.rs:163-174):
+  //   mel [8 frames][8 filters of n-tile nt] = P [8][band] x W^T,
+  // contraction slot t <-> bin 8 ks + t, slot t + 4 <-> bin 8 ks + 4 + t (two conflict-free 4-byte loads of P).
+  // An n-tile visits only the 8-bin k-steps its 8 filters' band touches; the bands widen with the filter
+  // index (1 .. 13 k-steps for the 128-filter bank), so a warp takes n-tile w and, beyond the first
+  // eight, NT - 1 - w: the widest with the narrowest (8 .. 14 k-steps per warp and round; with one m-tile
+  // of 16 filters per warp it was 2 .. 22, and every round waited for the last warp).
+  // Rows 8..15 of the A operand carry the low parts of the same frames: with A = [P_hi; P_lo] one MMA
+  // against W_hi yields hi x hi (rows 0..7) and lo x hi (rows 8..15), a second one against W_lo adds
+  // hi x lo (and the negligible lo x lo): two MMAs per k-step instead of three, no idle rows, and the split
+  // results are the operand registers as they are.
+  // The weight fragments come from L2 (the L1 left beside 227 KB of shared memory does not hold the 46 KB
+  // table): the FFT's registers are free at this point, so the first kPre double k-steps of a job are
+  // requested at once -- job 0's before the wait for the group's tile -- instead of one iteration ahead.
+  constexpr int kPre = 3;
+  auto mma_pair = [&](float (&accH)[4], float (&accL)[4], unsigned pp, const float4& w0, const float4& w1) {
+    const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 16));  // bins 8 ks + t, 8 ks + 4 + t
+    const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 48));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 pv = h ? pv1 : pv0;
+      const float4 w = h ? w1 : w0;
+      uint32_t ah0, al0, ah2, al2;
+      split_tf32(pv.x, ah0, al0);
+      split_tf32(pv.y, ah2, al2);
+      const float4 av = make_float4(__uint_as_float(ah0), __uint_as_float(al0), __uint_as_float(ah2), __uint_as_float(al2));
+      mma_tf32(accH, av, __float_as_uint(w.x), __float_as_uint(w.y));  // [hi; lo] x hi
+      mma_tf32(accL, av, __float_as_uint(w.z), __float_as_uint(w.w));  // [hi; lo] x lo
+    }
+  };
+  // out0: (frame t_round + g) of filter 0 in the time-minor output; fr_ok: that frame exists
+  auto mel_stage = [&](const float* tile, float* const out0, const bool fr_ok, unsigned wait_phase) {
+#pragma unroll 1
+    for (int job = 0; job < 2; ++job) {
+      const int nt = job == 0 ? wg : a.n_nt - 1 - wg;
+      const bool active = nt < a.n_nt && !(job == 1 && nt < kGroup);
+      const int n2 = active ? a.ks_n2[nt] : 0;
+      const float4* bp = a.mel_frag + (int64_t)(active ? a.mel_base[nt] : 0) * 32 + lane;
+      float4 wq[2 * kPre];
+      sfor<0, kPre>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        if (i < n2) { wq[2 * i] = __ldg(bp + 64 * i); wq[2 * i + 1] = __ldg(bp + 64 * i + 32); }
+      });
+      if (job == 0) mbar_wait(gbar, wait_phase);  // the group's eight tile rows are written
+      if (!active) continue;
+      float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
+      unsigned pp = (unsigned)__cvta_generic_to_shared(tile + g * kPs + t4 + 8 * a.ks_lo[nt]);
+      // a ring of kPre double k-steps: each slot is refilled kPre steps ahead as soon as it has been consumed
+#pragma unroll 1
+      for (int base = 0; base < n2; base += kPre) {
+        sfor<0, kPre>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          if (base + i < n2) {
+            mma_pair(accH, accL, pp + 64 * i, wq[2 * i], wq[2 * i + 1]);
+            if (base + i + kPre < n2) {
+              wq[2 * i] = __ldg(bp + 64 * (i + kPre));
+              wq[2 * i + 1] = __ldg(bp + 64 * (i + kPre) + 32);
+            }
+          }
+        });
+        pp += 64 * kPre;
+        bp += 64 * kPre;
+      }
+      // accumulator rows g / g + 8: (frame t_round + g, filters 8 nt + 2 t4 [+ 1]) from the high / low parts; the
+      // 8 lanes of a filter write 32 consecutive bytes of the time-minor output [row][m][t]
+      if (fr_ok) {
+        float* outp = out0 + (int64_t)(8 * nt + 2 * t4) * p.T_out;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float m = accH[i] + (accH[i + 2] + (accL[i] + accL[i + 2]));
+          if (p.log_mode) m = fast_ln(zero_handling(m));
+          if (8 * nt + 2 * t4 + i < nf) outp[(int64_t)i * p.T_out] = m;
+        }
+      }
+    }
+  };
+  bool have_prev = false;
+  const float* prev_tile = nullptr;
+  float* prev_out0 = nullptr;
+  bool prev_ok = false;
+  // 32-bit item arithmetic (the launcher declines n_items >= 2^31): the loop state lives across the whole FFT
+  const int n_items = (int)a.n_items, item_step = (int)gridDim.x * kGroups;
+  for (int item = (int)blockIdx.x * kGroups + group; item < n_items; item += item_step, buf ^= 1) {
+    const int row = item / a.rounds_per_row;
+    const int t_round = (item - row * a.rounds_per_row) * kFpr;
+    const float* rowp = p.pcm + (int64_t)row * p.row_stride;
     float* tile = tile0 + buf * kTileFloats;
     {
       const int64_t t = t_round + wg;
@@ -218,6 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
         xch[(k1 + 1) * kXs + u] = y1;
       });
       __syncwarp();
+      if (have_prev) {  // the previous round's filterbank product, while this frame sits in the transpose tile
+        mel_stage(prev_tile, prev_out0, prev_ok, gphase);
+        gphase ^= 1u;
+      }
       float2 gg[kR];
       {
         const float4* r4 = reinterpret_cast<const float4*>(xch + u * kXs);
@@ -234,14 +345,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       // tile.  Only whole interior frames are staged; a source that is 8 but not 16 bytes aligned is copied
       // from the 16-byte boundary below it (16 bytes more).
       {
-        const int64_t nitem = item + (int64_t)gridDim.x * kGroups;
+        const int nitem = item + item_step;
         staged = false;
-        if (a.stage && nitem < a.n_items) {
-          const int64_t nrow = nitem / a.rounds_per_row;
+        if (a.stage && nitem < n_items) {
+          const int nrow = nitem / a.rounds_per_row;
           const int64_t nt = (nitem - nrow * a.rounds_per_row) * kFpr + wg;
           const int64_t no0 = nt * p.S + c0;
           if (nt < p.T && no0 >= 0 && no0 + kW + 4 <= p.row_len) {
-            const float* src = p.pcm + nrow * p.row_stride + no0;
+            const float* src = p.pcm + (int64_t)nrow * p.row_stride + no0;
             sshift = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);  // 0 or 2
             staged = true;
             if (lane == 0) {
@@ -280,67 +391,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       if (isz)  // X[512] = conj Z[512]; bins 513..519 stay zero
         *reinterpret_cast<float4*>(Pf + 512) = make_float4(4.0f * fmaf(gg[16].x, gg[16].x, gg[16].y * gg[16].y), 0.f, 0.f, 0.f);
     }
-    // the group's tile of this round is complete (the other buffer belongs to the next round)
-    asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");
-
-    // ---- mel filterbank on the tensor cores (feature.rs:163-174):
-    //   mel [8 frames][8 filters of n-tile nt] = P [8][band] x W^T,
-    // contraction slot t <-> bin 8 ks + t, slot t + 4 <-> bin 8 ks + 4 + t (two conflict-free 4-byte loads of P).
-    // An n-tile visits only the 8-bin k-steps its 8 filters' band touches; the bands widen with the filter
-    // index (1 .. 13 k-steps for the 128-filter bank), so a warp takes n-tile w and, beyond the first
-    // eight, NT - 1 - w: the widest with the narrowest (8 .. 14 k-steps per warp and round; with one m-tile
-    // of 16 filters per warp it was 2 .. 22, and every round's barrier waited for the last warp).
-    // Rows 8..15 of the A operand carry the low parts of the same frames: with A = [P_hi; P_lo] one MMA
-    // against W_hi yields hi x hi (rows 0..7) and lo x hi (rows 8..15), a second one against W_lo adds
-    // hi x lo (and the negligible lo x lo): two MMAs per k-step instead of three, no idle rows, and the split
-    // results are the operand registers as they are.
-    float* const out0 = p.mel_out + row * nf * p.T_out + t_round + g;  // (frame t_round + g) of filter 0
-    const bool fr_ok = t_round + g < p.T_out;
-#pragma unroll 1
-    for (int job = 0; job < 2; ++job) {
-      const int nt = job == 0 ? wg : a.n_nt - 1 - wg;
-      if (nt >= a.n_nt || (job == 1 && nt < kGroup)) break;
-      float accH[4] = {0.f, 0.f, 0.f, 0.f}, accL[4] = {0.f, 0.f, 0.f, 0.f};
-      unsigned pp = (unsigned)__cvta_generic_to_shared(tile + g * kPs + t4 + 8 * a.ks_lo[nt]);
-      const float4* bp = a.mel_frag + (int64_t)a.mel_base[nt] * 32 + lane;
-      int n2 = a.ks_n2[nt];
-      // two k-steps per iteration (the band is padded to an even count with zero-weight blocks), the
-      // weight fragments of the next iteration are requested before the MMAs of this one
-      float4 w0, w1;
-      if (n2 > 0) { w0 = __ldg(bp); w1 = __ldg(bp + 32); }
-#pragma unroll 1
-      for (; n2 > 0; --n2) {
-        const float2 pv0 = make_float2(lds_f32(pp), lds_f32(pp + 16));  // bins 8 ks + t, 8 ks + 4 + t
-        const float2 pv1 = make_float2(lds_f32(pp + 32), lds_f32(pp + 48));
-        const float4 c0 = w0, c1 = w1;
-        pp += 64;
-        bp += 64;
-        if (n2 > 1) { w0 = __ldg(bp); w1 = __ldg(bp + 32); }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 pv = h ? pv1 : pv0;
-          const float4 w = h ? c1 : c0;
-          uint32_t ah0, al0, ah2, al2;
-          split_tf32(pv.x, ah0, al0);
-          split_tf32(pv.y, ah2, al2);
-          const float4 av = make_float4(__uint_as_float(ah0), __uint_as_float(al0), __uint_as_float(ah2), __uint_as_float(al2));
-          mma_tf32(accH, av, __float_as_uint(w.x), __float_as_uint(w.y));  // [hi; lo] x hi
-          mma_tf32(accL, av, __float_as_uint(w.z), __float_as_uint(w.w));  // [hi; lo] x lo
-        }
-      }
-      // accumulator rows g / g + 8: (frame t_round + g, filters 8 nt + 2 t4 [+ 1]) from the high / low parts; the
-      // 8 lanes of a filter write 32 consecutive bytes of the time-minor output [row][m][t]
-      if (fr_ok) {
-        float* outp = out0 + (int64_t)(8 * nt + 2 * t4) * p.T_out;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          float m = accH[i] + (accH[i + 2] + (accL[i] + accL[i + 2]));
-          if (p.log_mode) m = fast_ln(zero_handling(m));
-          if (8 * nt + 2 * t4 + i < nf) outp[(int64_t)i * p.T_out] = m;
-        }
-      }
-    }
+    __syncwarp();  // the warp's tile row is written (the other buffer belongs to the next round)
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar) : "memory");
+    have_prev = true;
+    prev_tile = tile;
+    prev_out0 = p.mel_out + (int64_t)row * nf * p.T_out + t_round + g;
+    prev_ok = t_round + g < p.T_out;
   }
+  if (have_prev) mel_stage(prev_tile, prev_out0, prev_ok, gphase);
 }
 
 // round-to-nearest (ties away) conversion f32 -> TF32, as cvt.rna.tf32.f32
@@ -468,6 +526,7 @@ int launch_stft2048m(const FrameParams& p, const Stft2048mTables* t, int sm_coun
   for (int i = 0; i < kNtMax; ++i) { a.ks_lo[i] = t->ks_lo[i]; a.ks_n2[i] = t->ks_n2[i]; a.mel_base[i] = t->mel_base[i]; }
   a.rounds_per_row = (int)((p.T_out + kFpr - 1) / kFpr);
   a.n_items = p.n_rows * (int64_t)a.rounds_per_row;
+  if (a.n_items + (int64_t)kGroups * sm_count >= (1LL << 31)) return -1000;  // 32-bit item arithmetic in the kernel
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
   static const bool no_stage = getenv("SS_STFT2048M_STAGE") && atoi(getenv("SS_STFT2048M_STAGE")) == 0;  // A/B switch
   a.stage = a.vec2 && !no_stage && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
