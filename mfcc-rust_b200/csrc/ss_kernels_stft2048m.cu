@@ -255,11 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
   const float* prev_tile = nullptr;
   float* prev_out0 = nullptr;
   bool prev_ok = false;
-  // 32-bit item arithmetic (the launcher declines n_items >= 2^31): the loop state lives across the whole FFT
-  const int n_items = (int)a.n_items, item_step = (int)gridDim.x * kGroups;
-  for (int item = (int)blockIdx.x * kGroups + group; item < n_items; item += item_step, buf ^= 1) {
-    const int row = item / a.rounds_per_row;
-    const int t_round = (item - row * a.rounds_per_row) * kFpr;
+  // item = row * rounds_per_row + rr walks by item_step; (row, rr) advance by its quotient and remainder instead of
+  // a division per round, in 32 bits (the launcher declines n_items >= 2^31): this state lives across the whole FFT
+  const int rpr = a.rounds_per_row, n_rows = (int)p.n_rows;
+  const int item_step = (int)gridDim.x * kGroups, step_q = item_step / rpr, step_r = item_step - step_q * rpr;
+  int row = ((int)blockIdx.x * kGroups + group) / rpr, rr = ((int)blockIdx.x * kGroups + group) - row * rpr;
+  for (; row < n_rows; buf ^= 1) {
+    const int t_round = rr * kFpr;
     const float* rowp = p.pcm + (int64_t)row * p.row_stride;
     float* tile = tile0 + buf * kTileFloats;
     {
@@ -345,11 +347,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       // tile.  Only whole interior frames are staged; a source that is 8 but not 16 bytes aligned is copied
       // from the 16-byte boundary below it (16 bytes more).
       {
-        const int nitem = item + item_step;
+        int nrow = row + step_q, nrr = rr + step_r;
+        if (nrr >= rpr) { nrr -= rpr; ++nrow; }
         staged = false;
-        if (a.stage && nitem < n_items) {
-          const int nrow = nitem / a.rounds_per_row;
-          const int64_t nt = (nitem - nrow * a.rounds_per_row) * kFpr + wg;
+        if (a.stage && nrow < n_rows) {
+          const int64_t nt = nrr * kFpr + wg;
           const int64_t no0 = nt * p.S + c0;
           if (nt < p.T && no0 >= 0 && no0 + kW + 4 <= p.row_len) {
             const float* src = p.pcm + (int64_t)nrow * p.row_stride + no0;
@@ -397,6 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
     prev_tile = tile;
     prev_out0 = p.mel_out + (int64_t)row * nf * p.T_out + t_round + g;
     prev_ok = t_round + g < p.T_out;
+    row += step_q;
+    rr += step_r;
+    if (rr >= rpr) { rr -= rpr; ++row; }
   }
   if (have_prev) mel_stage(prev_tile, prev_out0, prev_ok, gphase);
 }
