@@ -727,6 +727,21 @@ def test_derivative_features_bit_exact():
         sb.processing.derivative_extraction(np.zeros((4, 4), np.float32), 0)
 
 
+def test_cmvn_long_matrices_cooperative_pipeline():
+    """Matrices of 3 .. 40 MB: the co-resident worker / merger pipeline (k_cmvn_coop): more matrices than the lag and
+    the merger count, both modes, a hostile first row (the pivot of block 0), and the same bits as a one-matrix call."""
+    rng = np.random.default_rng(11)
+    for shape in [(11, 70_000, 13), (3, 120_000, 40)]:
+        xb = (rng.standard_normal(shape) * 2 + 1).astype(np.float32)
+        xb[:, 0, :] = 1e4
+        for vn in (True, False):
+            got = sb.cmvn(xb, vn)
+            for i in range(shape[0]):
+                np.testing.assert_allclose(got[i], o.cmvn(xb[i], vn, np.float64), atol=2e-4, err_msg=f"{shape} {vn} {i}")
+            one = sb.cmvn(xb[shape[0] - 1], vn)
+            assert np.array_equal(one, got[shape[0] - 1])
+
+
 def test_cmvnw_matches_oracle():
     rng = np.random.default_rng(12)
     for rows, cols, win in [(1000, 13, 301), (50, 13, 301), (97, 40, 51), (20000, 13, 301), (7, 3, 1), (300, 1, 299)]:
