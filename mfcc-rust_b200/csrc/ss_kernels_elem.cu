@@ -178,6 +178,63 @@ __global__ void __launch_bounds__(kCmvnSmallWarps * 32) k_cmvn_small(const float
   }
 }
 
+// Smaller still (rows * COLS <= kCmvnRegJ * stride; COLS one of the usual cepstral counts: the per-clip cepstra,
+// 97 x 13): the matrix lives in the registers of one warp.  The first stride = (32 / COLS) * COLS lanes walk it
+// with that stride, a multiple of COLS, so a lane stays in one column: no index arithmetic (COLS is a template
+// parameter: every load and store is base + immediate), no shared memory, and all of a lane's loads are in flight
+// at once (k_cmvn_small spends two thirds of its issue slots on addressing and shared-memory traffic).  The
+// 32 / COLS lanes of a column add their sums in lane order; variance in the two-pass form as above.
+constexpr int kCmvnRegJ = 64;
+template <int COLS>
+__global__ void __launch_bounds__(256, 2) k_cmvn_reg(const float* __restrict__ in, float* __restrict__ out, int64_t n_mats, int rows,
+                                                     int varnorm) {
+  constexpr int R = 32 / COLS, stride = R * COLS;
+  const int lane = threadIdx.x & 31;
+  const int n = rows * COLS;
+  const int c = lane % COLS;
+  const bool act = lane < stride;
+  const int nj = act ? (n - lane + stride - 1) / stride : 0;  // this lane's elements
+  const float inv_rows = 1.0f / (float)rows;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < n_mats; m += warps) {
+    const float* ps = in + m * n + lane;
+    float* pd = out + m * n + lane;
+    float v[kCmvnRegJ];
+#pragma unroll
+    for (int j = 0; j < kCmvnRegJ; ++j) v[j] = j < nj ? __ldg(ps + j * stride) : 0.f;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCmvnRegJ; ++j) s += v[j];
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < R; ++g) tot += __shfl_sync(0xffffffffu, s, c + g * COLS);
+    const float mean = tot * inv_rows;
+    float inv = 1.0f;
+    if (varnorm) {
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < kCmvnRegJ; ++j) {
+        const float d = v[j] - mean;
+        q += j < nj ? d * d : 0.f;
+      }
+      float tq = 0.f;
+#pragma unroll
+      for (int g = 0; g < R; ++g) tq += __shfl_sync(0xffffffffu, q, c + g * COLS);
+      inv = 1.0f / (sqrtf(tq * inv_rows) + kCmvnEps);  // processing.rs:283-292
+    }
+#pragma unroll
+    for (int j = 0; j < kCmvnRegJ; ++j)
+      if (j < nj) pd[j * stride] = (v[j] - mean) * inv;
+  }
+}
+template <int COLS>
+static int launch_cmvn_reg(const float* in, float* out, int64_t n_mats, int64_t rows, int varnorm, void* stream) {
+  const int64_t blocks = std::min<int64_t>((n_mats + 7) / 8, 16LL * kSmCountGuess);
+  k_cmvn_reg<COLS><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n_mats, (int)rows, varnorm);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 // Pass 1: per (matrix, row block) Welford statistics per column, merged across the block's
 // threads with Chan's formula.  Pass 2: merge the row blocks of the matrix, then normalise.
 // partial layout: [n_mats][nblk][cols][3] = (count, mean, M2)
@@ -752,6 +809,15 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
   if (cols > 256 || n_mats > 2147483647LL) return (int)cudaErrorInvalidValue;
   // matrices that fit a warp's slice of shared memory: the fused one-read / one-write kernel
   // (chosen by the matrix shape alone, so that a batch gives the same bits however the host layer chunks it)
+  static const bool no_reg = getenv("SS_CMVN_REG") && atoi(getenv("SS_CMVN_REG")) == 0;  // A/B switch
+  if (cols <= 32 && rows * cols <= kCmvnRegJ * ((32 / cols) * cols) && !no_reg) {
+    switch (cols) {  // the usual cepstral counts; other widths take the shared-memory kernel below
+      case 12: return launch_cmvn_reg<12>(in, out, n_mats, rows, varnorm, stream);
+      case 13: return launch_cmvn_reg<13>(in, out, n_mats, rows, varnorm, stream);
+      case 20: return launch_cmvn_reg<20>(in, out, n_mats, rows, varnorm, stream);
+      default: break;
+    }
+  }
   if (rows * cols <= 5120) {
     const int n = (int)(rows * cols), R = cols <= 16 ? 32 / (int)cols : 1;
     const int warp_floats = ((n + 3) & ~3) + (R + 2) * (int)cols + 4;

@@ -492,7 +492,9 @@ def test_cmvn():
     for i in (0, 13, 39):
         np.testing.assert_allclose(got[i], o.cmvn(batch[i], True), atol=2e-5)
     # many small matrices: the fused one-warp-per-matrix kernel (13 columns: two row groups; 100 columns: one)
-    for shape in [(300, 97, 13), (200, 50, 100), (129, 1, 7), (70, 31, 16), (64, 300, 17)]:
+    # ... and the register-resident kernel for the usual cepstral counts (12, 13, 20 columns; up to 64 elements per lane)
+    for shape in [(300, 97, 13), (200, 50, 100), (129, 1, 7), (70, 31, 16), (64, 300, 17), (50, 60, 12), (33, 40, 20), (129, 1, 13),
+                  (77, 128, 13), (77, 129, 13), (9, 2, 20)]:
         xb = (rng.standard_normal(shape) * 2 + 1).astype(np.float32)
         for vn in (True, False):
             got = sb.cmvn(xb, vn)
