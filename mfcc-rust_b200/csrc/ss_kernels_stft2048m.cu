@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
   }
   const unsigned gbar = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint64_t*>(smem + kTabFixed) + kWarps + (threadIdx.x >> 8));
   if ((threadIdx.x & 255) == 0) {
-    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(gbar), "r"(kGroup) : "memory");
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(gbar), "r"(kGroup * 32) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   unsigned gphase = 0;  // parity of the group barrier phase the pending tile completes
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       if (isz)  // X[512] = conj Z[512]; bins 513..519 stay zero
         *reinterpret_cast<float4*>(Pf + 512) = make_float4(4.0f * fmaf(gg[16].x, gg[16].x, gg[16].y * gg[16].y), 0.f, 0.f, 0.f);
     }
-    __syncwarp();  // the warp's tile row is written (the other buffer belongs to the next round)
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar) : "memory");
+    // the warp's tile row is written (the other buffer belongs to the next round): every lane announces its own stores
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar) : "memory");
     have_prev = true;
     prev_tile = tile;
     prev_out0 = p.mel_out + (int64_t)row * nf * p.T_out + t_round + g;

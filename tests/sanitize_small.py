@@ -86,5 +86,13 @@ for H in (256, 160, 101):
     sb.functions.stft2(y5, k5)
     sb.feature.mel_spectrogram2(y5, k5, log=True)
 sb.feature.melspectrogram_librosa(o.synth_signal(2, 5000, 38), sb.feature.librosa_config(16000, 512, 160, 80, devices=[0]), db=True)
+# librosa mode at n_fft = 2048 (k_stft2048<2> + k_mel_from_power<16>), the pipelined k_stft2048m with several rounds per
+# group (the filterbank product of round r inside round r + 1), the register-resident and the cooperative cmvn
+sb.feature.melspectrogram_librosa(o.synth_signal(2, 9000, 39), sb.feature.librosa_config(22050, 2048, 512, 128, devices=[0]), db=True)
+sb.feature.melspectrogram_librosa(o.synth_signal(1, 2048, 40), sb.feature.librosa_config(16000, 2048, 250, 40, devices=[0]))
+sb.feature.mel_spectrogram2(o.synth_signal(150, 22050, 41), sb.SpeechConfig(**C3, devices=[0]), log=True)
+sb.processing.cmvn(o.synth_signal(40, 60 * 12, 42).reshape(40, 60, 12), True)
+sb.processing.cmvn(o.synth_signal(9, 2 * 20, 43).reshape(9, 2, 20), False)
+sb.processing.cmvn(o.synth_signal(5, 70000 * 13, 44).reshape(5, 70000, 13), True)
 torch.cuda.synchronize()
 print("sanitize_small: all kernels ran")
