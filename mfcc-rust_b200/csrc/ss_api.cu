@@ -280,9 +280,9 @@ static void stft_params(ss_plan* pl, DeviceCtx* dc, FrameParams* p, const float*
 
 static DevBuf* plan_stream_scratch(DeviceCtx* dc, void* stream);
 
-// fft_points = 512: the register-FFT kernel + the banded mel kernel; the |X|^2 scratch lives per caller stream
+// fft_points = 512 / 1024: the register-FFT kernel + the banded mel kernel; the |X|^2 scratch lives per caller stream
 static int launch_stft512_any(ss_plan* pl, DeviceCtx* dc, const FrameParams& p, void* stream) {
-  if (pl->d.W != 512 || (pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC) || !(p.mel_out || p.stft_out)) return -1000;
+  if (!stft512_supported(pl->d) || (pl->d.cfg.flags & SS_FLAG_FORCE_GENERIC) || !(p.mel_out || p.stft_out)) return -1000;
   float* scratch = nullptr;
   if (p.mel_out) {
     DevBuf* sb = plan_stream_scratch(dc, stream);

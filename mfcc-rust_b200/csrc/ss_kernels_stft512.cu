@@ -1,5 +1,6 @@
-// fft_points = 512 on the STFT / librosa paths: functions::stft1/2 (functions.rs:86-233), feature::mel_spectrogram1/2
-// (feature.rs:151-174) and the librosa-compatible mel spectrogram for n_fft = 512.
+// fft_points = 512 and 1024 on the STFT / librosa paths: functions::stft1/2 (functions.rs:86-233),
+// feature::mel_spectrogram1/2 (feature.rs:151-174) and the librosa-compatible mel spectrogram for those n_fft.
+// (Kernel template k_stft512<R, ..>: R = 16 points per lane -> fft_points 512, R = 32 -> 1024.)
 //
 // Two kernels instead of one fused one (the fused MMA epilogue of k_fast512c is tied to speechpy framing):
 //   k_stft512        one half-warp per frame: window, the 16 x 16 four-step register FFT of k_fast512c / k_pspec512,
@@ -31,11 +32,17 @@ using ssfft::sfor;
 
 constexpr int kWarps = 8;
 constexpr int kXs = 18;                       // transpose row stride in float2 (144 B: conflict-free LDS.128)
-constexpr int kXchFrame = 16 * kXs;
-constexpr int kWarpFloats = 2 * kXchFrame * 2;
-constexpr int kTwRow = 36;
-constexpr int kTabTw = 16 * kTwRow;
-constexpr int kW = 512, kF = 257;
+// R complex points per lane, 16 lanes per frame: a 16 R-point complex FFT = a real FFT of W = 32 R samples
+template <int R>
+struct Geo {
+  static constexpr int kW = 32 * R, kNc = 16 * R, kF = kNc + 1;
+  static constexpr int kNS = R / 16;                   // 16-point sub-FFTs per lane in the second stage
+  static constexpr int kXchFrame = R * kXs;            // float2 per frame
+  static constexpr int kWarpFloats = 2 * kXchFrame * 2;
+  static constexpr int kTwRow = 2 * R + 4;             // floats per lane row of the W_Nc table
+  static constexpr int kTabTw = 16 * kTwRow;
+  static constexpr size_t kSmem = (size_t)(kTabTw + kW + kWarps * kWarpFloats) * sizeof(float);
+};
 
 __device__ __forceinline__ float zero_handling(float v) { return v == 0.0f ? kEps : v; }
 
@@ -52,23 +59,27 @@ __device__ __forceinline__ float stream_at(const FrameParams& p, int64_t q) {
   return p.pcm[r * p.row_stride + o];
 }
 
-template <bool LIBROSA>
+template <int R, bool LIBROSA>
 __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, const float* __restrict__ tw_tab, float* __restrict__ power,
                                                           int64_t row0, int64_t n_rows) {
-  __shared__ __align__(16) float tw_s[kTabTw];
-  __shared__ __align__(16) float win_s[kW];
-  __shared__ __align__(16) float xch_s[kWarps * kWarpFloats];
-  for (int i = threadIdx.x; i < kTabTw; i += kWarps * 32) tw_s[i] = __ldg(tw_tab + i);
+  using G = Geo<R>;
+  constexpr int kW = G::kW, kNc = G::kNc, kF = G::kF, kNS = G::kNS;
+  extern __shared__ __align__(16) float smem[];
+  float* tw_s = smem;
+  float* win_s = smem + G::kTabTw;
+  float* xch_s = win_s + kW;
+  for (int i = threadIdx.x; i < G::kTabTw; i += kWarps * 32) tw_s[i] = __ldg(tw_tab + i);
   for (int i = threadIdx.x; i < kW; i += kWarps * 32) win_s[i] = __ldg(p.tab.window + i);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fi = lane >> 4, u = lane & 15;
   const bool isz = (u == 0);
   const int partner = (lane & 16) | ((16 - u) & 15);
-  const float4* twrow = reinterpret_cast<const float4*>(tw_s + u * kTwRow);
-  float2 wu;  // W512^u
-  sincospif(-(float)u / 256.0f, &wu.y, &wu.x);
-  float2* xch = reinterpret_cast<float2*>(xch_s + warp * kWarpFloats) + fi * kXchFrame;
+  const float4* twrow = reinterpret_cast<const float4*>(tw_s + u * G::kTwRow);
+  float2 wu[kNS];  // W_{2 Nc}^{u + 16 s}
+#pragma unroll
+  for (int s = 0; s < kNS; ++s) sincospif(-(float)(u + 16 * s) / (float)kNc, &wu[s].y, &wu[s].x);
+  float2* xch = reinterpret_cast<float2*>(xch_s + warp * G::kWarpFloats) + fi * G::kXchFrame;
   const float2* win2 = reinterpret_cast<const float2*>(win_s) + u;  // window pairs (2m, 2m+1), m = u + 16 j
 
   const int64_t T = p.T, T_out = p.T_out;
@@ -90,17 +101,17 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
     const float* rowp = p.pcm + row * p.row_stride;
     const int64_t o0 = t * H + c0;
     // ---- framing + window: v[j] = (x w)[2m] + i (x w)[2m+1], m = u + 16 j
-    float2 v[16];
+    float2 v[R];
     if (!computed) {
-      sfor<0, 16>([&](auto jj) { v[decltype(jj)::value] = make_float2(0.f, 0.f); });
+      sfor<0, R>([&](auto jj) { v[decltype(jj)::value] = make_float2(0.f, 0.f); });
     } else if (o0 >= 0 && o0 + kW <= p.row_len && vec_ok) {
       const float* px = rowp + o0 + 2 * u;
-      sfor<0, 16>([&](auto jj) {
+      sfor<0, R>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
         v[j] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(px + 32 * j)), win2[16 * j]);
       });
     } else {
-      sfor<0, 16>([&](auto jj) {
+      sfor<0, R>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
         const float2 w = win2[16 * j];
         float xs[2];
@@ -118,9 +129,9 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
         v[j] = make_float2(xs[0] * w.x, xs[1] * w.y);
       });
     }
-    // ---- 256-point complex FFT: 16-point FFT over j, twiddle W256^{u k1}, transpose, 16-point FFT over the lanes
-    ssfft::fft_pow2<16>(v);
-    sfor<0, 8>([&](auto kk) {
+    // ---- Nc-point complex FFT: R-point FFT over j, twiddle W_Nc^{u k1}, transpose, 16-point FFTs over the lanes
+    ssfft::fft_pow2<R>(v);
+    sfor<0, R / 2>([&](auto kk) {
       constexpr int k1 = 2 * decltype(kk)::value;
       const float4 w = twrow[k1 / 2];
       float2 y0 = v[k1], y1 = v[k1 + 1];
@@ -130,47 +141,55 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
       xch[(k1 + 1) * kXs + u] = y1;
     });
     __syncwarp();
-    float2 gg[16];
-    {
-      const float4* r4 = reinterpret_cast<const float4*>(xch + u * kXs);
+    // lane u takes the rows k1 = u + 16 s: gg[s][k2] = Z[u + 16 s + R k2]
+    float2 gg[kNS][16];
+#pragma unroll
+    for (int s = 0; s < kNS; ++s) {
+      const float4* r4 = reinterpret_cast<const float4*>(xch + (u + 16 * s) * kXs);
       sfor<0, 8>([&](auto tt) {
         constexpr int i = decltype(tt)::value;
         const float4 x = r4[i];
-        gg[2 * i] = make_float2(x.x, x.y);
-        gg[2 * i + 1] = make_float2(x.z, x.w);
+        gg[s][2 * i] = make_float2(x.x, x.y);
+        gg[s][2 * i + 1] = make_float2(x.z, x.w);
       });
     }
     __syncwarp();
-    ssfft::fft_pow2<16>(gg);
-    // ---- real-FFT split: X[k] = xa / 2, X[256 - k] = conj(xb) / 2 for k = u + 16 k2
+#pragma unroll
+    for (int s = 0; s < kNS; ++s) ssfft::fft_pow2<16>(gg[s]);
+    // ---- real-FFT split: X[k] = xa / 2, X[Nc - k] = conj(xb) / 2 for k = u + 16 s + R k2 < Nc / 2 (k2 < 8).
+    // Nc - k = (R - u - 16 s) + R (15 - k2): row R - u - 16 s belongs to lane 16 - u, sub-FFT kNS - 1 - s (u > 0);
+    // lane 0 mirrors onto itself: sub-FFT 0 onto its own entry 16 - k2, sub-FFT s >= 1 onto sub-FFT kNS - s.
     float2* srow = (p.stft_out && stored) ? p.stft_out + (row * T_out + t) * kF : nullptr;
     float* prow = (power && computed) ? power + (rl * T + t) * kF : nullptr;
-    sfor<0, 8>([&](auto kk) {
-      constexpr int k2 = decltype(kk)::value;
-      float2 zb;
-      zb.x = __shfl_sync(0xffffffffu, gg[15 - k2].x, partner);
-      zb.y = __shfl_sync(0xffffffffu, gg[15 - k2].y, partner);
-      if (isz) zb = gg[(16 - k2) & 15];
-      const float2 za = gg[k2];
-      const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
-      const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
-      const float2 tt = ssfft::cmulf(ssfft::twmul<32, k2>(od), wu);
-      const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
-      const float2 Xa = make_float2(scale * xa.x, scale * xa.y), Xb = make_float2(scale * xb.x, -scale * xb.y);
-      const int ka = u + 16 * k2, kb = 256 - ka;
-      if (srow) {
-        srow[ka] = Xa;
-        srow[kb] = Xb;
-      }
-      if (prow) {
-        prow[ka] = fmaf(Xa.x, Xa.x, Xa.y * Xa.y);  // feature.rs:164: |X|^2
-        prow[kb] = fmaf(Xb.x, Xb.x, Xb.y * Xb.y);
-      }
-    });
-    if (isz) {  // X[128] = conj Z[128]
-      const float2 X = make_float2(2.0f * scale * gg[8].x, -2.0f * scale * gg[8].y);
-      if (srow) srow[128] = X;
-      if (prow) prow[128] = fmaf(X.x, X.x, X.y * X.y);
+#pragma unroll
+    for (int s = 0; s < kNS; ++s) {
+      sfor<0, 8>([&](auto kk) {
+        constexpr int k2 = decltype(kk)::value;
+        float2 zb;
+        zb.x = __shfl_sync(0xffffffffu, gg[kNS - 1 - s][15 - k2].x, partner);
+        zb.y = __shfl_sync(0xffffffffu, gg[kNS - 1 - s][15 - k2].y, partner);
+        if (isz) zb = s == 0 ? gg[0][(16 - k2) & 15] : gg[kNS - s][15 - k2];
+        const float2 za = gg[s][k2];
+        const float2 e = __fadd2_rn(za, make_float2(zb.x, -zb.y));
+        const float2 od = __fadd2_rn(make_float2(za.y, -za.x), make_float2(zb.y, zb.x));
+        const float2 tt = ssfft::cmulf(ssfft::twmul<32, k2>(od), wu[s]);  // W_{2 Nc}^{R k2} = W32^{k2}
+        const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
+        const float2 Xa = make_float2(scale * xa.x, scale * xa.y), Xb = make_float2(scale * xb.x, -scale * xb.y);
+        const int ka = u + 16 * s + R * k2, kb = kNc - ka;
+        if (srow) {
+          srow[ka] = Xa;
+          srow[kb] = Xb;
+        }
+        if (prow) {
+          prow[ka] = fmaf(Xa.x, Xa.x, Xa.y * Xa.y);  // feature.rs:164: |X|^2
+          prow[kb] = fmaf(Xb.x, Xb.x, Xb.y * Xb.y);
+        }
+      });
+    }
+    if (isz) {  // X[Nc / 2] = conj Z[Nc / 2], entry 8 of sub-FFT 0
+      const float2 X = make_float2(2.0f * scale * gg[0][8].x, -2.0f * scale * gg[0][8].y);
+      if (srow) srow[kNc / 2] = X;
+      if (prow) prow[kNc / 2] = fmaf(X.x, X.x, X.y * X.y);
     }
   }
 }
@@ -218,7 +237,7 @@ __global__ void __launch_bounds__(256) k_mel_from_power(const float* __restrict_
 }
 
 std::mutex g_mu;
-std::map<int, float*> g_tw;  // W256 table per device
+std::map<std::pair<int, int>, float*> g_tw;  // W_Nc table per (device, R)
 
 }  // namespace
 
@@ -244,11 +263,11 @@ int launch_mel_from_power(const float* power, const FrameParams& p, int64_t row0
   return tf == 16 ? launch_mel_tf<16>(power, p, row0, n_rows, F, stream) : launch_mel_tf<kMelFrames>(power, p, row0, n_rows, F, stream);
 }
 
-bool stft512_supported(const Derived& d) { return d.W == 512 && d.stft_ok; }
+bool stft512_supported(const Derived& d) { return (d.W == 512 || d.W == 1024) && d.stft_ok; }
 
 // scratch: power rows of the rows of one launch; sized by stft512_scratch_bytes for `rows_per_launch` rows
 size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch) {
-  const int64_t per_row = std::max<int64_t>(1, p.T) * kF * (int64_t)sizeof(float);
+  const int64_t per_row = std::max<int64_t>(1, p.T) * (p.N / 2 + 1) * (int64_t)sizeof(float);
   int64_t rpl = std::max<int64_t>(1, (256LL << 20) / per_row);
   rpl = std::min<int64_t>(rpl, std::max<int64_t>(1, p.n_rows));
   rpl = std::min<int64_t>(rpl, 65535);  // gridDim.y of the mel kernel
@@ -256,31 +275,36 @@ size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch) {
   return (size_t)(rpl * per_row);
 }
 
-int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* stream) {
-  if (p.N != kW || p.n_rows <= 0 || p.T_out <= 0) return p.N != kW ? -1000 : 0;
-  if (p.mel_out && !scratch) return -1000;
+template <int R>
+static int launch_stft_r(const FrameParams& p, float* scratch, int sm_count, void* stream) {
+  using G = Geo<R>;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
   const float* tw = nullptr;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    float*& t = g_tw[dev];
+    float*& t = g_tw[{dev, R}];
     if (!t) {
-      std::vector<float> h(kTabTw, 0.f);
+      std::vector<float> h(G::kTabTw, 0.f);
       const double pi = 3.14159265358979323846264338327950288;
       for (int u = 0; u < 16; ++u)
-        for (int k1 = 0; k1 < 16; ++k1) {
-          const double ang = -2.0 * pi * (double)(u * k1) / 256.0;
-          h[u * kTwRow + 2 * k1] = (float)std::cos(ang);
-          h[u * kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
+        for (int k1 = 0; k1 < R; ++k1) {
+          const double ang = -2.0 * pi * (double)(u * k1) / (double)G::kNc;
+          h[u * G::kTwRow + 2 * k1] = (float)std::cos(ang);
+          h[u * G::kTwRow + 2 * k1 + 1] = (float)std::sin(ang);
         }
-      if ((e = cudaMalloc(&t, kTabTw * sizeof(float))) != cudaSuccess) return (int)e;
-      if ((e = cudaMemcpy(t, h.data(), kTabTw * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+      if ((e = cudaMalloc(&t, G::kTabTw * sizeof(float))) != cudaSuccess) return (int)e;
+      if ((e = cudaMemcpy(t, h.data(), G::kTabTw * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     }
     tw = t;
   }
   const bool librosa = p.mode == kModeLibrosa;
+  if (G::kSmem > 48 * 1024) {
+    e = librosa ? cudaFuncSetAttribute(k_stft512<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)
+                : cudaFuncSetAttribute(k_stft512<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem);
+    if (e != cudaSuccess) return (int)e;
+  }
   int64_t rpl = p.n_rows;
   if (p.mel_out) stft512_scratch_bytes(p, &rpl);
   cudaStream_t s = (cudaStream_t)stream;
@@ -289,17 +313,24 @@ int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* str
     const int64_t pairs = nr * ((p.T_out + 1) / 2);
     const int64_t grid = std::min<int64_t>((pairs + kWarps - 1) / kWarps, 16LL * sm_count);
     float* pw = p.mel_out ? scratch : nullptr;
-    if (librosa) k_stft512<true><<<(unsigned)grid, kWarps * 32, 0, s>>>(p, tw, pw, r0, nr);
-    else k_stft512<false><<<(unsigned)grid, kWarps * 32, 0, s>>>(p, tw, pw, r0, nr);
+    if (librosa) k_stft512<R, true><<<(unsigned)grid, kWarps * 32, G::kSmem, s>>>(p, tw, pw, r0, nr);
+    else k_stft512<R, false><<<(unsigned)grid, kWarps * 32, G::kSmem, s>>>(p, tw, pw, r0, nr);
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     if (p.mel_out) {
-      const int me = launch_mel_from_power(scratch, p, r0, nr, kF, stream);
+      const int me = launch_mel_from_power(scratch, p, r0, nr, G::kF, stream);
       if (me) return me;
     }
   }
-  note_kernel("k_stft512");
+  note_kernel(R == 16 ? "k_stft512" : "k_stft1024");
   return 0;
+}
+
+int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* stream) {
+  if (p.N != 512 && p.N != 1024) return -1000;
+  if (p.n_rows <= 0 || p.T_out <= 0) return 0;
+  if (p.mel_out && !scratch) return -1000;
+  return p.N == 512 ? launch_stft_r<16>(p, scratch, sm_count, stream) : launch_stft_r<32>(p, scratch, sm_count, stream);
 }
 
 }  // namespace ss

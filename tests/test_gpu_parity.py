@@ -578,20 +578,26 @@ W512 = [dict(sample_rate=16000, fft_points=512, frame_length=256.5 / 16000, fram
         dict(sample_rate=16000, fft_points=512, frame_length=160.5 / 16000, frame_stride=0.01, num_cepstral=13, num_filters=40,
              low_frequency=50.0, high_frequency=7000.0),          # H = 160: every row's first frames read the previous row's tail
         dict(sample_rate=22050, fft_points=512, frame_length=101.5 / 22050, frame_stride=0.01, num_cepstral=13, num_filters=23,
-             low_frequency=0.0, high_frequency=11025.0)]          # odd hop: the per-sample path for every frame
+             low_frequency=0.0, high_frequency=11025.0),          # odd hop: the per-sample path for every frame
+        # fft_points = 1024: the same kernel template with 32 points per lane (two 16-point sub-FFTs per lane in the second stage)
+        dict(sample_rate=16000, fft_points=1024, frame_length=256.5 / 16000, frame_stride=0.01, num_cepstral=13, num_filters=64,
+             low_frequency=0.0, high_frequency=8000.0),
+        dict(sample_rate=22050, fft_points=1024, frame_length=441.5 / 22050, frame_stride=0.01, num_cepstral=13, num_filters=96,
+             low_frequency=20.0, high_frequency=11025.0)]         # odd hop
 
 
 @pytest.mark.parametrize("kw", W512)
 def test_stft512_register_fft_path_matches_generic_and_oracle(kw):
     """fft_points = 512: k_stft512 (+ k_mel_from_power) against the any-length kernel and the oracle -- complex STFT, mel and
     log-mel, ragged lengths, rows shorter than the overlap memory, row-to-row and call-to-call carry, odd frame counts"""
+    kname = b"k_stft512" if kw["fft_points"] == 512 else b"k_stft1024"
     for n, ttd in [(5, 16000), (3, 4001), (7, 257), (2, 100), (1, 48017), (33, 2048)]:
         x = o.synth_signal(n, ttd, 2000 + ttd)
         fast, gen, oc = sb.SpeechConfig(**kw), sb.SpeechConfig(**kw, flags=GENERIC), o.SpeechConfig(**kw)
         assert fast.info.fast_stft == 1 and gen.info.fast_stft == 0
         for call in range(2):  # the second call starts from the memory the first one left
             a = sb.functions.stft2(x, fast)
-            assert sb.lib.ss_last_kernel_name() == b"k_stft512"
+            assert sb.lib.ss_last_kernel_name() == kname
             b, want = sb.functions.stft2(x, gen), o.stft2(x, oc)
             assert sb.lib.ss_last_kernel_name() == b"k_frames_generic"
             pk = np.abs(want).max()
@@ -601,7 +607,7 @@ def test_stft512_register_fft_path_matches_generic_and_oracle(kw):
         for log in (False, True):
             fast, gen, oc = sb.SpeechConfig(**kw), sb.SpeechConfig(**kw, flags=GENERIC), o.SpeechConfig(**kw)
             a = sb.feature.mel_spectrogram2(x, fast, log=log)
-            assert sb.lib.ss_last_kernel_name() == b"k_stft512"
+            assert sb.lib.ss_last_kernel_name() == kname
             b = sb.feature.mel_spectrogram2(x, gen, log=log)
             want = o.log_mel_spectrogram2(x, oc) if log else o.mel_spectrogram2(x, oc)
             if log:
@@ -613,20 +619,22 @@ def test_stft512_register_fft_path_matches_generic_and_oracle(kw):
                 assert_spec_close(a, b, what=f"512 fast vs generic mel {n}x{ttd}")
 
 
-def test_librosa_mode_n_fft_512_register_fft_kernel():
-    for sr, hop, n_mels, n, rows in [(16000, 160, 80, 16000 * 2 + 5, 3), (16000, 128, 40, 4000, 2), (22050, 512, 64, 9001, 4), (8000, 77, 23, 300, 1)]:
-        cfg = sb.feature.librosa_config(sr, 512, hop, n_mels, 0.0, None)
+@pytest.mark.parametrize("n_fft", [512, 1024])
+def test_librosa_mode_n_fft_512_1024_register_fft_kernel(n_fft):
+    kname = b"k_stft512" if n_fft == 512 else b"k_stft1024"
+    for sr, hop, n_mels, n, rows in [(16000, 160, 80, 16000 * 2 + 5, 3), (16000, 128, 40, 4000, 2), (22050, 512, 64, 9001, 4), (8000, 77, 23, 600, 1)]:
+        cfg = sb.feature.librosa_config(sr, n_fft, hop, n_mels, 0.0, None)
         assert cfg.info.fast_stft == 1
         y = o.synth_signal(rows, n, 0x5EED0512 + hop)
         got = sb.feature.melspectrogram_librosa(y, cfg)
-        assert sb.lib.ss_last_kernel_name() == b"k_stft512"
-        want = o.librosa_melspectrogram(y, sr, 512, hop, n_mels, 0.0, None)
+        assert sb.lib.ss_last_kernel_name() == kname
+        want = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, 0.0, None)
         assert got.shape == want.shape == (rows, n_mels, 1 + n // hop)
-        assert_spec_close(got, want, what=f"librosa 512 mel hop {hop}")
+        assert_spec_close(got, want, what=f"librosa {n_fft} mel hop {hop}")
         gdb = sb.feature.melspectrogram_librosa(y, cfg, db=True)
-        wdb = o.librosa_melspectrogram(y, sr, 512, hop, n_mels, 0.0, None, db=True)
+        wdb = o.librosa_melspectrogram(y, sr, n_fft, hop, n_mels, 0.0, None, db=True)
         loud = want > 1e-6 * want.max()
-        assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what="librosa 512 power_to_db")
+        assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what=f"librosa {n_fft} power_to_db")
 
 
 def test_librosa_mode_n_fft_2048_register_fft_kernel():
