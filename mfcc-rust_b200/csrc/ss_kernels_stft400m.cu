@@ -12,7 +12,7 @@
 //     load): an item is a run of frames of one row; a warp works through it three frames per FFT
 //     round, the |X|^2 rows go to a private 12-row ring in shared memory and every time 8 more
 //     frames are complete the ring feeds one 8-frame MMA tile;
-//   * the samples of the next round (720 contiguous floats) are fetched with cp.async into the
+//   * the samples of the next round are fetched by TMA bulk copies (one per frame) into the
 //     transpose tile while the current round finishes, so the global-load latency is off the
 //     critical path and the window multiply reads shared memory;
 //   * the filterbank runs on the tensor cores, transposed: mel^T [16 MT filters][8 frames] =
@@ -60,12 +60,9 @@ struct Geo {
   static constexpr int kWarpFloats = kFpw * 202 * 2 + kTileFloats;
 };
 constexpr int kStage = kW + (kFpw - 1) * 160;    // samples of one round when hop = 160 (staging needs hop == 160)
-// The staged samples land with 20 floats of padding after every 160: frame fi then starts 180 fi floats in
-// (20 fi banks apart, like the transpose tile's frames) and the LDS.64 of the three frames do not collide.
-// Sample r = 2u + 20j (+1) of a frame sits at 180 fi + r + 20 (j / 8).
-constexpr int kStageSeg = 160, kStagePitch = 180;
-constexpr int kStageSegs = (kStage + kStageSeg - 1) / kStageSeg;  // 5 bulk copies: 4 x 640 B + 320 B
-static_assert(kStagePitch * (kStageSegs - 1) + kStage - kStageSeg * (kStageSegs - 1) <= kXchFloats, "staged round fits the transpose tile");
+// The staged samples of frame fi land in that frame's slot of the transpose tile (404 floats apart, i.e. 20 banks:
+// the LDS.64 of the three frames do not collide).
+static_assert(kW <= 2 * kXchFrame, "a staged frame fits its transpose slot");
 // Physical row of logical row k1 in a frame's transpose tile.  Lane u reads rows u and 20 - u (10 for u = 0)
 // with LDS.128; this placement makes the first conflict-free across the three frames of a warp (4 wavefronts)
 // and leaves the second at 6 (natural order: 7 and 10).  Found by exhaustive search over 16-byte bank groups.
@@ -74,7 +71,7 @@ __device__ constexpr int kRowOf[20] = {0, 5, 4, 3, 1, 6, 2, 7, 8, 11, 16, 18, 17
 static_assert(Geo<false>::kWarpFloats % 4 == 0 && Geo<true>::kWarpFloats % 4 == 0, "per-warp scratch must stay 16-byte aligned");
 static_assert(Geo<false>::kWarpFloats == kXchFloats + Geo<false>::kTileFloats, "transpose tile size");
 constexpr int kMtMax = 8;                // nf <= 128
-constexpr int kMbarFloats = 2 * 34;      // one 8-byte mbarrier per warp + one for the table copy, after the tables
+constexpr int kMbarFloats = 2 * 34;      // one 8-byte mbarrier per warp + one for the table copy, at the start of the dynamic shared memory
 constexpr int kTwRow = 44;               // floats per lane row of the W200 table (20 float2 + pad)
 // fixed table blob (floats)
 // W200 table: one copy per frame of the round, lane u's row in slot kTwSlot[u], the copies 452 floats apart:
@@ -114,7 +111,7 @@ struct Stft400mArgs {
   int64_t n_units;      // rows * units_per_row: the work is cut into units of kChunkAlign frames and every
   int units_per_row;    // resident warp takes one contiguous, equally long run of units (static, balanced)
   int vec2;             // frames start 8-byte aligned
-  int stage;            // hop == 160 and frames start 16-byte aligned: cp.async staging of whole rounds
+  int stage;            // hop == 160 and frames start 16-byte aligned: bulk-copy staging of whole rounds
   int pair_ok;          // T_out is even and the output is 8-byte aligned: float2 stores
   int n_mt;             // m-tiles of 16 filters
   int ks_lo[kMtMax], ks_n2[kMtMax], mel_base[kMtMax];
@@ -148,9 +145,11 @@ template <bool STFT, bool FULL>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs a) {
   constexpr int kPs = Geo<FULL>::kPs, kWarpFloats = Geo<FULL>::kWarpFloats;
   extern __shared__ __align__(16) float smem[];
-  float* tab_s = smem;
-  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem + a.tab_floats);  // one mbarrier per warp
-  float* warp_s = smem + a.tab_floats + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
+  // layout: mbarriers, the warps' scratch, then the tables (whose size depends on the bank): the per-warp addresses are
+  // compile-time offsets from the warp index and need no register
+  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem);  // one mbarrier per warp
+  float* warp_s = smem + kMbarFloats + (threadIdx.x >> 5) * kWarpFloats;
+  float* tab_s = smem + kMbarFloats + (blockDim.x >> 5) * kWarpFloats;
   const FrameParams& p = a.p;
   const int nf = p.nf;
   // the tables arrive by one TMA bulk copy
@@ -249,15 +248,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
         const float* src = rowp + (int64_t)(fbeg + kFpw * rd) * p.S + c0;
         const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_s);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(kStage * 4) : "memory");
+        // one copy per frame (400 samples each; the overlaps come twice, out of L2) into the frames' own 404-float slots:
+        // three UBLKCP per round instead of five 160-sample segments with padding (each costs ~14 issue slots of
+        // uniform-register setup), and the window pass reads plain frame offsets
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(kFpw * kW * 4) : "memory");
 #pragma unroll
-        for (int sg = 0; sg < kStageSegs; ++sg) {
-          const int n = (sg + 1 < kStageSegs ? kStageSeg : kStage - kStageSeg * (kStageSegs - 1)) * 4;
+        for (int sg = 0; sg < kFpw; ++sg)
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           dst + sg * kStagePitch * 4),
-                       "l"(src + sg * kStageSeg), "r"(n), "r"(mbar)
+                           dst + sg * 2 * kXchFrame * 4),
+                       "l"(src + sg * 160), "r"(kW * 4), "r"(mbar)
                        : "memory");
-        }
       }
     };
     bool staged = n_rounds > 0 && stageable(0);
@@ -289,10 +289,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_stft400m(const Stft400mArgs 
             } while (!done);
             phase ^= 1u;
           }
-          const float* sx = stage_s + fi * kStagePitch + 2 * u;
+          const float* sx = stage_s + fi * 2 * kXchFrame + 2 * u;
           sfor<0, kR1>([&](auto jj) {
             constexpr int j = decltype(jj)::value;
-            v[j] = __fmul2_rn(*reinterpret_cast<const float2*>(sx + 20 * j + 20 * (j / 8)), win2[10 * j]);
+            v[j] = __fmul2_rn(*reinterpret_cast<const float2*>(sx + 20 * j), win2[10 * j]);
           });
           __syncwarp();  // the buffer is the transpose tile again
         } else {
@@ -629,7 +629,7 @@ int launch_stft400m(const FrameParams& p, const Stft400mTables* t, int sm_count,
   a.units_per_row = (int)((p.T_out + kChunkAlign - 1) / kChunkAlign);
   a.n_units = p.n_rows * (int64_t)a.units_per_row;
   a.vec2 = (p.S % 2 == 0) && (p.row_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 8 == 0);
-  // whole rounds can be staged with 16-byte cp.async when every round starts 16-byte aligned
+  // whole rounds can be staged by bulk copies when every frame starts 16-byte aligned
   const int64_t c0 = t->full ? -kW / 2 : (int64_t)(p.n_pad + 1) * p.S - p.N;
   a.stage = p.S == 160 && (p.row_stride % 4 == 0) && (((c0 % 4) + 4) % 4 == 0) && (reinterpret_cast<uintptr_t>(p.pcm) % 16 == 0);
   a.pair_ok = (p.T_out % 2 == 0) && (reinterpret_cast<uintptr_t>(p.mel_out) % 8 == 0);
