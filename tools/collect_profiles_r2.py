@@ -18,7 +18,7 @@ def last_json_line(path):
 
 
 names = ["c1", "c2", "c3", "c4", "c5", "c2_reference", "c2_generic", "p_preemphasis", "p_stack", "p_cmvn", "p_cmvn_long", "p_pspec",
-         "p_pspec_generic"]
+         "p_pspec_generic", "p_cmvn_long_3pass", "p_cmvn_smem"]
 for f in names:
     src = g / f"r2z_bench_{f}.json"
     if src.exists():
@@ -63,7 +63,8 @@ for rep, kn, name, cfg, clips, phases in [
         ("prof_stft400m_r2", "k_stft400mILb0ELb0", "ncu_stft400m_r2", None, None, False),
         ("prof_stft2048m_r2", "k_stft2048m", "ncu_stft2048m_r2", "c3", 4096, False),
         ("prof_pspec512_r2", "k_pspec512ILi13", "ncu_pspec512_r2", None, None, False),
-        ("prof_cmvn_small_r2", "k_cmvn_small", "ncu_cmvn_small_r2", None, None, False)]:
+        ("prof_cmvn_reg_r2", "k_cmvn_reg", "ncu_cmvn_reg_r2", None, None, False),
+        ("prof_cmvn_coop_r2", "k_cmvn_coop", "ncu_cmvn_coop_r2", None, None, False)]:
     rp = g / f"{rep}.ncu-rep"
     if not rp.exists():
         print("missing", rp)
@@ -74,6 +75,8 @@ for rep, kn, name, cfg, clips, phases in [
         tr[cfg] = {"kernel": kn.split("IL")[0].split("E")[0] if kn.startswith("k_fast") else kn.split("IL")[0], "clips": clips, "dram_bytes": traffic(txt),
                    "source": f"profiles/{name}.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full)"}
 (pr / "ncu_traffic.json").write_text(json.dumps(tr, indent=1) + "\n")
+if (g / "r2z_time_stft.txt").exists():
+    (pr / "stft_paths_r2.txt").write_text((g / "r2z_time_stft.txt").read_text())
 for tool in ("memcheck", "racecheck"):
     f = g / f"r2z_sanitize_{tool}.log"
     if f.exists():

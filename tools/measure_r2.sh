@@ -22,7 +22,11 @@ ncu --set full --import-source on --clock-control none -k regex:k_fast512c -c 1 
 ncu --set full --import-source on --clock-control none -k regex:k_stft400m -c 1 -f -o gpurun_out/prof_stft400m_r2 python bench.py --config c4 --clips 1024 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_r2_c4.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_stft2048m -c 1 -f -o gpurun_out/prof_stft2048m_r2 python bench.py --config c3 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_r2_c3.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_pspec512 -c 1 -f -o gpurun_out/prof_pspec512_r2 python bench.py --config p_pspec --steps 1 --warmup 1 > gpurun_out/ncu_r2_pspec.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:k_cmvn_small -c 1 -f -o gpurun_out/prof_cmvn_small_r2 python bench.py --config p_cmvn --steps 1 --warmup 1 > gpurun_out/ncu_r2_cmvn.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_cmvn_reg -c 1 -f -o gpurun_out/prof_cmvn_reg_r2 python bench.py --config p_cmvn --steps 1 --warmup 1 > gpurun_out/ncu_r2_cmvn.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_cmvn_coop -c 1 -f -o gpurun_out/prof_cmvn_coop_r2 python bench.py --config p_cmvn_long --steps 1 --warmup 1 > gpurun_out/ncu_r2_cmvn_long.log 2>&1
+SS_CMVN_COOP=0 python bench.py --config p_cmvn_long --steps 20 > gpurun_out/r2z_bench_p_cmvn_long_3pass.json 2>/dev/null
+SS_CMVN_REG=0 python bench.py --config p_cmvn --steps 20 > gpurun_out/r2z_bench_p_cmvn_smem.json 2>/dev/null
+python tools/time_stft.py > gpurun_out/r2z_time_stft.txt 2>&1
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tests/sanitize_small.py > gpurun_out/r2z_sanitize_$tool.log 2>&1
   echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/r2z_sanitize_$tool.log | tail -1)"
