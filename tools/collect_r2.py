@@ -21,7 +21,16 @@ for f in sorted(G.glob("r2s_c*_n*.json")):
     if not d:
         continue
     name = f.stem[4:]  # c2_weak_n8
-    shutil.copy(f, P / f"bench_r2_{name}.json")
+    t = last_json(G / f"r2t_{name}.json") if (G / f"r2t_{name}.json").exists() else None
+    if t:  # device-resident fields re-measured with the final kernels (tools/run_scaling_c34.sh)
+        for k in ("ms_per_step", "value", "roofline", "clocks", "steps", "warmup", "gpu_launches", "frames_per_s"):
+            if k in t:
+                d[k] = t[k]
+        d["remeasured"] = ("device-resident fields (ms_per_step, value, roofline, clocks) from tools/run_scaling_c34.sh on the final kernels; "
+                           "the e2e fields, where present, from tools/run_scaling.sh earlier in the round (PCIe-bound)")
+        (P / f"bench_r2_{name}.json").write_text(json.dumps(d) + "\n")
+    else:
+        shutil.copy(f, P / f"bench_r2_{name}.json")
     cfg, sc, n = name.split("_")
     rows.append((cfg, sc, int(n[1:]), d))
 for f in sorted(G.glob("r2s_pcie_n*.json")):
