@@ -500,7 +500,7 @@ def test_cmvn():
             got = sb.cmvn(xb, vn)
             for i in (0, shape[0] // 2, shape[0] - 1):
                 np.testing.assert_allclose(got[i], o.cmvn(xb[i], vn), atol=2e-5, err_msg=f"{shape} {vn} {i}")
-    # several long matrices: L2-sized batches, shifted-sum statistics (a large offset must not hurt the variance)
+    # several long matrices: the cooperative L2 pipeline, shifted-sum statistics (a large offset must not hurt the variance)
     long_ = (rng.standard_normal((5, 300_000, 13)) * 0.5 + 40).astype(np.float32)
     got = sb.cmvn(long_, True)
     for i in (0, 4):
