@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
   const int c0 = (p.n_pad + 1) * p.S - p.N;
   // this warp's job in the filterbank product: one m-tile (16 filters) of its group's 8 frames
   const int group = warp >> 3, wg = warp & 7;
-  int buf = 0;
+  int buf = 0, rot = 0;
 
   // ---- mel filterbank on the tensor cores (feature.rs:163-174):
   //   mel [8 frames][8 filters of n-tile nt] = P [8][band] x W^T,
@@ -206,10 +206,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
     }
   };
   // out0: (frame t_round + g) of filter 0 in the time-minor output; fr_ok: that frame exists
-  auto mel_stage = [&](const float* tile, float* const out0, const bool fr_ok, unsigned wait_phase) {
+  // wr: which pair of n-tiles this warp takes.  It rotates with the round, so every warp sees every band width in turn:
+  // with a fixed pair the warp that owns the widest bands (16 k-steps against 8) is the last to arrive in every round.
+  auto mel_stage = [&](const float* tile, float* const out0, const bool fr_ok, unsigned wait_phase, int wr) {
 #pragma unroll 1
     for (int job = 0; job < 2; ++job) {
-      const int nt = job == 0 ? wg : a.n_nt - 1 - wg;
+      const int nt = job == 0 ? wr : a.n_nt - 1 - wr;
       const bool active = nt < a.n_nt && !(job == 1 && nt < kGroup);
       const int n2 = active ? a.ks_n2[nt] : 0;
       const float4* bp = a.mel_frag + (int64_t)(active ? a.mel_base[nt] : 0) * 32 + lane;
@@ -328,8 +330,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
       });
       __syncwarp();
       if (have_prev) {  // the previous round's filterbank product, while this frame sits in the transpose tile
-        mel_stage(prev_tile, prev_out0, prev_ok, gphase);
+        mel_stage(prev_tile, prev_out0, prev_ok, gphase, (wg + rot) & (kGroup - 1));
         gphase ^= 1u;
+        ++rot;
       }
       float2 gg[kR];
       {
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_stft2048m(const Stft2048mArgs a
     rr += step_r;
     if (rr >= rpr) { rr -= rpr; ++row; }
   }
-  if (have_prev) mel_stage(prev_tile, prev_out0, prev_ok, gphase);
+  if (have_prev) mel_stage(prev_tile, prev_out0, prev_ok, gphase, (wg + rot) & (kGroup - 1));
 }
 
 // round-to-nearest (ties away) conversion f32 -> TF32, as cvt.rna.tf32.f32
