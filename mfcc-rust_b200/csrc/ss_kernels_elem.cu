@@ -375,11 +375,12 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
 // a matrix's counter, merge the workers' partials in block order (Chan's formula; the bits do not depend on the
 // batch) and publish mean and 1 / (std + eps).  No grid-wide barrier; the lag keeps the merge (~5 us) off the
 // workers' path.  Measured on 64 x (359,997 x 13): DRAM reads 1.20 GB = the input once (three-pass kernels: 2.33 GB),
-// 0.75 ms against 0.90 ms.  What is left is not bandwidth: every block walks every matrix, so a matrix costs one
-// block's chain of dependent round trips (two DRAM batches, three block reductions, fence + counter, flag, two L2
-// batches: ~11 us) -- prefetching the next matrix's first batch and per-thread polling of tagged statistics
-// records were tried and lost to register spills and to 150,000 threads polling the L2.
-constexpr int kCoopThreads = 512, kCoopBlocksPerSm = 2, kCoopMergers = 4, kCoopBatch = 16;
+// 0.73 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
+// matrix costs one block's chain of dependent round trips (DRAM batches, three block reductions, fence + counter,
+// flag, L2 batches: ~11 us).  Two matrices per step (G = 2) buy 3 %; four spill; 16-byte vectors (one trip per
+// matrix, 128 bytes per thread in flight) measured 0.82 ms; prefetching the next matrix's first batch and per-thread
+// polling of tagged statistics records lost to register spills and to 150,000 threads polling the L2.
+constexpr int kCoopThreads = 512, kCoopBlocksPerSm = 2, kCoopMergers = 4, kCoopBatch = 8, kCoopGroupMax = 4;
 constexpr int64_t kCoopMinMatBytes = 3LL << 20, kCoopMaxMatBytes = 40LL << 20, kCoopL2Bytes = 64LL << 20;
 struct CoopArgs {
   const float* in;
@@ -394,16 +395,11 @@ struct CoopArgs {
 __device__ __forceinline__ void spin_until(const int* p, int want) {
   while (*reinterpret_cast<const volatile int*>(p) < want) __nanosleep(100);
 }
-__global__ void __launch_bounds__(kCoopThreads, kCoopBlocksPerSm) k_cmvn_coop(const CoopArgs a) {
-  extern __shared__ float sm[];  // [lanes][cols][3], then [8][cols][3]
+// the merger blocks of the cooperative kernels: matrix m belongs to merger m mod kCoopMergers
+__device__ __forceinline__ void coop_merger(const CoopArgs& a, float* red, float* red2, int workers) {
   const int cols = a.cols;
   const int lanes = kCoopThreads / cols;
   const int lane = threadIdx.x / cols, c = threadIdx.x - lane * cols;
-  float* red = sm;
-  float* red2 = sm + (size_t)lanes * cols * 3;
-  const int workers = gridDim.x - kCoopMergers;
-  if ((int)blockIdx.x >= workers) {
-    // ---- merger
     const int me = blockIdx.x - workers;
     for (int64_t m = me; m < a.n_mats; m += kCoopMergers) {
       if (threadIdx.x == 0) spin_until(a.counter + m, workers);
@@ -457,6 +453,21 @@ __global__ void __launch_bounds__(kCoopThreads, kCoopBlocksPerSm) k_cmvn_coop(co
       __syncthreads();
       if (threadIdx.x == 0) atomicExch(a.flag + m, 1);
     }
+}
+
+// G: matrices per pipeline step.  A step's loads for all G matrices are issued together, so the chain of dependent round
+// trips (the pipeline's clock, below) is paid once per G matrices.
+template <int G>
+__global__ void __launch_bounds__(kCoopThreads, kCoopBlocksPerSm) k_cmvn_coop(const CoopArgs a) {
+  extern __shared__ float sm[];  // G x ([lanes][cols][3], then [8][cols][3])
+  const int cols = a.cols;
+  const int lanes = kCoopThreads / cols;
+  const int lane = threadIdx.x / cols, c = threadIdx.x - lane * cols;
+  float* red = sm;
+  float* red2 = sm + (size_t)G * lanes * cols * 3;
+  const int workers = gridDim.x - kCoopMergers;
+  if ((int)blockIdx.x >= workers) {
+    coop_merger(a, red, red2, workers);
     return;
   }
   // ---- worker: rows [r0, r1) of every matrix.  The first lanes * cols threads walk the block's n = (r1 - r0) * cols
@@ -470,77 +481,124 @@ __global__ void __launch_bounds__(kCoopThreads, kCoopBlocksPerSm) k_cmvn_coop(co
   const int stride = lanes * cols, t = threadIdx.x;
   const bool act = t < stride && n > 0;
   const int mid = (int)((r1 - r0) >> 1) * cols + c, last = n - cols + c;  // cmvn_pivot's rows, block-relative
-  for (int64_t i = 0; i < a.n_mats + a.lag; ++i) {
-    if (i < a.n_mats) {
-      const float* x = a.in + (i * a.rows + r0) * cols;
-      float n_t = 0.f, s1 = 0.f, s2 = 0.f, pivot = 0.f;
+  const int64_t n_steps = (a.n_mats + G - 1) / G;
+  const int red_sz = stride * 3, red2_sz = 8 * cols * 3;
+  for (int64_t st = 0; st < n_steps + a.lag; ++st) {
+    if (st < n_steps) {
+      const int64_t m0 = st * G;
+      const int g_n = (int)min((int64_t)G, a.n_mats - m0);
+      const float* x0 = a.in + (m0 * a.rows + r0) * cols;
+      const int64_t mstride = a.rows * cols;  // matrix to matrix
+      float s1[G], s2[G], pivot[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) { s1[g] = 0.f; s2[g] = 0.f; pivot[g] = 0.f; }
+      float n_t = 0.f;
       if (act) {
-        const float p0 = x[c], p1 = x[mid], p2 = x[last];
+        float p0[G], p1[G], p2[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float* x = x0 + (g < g_n ? g : 0) * mstride;  // a missing matrix of the last step re-reads the first one
+          p0[g] = x[c]; p1[g] = x[mid]; p2[g] = x[last];
+        }
         for (int k = t; k < n; k += kCoopBatch * stride) {
-          float v[kCoopBatch];
+          float v[G][kCoopBatch];
 #pragma unroll
-          for (int q = 0; q < kCoopBatch; ++q) v[q] = x[min(k + q * stride, n - 1)];
-          pivot = fmaxf(fminf(p0, p1), fminf(fmaxf(p0, p1), p2));
+          for (int g = 0; g < G; ++g) {
+            const float* x = x0 + (g < g_n ? g : 0) * mstride;
 #pragma unroll
-          for (int q = 0; q < kCoopBatch; ++q) v[q] = k + q * stride < n ? v[q] - pivot : 0.f;
+            for (int q = 0; q < kCoopBatch; ++q) v[g][q] = x[min(k + q * stride, n - 1)];
+          }
 #pragma unroll
-          for (int q = 0; q < kCoopBatch; q += 8) {
-            s1 += ((v[q] + v[q + 1]) + (v[q + 2] + v[q + 3])) + ((v[q + 4] + v[q + 5]) + (v[q + 6] + v[q + 7]));
-            s2 += ((v[q] * v[q] + v[q + 1] * v[q + 1]) + (v[q + 2] * v[q + 2] + v[q + 3] * v[q + 3])) +
-                  ((v[q + 4] * v[q + 4] + v[q + 5] * v[q + 5]) + (v[q + 6] * v[q + 6] + v[q + 7] * v[q + 7]));
+          for (int g = 0; g < G; ++g) {
+            pivot[g] = fmaxf(fminf(p0[g], p1[g]), fminf(fmaxf(p0[g], p1[g]), p2[g]));  // cmvn_pivot
+#pragma unroll
+            for (int q = 0; q < kCoopBatch; ++q) v[g][q] = k + q * stride < n ? v[g][q] - pivot[g] : 0.f;
+#pragma unroll
+            for (int q = 0; q < kCoopBatch; q += 4) {
+              s1[g] += (v[g][q] + v[g][q + 1]) + (v[g][q + 2] + v[g][q + 3]);
+              s2[g] += (v[g][q] * v[g][q] + v[g][q + 1] * v[g][q + 1]) + (v[g][q + 2] * v[g][q + 2] + v[g][q + 3] * v[g][q + 3]);
+            }
           }
         }
         n_t = (float)((n - t + stride - 1) / stride);  // elements of this thread
       }
       if (t < stride) {
-        float* s = red + (size_t)t * 3;
-        s[0] = n_t; s[1] = s1; s[2] = s2;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float* s = red + g * red_sz + (size_t)t * 3;
+          s[0] = n_t; s[1] = s1[g]; s[2] = s2[g];
+        }
       }
       __syncthreads();
       if (t < 8 * cols) {
         const int part = t / cols, cc = t - part * cols;
-        float N = 0.f, S1 = 0.f, S2 = 0.f;
-        for (int l = part; l < lanes; l += 8) {
-          const float* s = red + ((size_t)l * cols + cc) * 3;
-          N += s[0]; S1 += s[1]; S2 += s[2];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float N = 0.f, S1 = 0.f, S2 = 0.f;
+          for (int l = part; l < lanes; l += 8) {
+            const float* s = red + g * red_sz + ((size_t)l * cols + cc) * 3;
+            N += s[0]; S1 += s[1]; S2 += s[2];
+          }
+          float* s = red2 + g * red2_sz + ((size_t)part * cols + cc) * 3;
+          s[0] = N; s[1] = S1; s[2] = S2;
         }
-        float* s = red2 + ((size_t)part * cols + cc) * 3;
-        s[0] = N; s[1] = S1; s[2] = S2;
       }
       __syncthreads();
       if (t < cols) {
-        float N = 0.f, S1 = 0.f, S2 = 0.f;
-        for (int l = 0; l < 8; ++l) {
-          const float* s = red2 + ((size_t)l * cols + t) * 3;
-          N += s[0]; S1 += s[1]; S2 += s[2];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g < g_n) {
+            float N = 0.f, S1 = 0.f, S2 = 0.f;
+            for (int l = 0; l < 8; ++l) {
+              const float* s = red2 + g * red2_sz + ((size_t)l * cols + t) * 3;
+              N += s[0]; S1 += s[1]; S2 += s[2];
+            }
+            float* o = a.partial + (((size_t)((m0 + g) % a.ring) * workers + blockIdx.x) * cols + t) * 3;
+            o[0] = N;  // t < cols: this thread's pivot is column t's
+            o[1] = N > 0.f ? pivot[g] + S1 / N : 0.f;
+            o[2] = N > 0.f ? fmaxf(S2 - S1 * (S1 / N), 0.f) : 0.f;
+          }
         }
-        float* o = a.partial + (((size_t)(i % a.ring) * workers + blockIdx.x) * cols + t) * 3;
-        o[0] = N;  // t < cols: this thread's pivot is column t's
-        o[1] = N > 0.f ? pivot + S1 / N : 0.f;
-        o[2] = N > 0.f ? fmaxf(S2 - S1 * (S1 / N), 0.f) : 0.f;
         __threadfence();
       }
       __syncthreads();
-      if (t == 0) atomicAdd(a.counter + i, 1);
+      if (t < g_n) atomicAdd(a.counter + m0 + t, 1);
     }
-    if (i >= a.lag) {
-      const int64_t m = i - a.lag;
-      if (t == 0) spin_until(a.flag + m, 1);
+    if (st >= a.lag) {
+      const int64_t m0 = (st - a.lag) * G;
+      const int g_n = (int)min((int64_t)G, a.n_mats - m0);
+      if (t < g_n) spin_until(a.flag + m0 + t, 1);
       __syncthreads();
       __threadfence();
       if (act) {
-        const float mean = __ldcg(a.stats + ((size_t)m * cols + c) * 2);
-        const float inv = __ldcg(a.stats + ((size_t)m * cols + c) * 2 + 1);  // 1 when !varnorm
-        const float* x = a.in + (m * a.rows + r0) * cols;
-        float* y = a.out + (m * a.rows + r0) * cols;
+        float mean[G], inv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int64_t m = m0 + (g < g_n ? g : 0);
+          mean[g] = __ldcg(a.stats + ((size_t)m * cols + c) * 2);
+          inv[g] = __ldcg(a.stats + ((size_t)m * cols + c) * 2 + 1);  // 1 when !varnorm
+        }
+        const float* x0 = a.in + (m0 * a.rows + r0) * cols;
+        float* y0 = a.out + (m0 * a.rows + r0) * cols;
+        const int64_t mstride = a.rows * cols;
         for (int k = t; k < n; k += kCoopBatch * stride) {  // one round trip (to L2) per batch, as above
-          float v[kCoopBatch];
+          float v[G][kCoopBatch];
 #pragma unroll
-          for (int q = 0; q < kCoopBatch; ++q) v[q] = __ldcs(x + min(k + q * stride, n - 1));  // last use of the line: evict first
+          for (int g = 0; g < G; ++g) {
+            const float* x = x0 + (g < g_n ? g : 0) * mstride;
 #pragma unroll
-          for (int q = 0; q < kCoopBatch; ++q) {
-            const float d = v[q] - mean;
-            if (k + q * stride < n) __stcs(y + k + q * stride, a.varnorm ? d * inv : d);  // streaming: the L2 belongs to the sums' reads
+            for (int q = 0; q < kCoopBatch; ++q) v[g][q] = __ldcs(x + min(k + q * stride, n - 1));  // last use of the line: evict first
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (g < g_n) {
+              float* y = y0 + g * mstride;
+#pragma unroll
+              for (int q = 0; q < kCoopBatch; ++q) {
+                const float d = v[g][q] - mean[g];
+                if (k + q * stride < n) __stcs(y + k + q * stride, a.varnorm ? d * inv[g] : d);  // streaming: the L2 belongs to the sums' reads
+              }
+            }
           }
         }
       }
@@ -786,6 +844,13 @@ static int cmvn_coop_lag(int64_t rows, int64_t cols) {
   if (lag_env > 0) return std::min(lag_env, 8);
   return (int)std::min<int64_t>(8, std::max<int64_t>(2, kCoopL2Bytes / mat_bytes - 1));
 }
+// matrices per pipeline step and the lag in steps
+static void cmvn_coop_steps(int lag_mats, int* group, int* lag_steps) {
+  static const int g_env = getenv("SS_CMVN_GROUP") ? atoi(getenv("SS_CMVN_GROUP")) : 0;  // measurements
+  const int g = g_env == 1 || g_env == 2 || g_env == 4 ? g_env : 2;
+  *group = g;
+  *lag_steps = std::max(1, (lag_mats + 1) / g - 1);
+}
 static size_t coop_align(size_t b) { return (b + 255) & ~(size_t)255; }
 
 size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols) {
@@ -797,7 +862,7 @@ size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols) {
   if (!lag) return three_pass;
   // partial ring + statistics + counters and flags (launch_cmvn lays them out in this order)
   const int64_t coop_blocks = (int64_t)kCoopBlocksPerSm * kSmCountGuess;
-  const size_t coop = coop_align((size_t)(lag + 1) * coop_blocks * cols * 3 * sizeof(float)) + coop_align((size_t)n_mats * cols * 2 * sizeof(float)) +
+  const size_t coop = coop_align((size_t)(lag + 1) * kCoopGroupMax * coop_blocks * cols * 3 * sizeof(float)) + coop_align((size_t)n_mats * cols * 2 * sizeof(float)) +
                       coop_align((size_t)n_mats * 2 * sizeof(int));
   return std::max(three_pass, coop);
 }
@@ -836,11 +901,15 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
     // long matrices: the cooperative one-DRAM-read pipeline, when the device can hold its whole grid
     int dev = 0, sms = 0, coop_ok = 0, per_sm = 0;
     const int lanes = kCoopThreads / (int)cols;
-    const size_t smem = ((size_t)lanes * cols * 3 + (size_t)8 * cols * 3) * sizeof(float);
+    int G = 1, lag_steps = 1;
+    cmvn_coop_steps(lag, &G, &lag_steps);
+    const size_t smem = (size_t)G * ((size_t)lanes * cols * 3 + (size_t)8 * cols * 3) * sizeof(float);
+    const void* kern = G == 1 ? (const void*)k_cmvn_coop<1> : G == 2 ? (const void*)k_cmvn_coop<2> : (const void*)k_cmvn_coop<4>;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cmvn_coop, kCoopThreads, smem);
+    if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoopThreads, smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t nblk = std::min<int64_t>((int64_t)std::min(per_sm, kCoopBlocksPerSm) * sms, (int64_t)kCoopBlocksPerSm * kSmCountGuess);
     const int64_t workers = nblk - kCoopMergers;
@@ -851,12 +920,12 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
       a.n_mats = n_mats;
       a.rows = rows;
       a.cols = (int)cols;
-      a.lag = lag;
-      a.ring = lag + 1;
+      a.lag = lag_steps;
+      a.ring = (lag_steps + 1) * G;  // <= (lag + 1) * kCoopGroupMax slots (cmvn_scratch_bytes)
       a.varnorm = varnorm;
       char* sp = reinterpret_cast<char*>(scratch);
       a.partial = reinterpret_cast<float*>(sp);
-      sp += coop_align((size_t)(lag + 1) * kCoopBlocksPerSm * kSmCountGuess * cols * 3 * sizeof(float));
+      sp += coop_align((size_t)(lag + 1) * kCoopGroupMax * kCoopBlocksPerSm * kSmCountGuess * cols * 3 * sizeof(float));
       a.stats = reinterpret_cast<float*>(sp);
       sp += coop_align((size_t)n_mats * cols * 2 * sizeof(float));
       a.counter = reinterpret_cast<int*>(sp);
@@ -864,7 +933,7 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
       e = cudaMemsetAsync(a.counter, 0, (size_t)n_mats * 2 * sizeof(int), (cudaStream_t)stream);
       if (e != cudaSuccess) return (int)e;
       void* args[] = {(void*)&a};
-      e = cudaLaunchCooperativeKernel((const void*)k_cmvn_coop, dim3((unsigned)nblk), dim3(kCoopThreads), args, smem, (cudaStream_t)stream);
+      e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)nblk), dim3(kCoopThreads), args, smem, (cudaStream_t)stream);
       count_launch();
       return (int)e;
     }
