@@ -375,12 +375,12 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
 // a matrix's counter, merge the workers' partials in block order (Chan's formula; the bits do not depend on the
 // batch) and publish mean and 1 / (std + eps).  No grid-wide barrier; the lag keeps the merge (~5 us) off the
 // workers' path.  Measured on 64 x (359,997 x 13): DRAM reads 1.20 GB = the input once (three-pass kernels: 2.33 GB),
-// 0.73 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
+// 0.75 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
 // matrix costs one block's chain of dependent round trips (DRAM batches, three block reductions, fence + counter,
-// flag, L2 batches: ~11 us).  Two matrices per step (G = 2) buy 3 %; four spill; 16-byte vectors (one trip per
+// flag, L2 batches: ~11 us).  Two matrices per step (G = 2) buy 1 % and lose the L2 reuse; four spill; 16-byte vectors (one trip per
 // matrix, 128 bytes per thread in flight) measured 0.82 ms; prefetching the next matrix's first batch and per-thread
 // polling of tagged statistics records lost to register spills and to 150,000 threads polling the L2.
-constexpr int kCoopThreads = 512, kCoopBlocksPerSm = 2, kCoopMergers = 4, kCoopBatch = 8, kCoopGroupMax = 4;
+constexpr int kCoopThreads = 512, kCoopBlocksPerSm = 2, kCoopMergers = 4, kCoopGroupMax = 4;
 constexpr int64_t kCoopMinMatBytes = 3LL << 20, kCoopMaxMatBytes = 40LL << 20, kCoopL2Bytes = 64LL << 20;
 struct CoopArgs {
   const float* in;
@@ -459,6 +459,7 @@ __device__ __forceinline__ void coop_merger(const CoopArgs& a, float* red, float
 // trips (the pipeline's clock, below) is paid once per G matrices.
 template <int G>
 __global__ void __launch_bounds__(kCoopThreads, kCoopBlocksPerSm) k_cmvn_coop(const CoopArgs a) {
+  constexpr int kCoopBatch = G == 1 ? 16 : 8;  // loads per thread, matrix and round trip
   extern __shared__ float sm[];  // G x ([lanes][cols][3], then [8][cols][3])
   const int cols = a.cols;
   const int lanes = kCoopThreads / cols;
@@ -847,7 +848,9 @@ static int cmvn_coop_lag(int64_t rows, int64_t cols) {
 // matrices per pipeline step and the lag in steps
 static void cmvn_coop_steps(int lag_mats, int* group, int* lag_steps) {
   static const int g_env = getenv("SS_CMVN_GROUP") ? atoi(getenv("SS_CMVN_GROUP")) : 0;  // measurements
-  const int g = g_env == 1 || g_env == 2 || g_env == 4 ? g_env : 2;
+  // default 1: two matrices per step are 1 % faster (0.746 against 0.753 ms) but put four matrices between the sums and
+  // the normalisation, which no longer fit the L2 next to the output stream: DRAM reads 2.23 GB instead of 1.20 GB
+  const int g = g_env == 1 || g_env == 2 || g_env == 4 ? g_env : 1;
   *group = g;
   *lag_steps = std::max(1, (lag_mats + 1) / g - 1);
 }
