@@ -370,12 +370,12 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
 // Long matrices (hours of cepstra per matrix, e.g. 360,000 x 13 = 18.7 MB): one persistent, co-resident grid
 // (cooperative launch) pipelines the matrices through the L2 so that each crosses the DRAM bus once per direction
 // instead of twice in.  Worker blocks own a fixed row range: they sum it for matrix i (shifted sums, as
-// k_cmvn_partial) and announce it on the matrix's counter, then normalise the same rows of matrix i - lag out of
+// k_cmvn_partial) and announce it on the matrix's counter, then normalise the same rows of matrix i - lag (lag = 1) out of
 // L2 once its statistics are flagged.  A few merger blocks (matrix m belongs to merger m mod kCoopMergers) wait for
 // a matrix's counter, merge the workers' partials in block order (Chan's formula; the bits do not depend on the
 // batch) and publish mean and 1 / (std + eps).  No grid-wide barrier; the lag keeps the merge (~5 us) off the
-// workers' path.  Measured on 64 x (359,997 x 13): DRAM reads 1.20 GB = the input once (three-pass kernels: 2.33 GB),
-// 0.75 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
+// workers' path.  Measured on 64 x (359,997 x 13): DRAM reads 1.23 GB = the input once (three-pass kernels: 2.33 GB),
+// 0.79 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
 // matrix costs one block's chain of dependent round trips (DRAM batches, three block reductions, fence + counter,
 // flag, L2 batches: ~11 us).  Two matrices per step (G = 2) buy 1 % and lose the L2 reuse; four spill; 16-byte vectors (one trip per
 // matrix, 128 bytes per thread in flight) measured 0.82 ms; prefetching the next matrix's first batch and per-thread
@@ -843,7 +843,9 @@ static int cmvn_coop_lag(int64_t rows, int64_t cols) {
   if (off || cols > 64 || mat_bytes < kCoopMinMatBytes || mat_bytes > kCoopMaxMatBytes) return 0;
   static const int lag_env = getenv("SS_CMVN_LAG") ? atoi(getenv("SS_CMVN_LAG")) : 0;  // measurements
   if (lag_env > 0) return std::min(lag_env, 8);
-  return (int)std::min<int64_t>(8, std::max<int64_t>(2, kCoopL2Bytes / mat_bytes - 1));
+  // the sums run as few matrices ahead as the merge latency allows: each one in between has to stay in the L2 next to the
+  // output stream (18.7 MB matrices: one ahead re-reads nothing from DRAM, two ahead a third of the matrix)
+  return (int)std::min<int64_t>(8, std::max<int64_t>(1, kCoopL2Bytes / mat_bytes - 2));
 }
 // matrices per pipeline step and the lag in steps
 static void cmvn_coop_steps(int lag_mats, int* group, int* lag_steps) {
