@@ -386,9 +386,9 @@ struct CoopArgs {
   const float* in;
   float* out;
   float* partial;   // [ring][workers][cols][3]
-  float* stats;     // [n_mats][cols][2]
+  unsigned long long* stats;  // [n_mats][cols][2] records: bits of mean / 1 / (std + eps) | (m + 1) << 32 -- each 8-byte record
+                              // carries its own "published" tag (zeroed before the launch)
   int* counter;     // [n_mats] workers done with the sums of matrix m   (zeroed before the launch)
-  int* flag;        // [n_mats] statistics of matrix m published         (zeroed before the launch)
   int64_t n_mats, rows;
   int cols, lag, ring, varnorm;
 };
@@ -408,20 +408,18 @@ __device__ __forceinline__ void coop_merger(const CoopArgs& a, float* red, float
       const float* pbuf = a.partial + (size_t)(m % a.ring) * workers * cols * 3;
       if (lane < lanes) {
         Wf acc = {0.f, 0.f, 0.f};
-        int bq = lane;
-        for (; bq + 3 * lanes < workers; bq += 4 * lanes) {  // twelve independent L2 loads, then four merges in block order
-          Wf w[4];
+        // eight partials (24 clamped, unconditional L2 loads) per round trip, merged in block order: with ~300 workers
+        // and 39 lanes that is one trip per merge -- the merge sits on the workers' path when the lag is one matrix
+        for (int b0 = lane; b0 < workers; b0 += 8 * lanes) {
+          Wf w[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float* s = pbuf + ((size_t)(bq + q * lanes) * cols + c) * 3;
-            w[q] = Wf{__ldcg(s), __ldcg(s + 1), __ldcg(s + 2)};
+          for (int q = 0; q < 8; ++q) {
+            const int bb = b0 + q * lanes;
+            const float* s = pbuf + ((size_t)min(bb, workers - 1) * cols + c) * 3;
+            w[q] = Wf{bb < workers ? __ldcg(s) : 0.f, __ldcg(s + 1), __ldcg(s + 2)};
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc = wf_merge(acc, w[q]);
-        }
-        for (; bq < workers; bq += lanes) {
-          const float* s = pbuf + ((size_t)bq * cols + c) * 3;
-          acc = wf_merge(acc, Wf{__ldcg(s), __ldcg(s + 1), __ldcg(s + 2)});
+          for (int q = 0; q < 8; ++q) acc = wf_merge(acc, w[q]);  // n == 0: skipped
         }
         float* s = red + ((size_t)lane * cols + c) * 3;
         s[0] = acc.n; s[1] = acc.mean; s[2] = acc.m2;
@@ -444,14 +442,16 @@ __device__ __forceinline__ void coop_merger(const CoopArgs& a, float* red, float
           const float* s = red2 + ((size_t)l * cols + threadIdx.x) * 3;
           acc = wf_merge(acc, Wf{s[0], s[1], s[2]});
         }
-        float* o = a.stats + ((size_t)m * cols + threadIdx.x) * 2;
-        o[0] = acc.mean;
         // processing.rs:283-292: std with ddof 0, divide by (std + 2^-30)
-        o[1] = a.varnorm ? 1.0f / (sqrtf(acc.m2 / acc.n) + kCmvnEps) : 1.0f;
-        __threadfence();
+        const float inv = a.varnorm ? 1.0f / (sqrtf(acc.m2 / acc.n) + kCmvnEps) : 1.0f;
+        // value and tag land together (aligned 8-byte stores): no flag, no fence, and the workers' 2 * cols polling
+        // threads get the statistics with the round trip that tells them they are there
+        volatile unsigned long long* o = a.stats + ((size_t)m * cols + threadIdx.x) * 2;
+        const unsigned long long tag = (unsigned long long)(unsigned)(m + 1) << 32;
+        o[0] = tag | __float_as_uint(acc.mean);
+        o[1] = tag | __float_as_uint(inv);
       }
-      __syncthreads();
-      if (threadIdx.x == 0) atomicExch(a.flag + m, 1);
+      __syncthreads();  // red / red2 are rewritten for the next matrix
     }
 }
 
@@ -568,16 +568,28 @@ __global__ void __launch_bounds__(kCoopThreads, kCoopBlocksPerSm) k_cmvn_coop(co
     if (st >= a.lag) {
       const int64_t m0 = (st - a.lag) * G;
       const int g_n = (int)min((int64_t)G, a.n_mats - m0);
-      if (t < g_n) spin_until(a.flag + m0 + t, 1);
+      if (t < 2 * cols) {  // 2 * cols threads per block poll the tagged records and park the values in shared memory
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g < g_n) {
+            const volatile unsigned long long* rp = a.stats + (size_t)(m0 + g) * cols * 2 + t;
+            unsigned long long r = *rp;
+            while ((unsigned)(r >> 32) != (unsigned)(m0 + g + 1)) {
+              __nanosleep(100);
+              r = *rp;
+            }
+            red2[g * 2 * cols + t] = __uint_as_float((unsigned)r);
+          }
+        }
+      }
       __syncthreads();
-      __threadfence();
       if (act) {
         float mean[G], inv[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const int64_t m = m0 + (g < g_n ? g : 0);
-          mean[g] = __ldcg(a.stats + ((size_t)m * cols + c) * 2);
-          inv[g] = __ldcg(a.stats + ((size_t)m * cols + c) * 2 + 1);  // 1 when !varnorm
+          const int gg = g < g_n ? g : 0;
+          mean[g] = red2[gg * 2 * cols + 2 * c];
+          inv[g] = red2[gg * 2 * cols + 2 * c + 1];  // 1 when !varnorm
         }
         const float* x0 = a.in + (m0 * a.rows + r0) * cols;
         float* y0 = a.out + (m0 * a.rows + r0) * cols;
@@ -867,8 +879,8 @@ size_t cmvn_scratch_bytes(int64_t n_mats, int64_t rows, int64_t cols) {
   if (!lag) return three_pass;
   // partial ring + statistics + counters and flags (launch_cmvn lays them out in this order)
   const int64_t coop_blocks = (int64_t)kCoopBlocksPerSm * kSmCountGuess;
-  const size_t coop = coop_align((size_t)(lag + 1) * kCoopGroupMax * coop_blocks * cols * 3 * sizeof(float)) + coop_align((size_t)n_mats * cols * 2 * sizeof(float)) +
-                      coop_align((size_t)n_mats * 2 * sizeof(int));
+  const size_t coop = coop_align((size_t)(lag + 1) * kCoopGroupMax * coop_blocks * cols * 3 * sizeof(float)) + coop_align((size_t)n_mats * cols * 2 * sizeof(unsigned long long)) +
+                      coop_align((size_t)n_mats * sizeof(int));
   return std::max(three_pass, coop);
 }
 
@@ -931,11 +943,11 @@ int launch_cmvn(const float* in, int64_t n_mats, int64_t rows, int64_t cols, int
       char* sp = reinterpret_cast<char*>(scratch);
       a.partial = reinterpret_cast<float*>(sp);
       sp += coop_align((size_t)(lag + 1) * kCoopGroupMax * kCoopBlocksPerSm * kSmCountGuess * cols * 3 * sizeof(float));
-      a.stats = reinterpret_cast<float*>(sp);
-      sp += coop_align((size_t)n_mats * cols * 2 * sizeof(float));
+      a.stats = reinterpret_cast<unsigned long long*>(sp);
+      const size_t rec_bytes = coop_align((size_t)n_mats * cols * 2 * sizeof(unsigned long long));
+      sp += rec_bytes;
       a.counter = reinterpret_cast<int*>(sp);
-      a.flag = a.counter + n_mats;
-      e = cudaMemsetAsync(a.counter, 0, (size_t)n_mats * 2 * sizeof(int), (cudaStream_t)stream);
+      e = cudaMemsetAsync(a.stats, 0, rec_bytes + (size_t)n_mats * sizeof(int), (cudaStream_t)stream);
       if (e != cudaSuccess) return (int)e;
       void* args[] = {(void*)&a};
       e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)nblk), dim3(kCoopThreads), args, smem, (cudaStream_t)stream);
