@@ -371,15 +371,14 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
 // (cooperative launch) pipelines the matrices through the L2 so that each crosses the DRAM bus once per direction
 // instead of twice in.  Worker blocks own a fixed row range: they sum it for matrix i (shifted sums, as
 // k_cmvn_partial) and announce it on the matrix's counter, then normalise the same rows of matrix i - lag (lag = 1) out of
-// L2 once its statistics are flagged.  A few merger blocks (matrix m belongs to merger m mod kCoopMergers) wait for
+// L2 once its statistics are published.  A few merger blocks (matrix m belongs to merger m mod kCoopMergers) wait for
 // a matrix's counter, merge the workers' partials in block order (Chan's formula; the bits do not depend on the
-// batch) and publish mean and 1 / (std + eps).  No grid-wide barrier; the lag keeps the merge (~5 us) off the
-// workers' path.  Measured on 64 x (359,997 x 13): DRAM reads 1.23 GB = the input once (three-pass kernels: 2.33 GB),
-// 0.79 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
+// batch) and publish mean and 1 / (std + eps) as tagged 8-byte records.  No grid-wide barrier.  Measured on
+// 64 x (359,997 x 13): DRAM reads 1.21 GB = the input once (three-pass kernels: 2.33 GB), 0.70 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
 // matrix costs one block's chain of dependent round trips (DRAM batches, three block reductions, fence + counter,
 // flag, L2 batches: ~11 us).  Two matrices per step (G = 2) buy 1 % and lose the L2 reuse; four spill; 16-byte vectors (one trip per
-// matrix, 128 bytes per thread in flight) measured 0.82 ms; prefetching the next matrix's first batch and per-thread
-// polling of tagged statistics records lost to register spills and to 150,000 threads polling the L2.
+// matrix, 128 bytes per thread in flight) measured 0.82 ms; prefetching the next matrix's first batch lost to register
+// spills, and letting every thread poll the statistics records to 150,000 threads polling the L2.
 constexpr int kCoopThreads = 512, kCoopBlocksPerSm = 2, kCoopMergers = 4, kCoopGroupMax = 4;
 constexpr int64_t kCoopMinMatBytes = 3LL << 20, kCoopMaxMatBytes = 40LL << 20, kCoopL2Bytes = 64LL << 20;
 struct CoopArgs {
