@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) k_cmvn_apply(const float* in, float* out,
 // L2 once its statistics are published.  A few merger blocks (matrix m belongs to merger m mod kCoopMergers) wait for
 // a matrix's counter, merge the workers' partials in block order (Chan's formula; the bits do not depend on the
 // batch) and publish mean and 1 / (std + eps) as tagged 8-byte records.  No grid-wide barrier.  Measured on
-// 64 x (359,997 x 13): DRAM reads 1.21 GB = the input once (three-pass kernels: 2.33 GB), 0.70 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
+// 64 x (359,997 x 13): DRAM reads 1.21 GB = the input once (three-pass kernels: 2.33 GB), 0.71 ms against 0.89 ms.  What is left is not bandwidth and not bytes in flight: every block walks every matrix, so a
 // matrix costs one block's chain of dependent round trips (DRAM batches, three block reductions, fence + counter,
 // flag, L2 batches: ~11 us).  Two matrices per step (G = 2) buy 1 % and lose the L2 reuse; four spill; 16-byte vectors (one trip per
 // matrix, 128 bytes per thread in flight) measured 0.82 ms; prefetching the next matrix's first batch lost to register
@@ -582,14 +582,15 @@ __global__ void __launch_bounds__(kCoopThreads, kCoopBlocksPerSm) k_cmvn_coop(co
         }
       }
       __syncthreads();
-      if (act) {
-        float mean[G], inv[G];
+      float mean[G], inv[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int gg = g < g_n ? g : 0;
-          mean[g] = red2[gg * 2 * cols + 2 * c];
-          inv[g] = red2[gg * 2 * cols + 2 * c + 1];  // 1 when !varnorm
-        }
+      for (int g = 0; g < G; ++g) {
+        const int gg = g < g_n ? g : 0;
+        mean[g] = red2[gg * 2 * cols + 2 * c];
+        inv[g] = red2[gg * 2 * cols + 2 * c + 1];  // 1 when !varnorm
+      }
+      __syncthreads();  // everyone has its statistics: red2 may be rewritten (in the drain steps by the next poll right away)
+      if (act) {
         const float* x0 = a.in + (m0 * a.rows + r0) * cols;
         float* y0 = a.out + (m0 * a.rows + r0) * cols;
         const int64_t mstride = a.rows * cols;
