@@ -166,6 +166,8 @@ bool stft512_supported(const Derived& d);
 size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch);
 int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* stream);
 int launch_mel_from_power(const float* power, const FrameParams& p, int64_t row0, int64_t n_rows, int F, void* stream);
+// bytes of |X|^2 scratch per launch of the two-kernel paths (256 MB; SS_POWER_SLAB_KB shrinks it so that tests cross slabs)
+int64_t power_slab_bytes();
 
 int launch_preemphasis(const float* in, float* out, int64_t n_rows, int64_t n, int64_t row_stride,
                        int64_t shift, float cof, void* stream);

@@ -399,7 +399,7 @@ int launch_stft2048(const FrameParams& p, const Stft2048Tables* t, int sm_count,
 // `scratch` (stft2048_power_scratch_bytes), then k_mel_from_power (ss_kernels_stft512.cu) over the Slaney bank
 size_t stft2048_power_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch) {
   const int64_t per_row = std::max<int64_t>(1, p.T) * (kM + 1) * (int64_t)sizeof(float);
-  int64_t rpl = std::max<int64_t>(1, (256LL << 20) / per_row);
+  int64_t rpl = std::max<int64_t>(1, power_slab_bytes() / per_row);
   rpl = std::min<int64_t>(rpl, std::max<int64_t>(1, p.n_rows));
   rpl = std::min<int64_t>(rpl, 65535);
   if (rows_per_launch) *rows_per_launch = rpl;

@@ -263,12 +263,18 @@ int launch_mel_from_power(const float* power, const FrameParams& p, int64_t row0
   return tf == 16 ? launch_mel_tf<16>(power, p, row0, n_rows, F, stream) : launch_mel_tf<kMelFrames>(power, p, row0, n_rows, F, stream);
 }
 
+int64_t power_slab_bytes() {
+  const char* e = getenv("SS_POWER_SLAB_KB");  // read per call: the tests toggle it
+  const int64_t kb = e ? atoll(e) : 0;
+  return kb > 0 ? kb << 10 : 256LL << 20;
+}
+
 bool stft512_supported(const Derived& d) { return (d.W == 512 || d.W == 1024) && d.stft_ok; }
 
 // scratch: power rows of the rows of one launch; sized by stft512_scratch_bytes for `rows_per_launch` rows
 size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch) {
   const int64_t per_row = std::max<int64_t>(1, p.T) * (p.N / 2 + 1) * (int64_t)sizeof(float);
-  int64_t rpl = std::max<int64_t>(1, (256LL << 20) / per_row);
+  int64_t rpl = std::max<int64_t>(1, power_slab_bytes() / per_row);
   rpl = std::min<int64_t>(rpl, std::max<int64_t>(1, p.n_rows));
   rpl = std::min<int64_t>(rpl, 65535);  // gridDim.y of the mel kernel
   if (rows_per_launch) *rows_per_launch = rpl;

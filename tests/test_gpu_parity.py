@@ -637,6 +637,28 @@ def test_librosa_mode_n_fft_512_1024_register_fft_kernel(n_fft):
         assert_log_close(gdb[loud], wdb[loud], atol=2e-3, what=f"librosa {n_fft} power_to_db")
 
 
+def test_power_scratch_slabs_of_the_two_kernel_paths(monkeypatch):
+    """The |X|^2 scratch of k_stft512 / k_stft1024 / k_stft2048<2> + k_mel_from_power is processed in slabs of rows: with
+    a 64 KB slab a small batch crosses many slab boundaries and must give the bits of the one-slab run."""
+    cases = [(sb.feature.librosa_config(16000, 512, 160, 80, 0.0, None), 9, 3000),
+             (sb.feature.librosa_config(22050, 1024, 256, 64, 0.0, None), 7, 5000),
+             (sb.feature.librosa_config(22050, 2048, 512, 128, 0.0, None), 11, 9000)]
+    for cfg, rows, n in cases:
+        y = o.synth_signal(rows, n, 0x51AB + n)
+        monkeypatch.delenv("SS_POWER_SLAB_KB", raising=False)
+        whole = sb.feature.melspectrogram_librosa(y, cfg)
+        monkeypatch.setenv("SS_POWER_SLAB_KB", "64")
+        slabs = sb.feature.melspectrogram_librosa(y, cfg)
+        assert np.array_equal(whole, slabs)
+    kw = dict(sample_rate=16000, fft_points=1024, frame_length=256.5 / 16000, frame_stride=0.01, num_cepstral=13, num_filters=64,
+              low_frequency=0.0, high_frequency=8000.0)
+    x = o.synth_signal(9, 4001, 0x51AC)
+    monkeypatch.delenv("SS_POWER_SLAB_KB", raising=False)
+    whole = sb.feature.mel_spectrogram2(x, sb.SpeechConfig(**kw), log=True)
+    monkeypatch.setenv("SS_POWER_SLAB_KB", "64")
+    assert np.array_equal(whole, sb.feature.mel_spectrogram2(x, sb.SpeechConfig(**kw), log=True))
+
+
 def test_librosa_mode_n_fft_2048_register_fft_kernel():
     """librosa's default n_fft: k_stft2048<power> -> |X|^2 rows of all 1025 bins -> k_mel_from_power over the Slaney bank."""
     for sr, hop, n_mels, n, rows in [(22050, 512, 128, 22050 * 2 + 3, 3), (16000, 160, 80, 16000, 2), (44100, 1024, 64, 30001, 2),
