@@ -761,9 +761,11 @@ def test_derivative_features_bit_exact():
 
 def test_cmvn_long_matrices_cooperative_pipeline():
     """Matrices of 3 .. 40 MB: the co-resident worker / merger pipeline (k_cmvn_coop): more matrices than the lag and
-    the merger count, both modes, a hostile first row (the pivot of block 0), and the same bits as a one-matrix call."""
+    the merger count, both modes, a hostile first row (the pivot of block 0), and the same bits as a one-matrix call.
+    Smaller ones: the partial / merge / apply kernels under the same conditions."""
     rng = np.random.default_rng(11)
-    for shape in [(11, 70_000, 13), (3, 120_000, 40)]:
+    # the last two shapes (1.6 MB matrices) stay on the three-pass kernels: same pivot, same tolerance
+    for shape in [(11, 70_000, 13), (3, 120_000, 40), (4, 30_000, 13), (3, 5_000, 80)]:
         xb = (rng.standard_normal(shape) * 2 + 1).astype(np.float32)
         xb[:, 0, :] = 1e4
         for vn in (True, False):
