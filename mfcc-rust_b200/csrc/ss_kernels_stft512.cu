@@ -8,7 +8,7 @@
 //                    Frames inside their row are loaded as float2; frames that touch the overlap memory, the previous
 //                    row, the zero padding (stream model, functions.rs:99-121) or the reflected edges (librosa mode)
 //                    fetch per sample through the same index formulas as k_frames_generic.
-//   k_mel_from_power banded mel reduction of 32 frames x all filters per block from those rows, time-minor store
+//   k_mel_from_power banded mel reduction of 16 (F = 257) or 8 (wider spectra) frames x all filters per block from those rows, time-minor store
 //                    [row][m][t] (feature.rs:173), ln(zero_handling) / power_to_db on request.
 // The |X|^2 scratch costs one extra write and read of 1 KB per frame; measured 4 x the rate of the any-length kernel
 // (8,192 x 10 s rows, hop 256: 5.9 ms against 23.0 ms; librosa mode, hop 160: 9.5 ms against 39.7 ms).  Each filter sums its bins in index order, as the reference's einsum does.
