@@ -1,6 +1,6 @@
 // fft_points = 512 and 1024 on the STFT / librosa paths: functions::stft1/2 (functions.rs:86-233),
 // feature::mel_spectrogram1/2 (feature.rs:151-174) and the librosa-compatible mel spectrogram for those n_fft.
-// (Kernel template k_stft512<R, ..>: R = 16 points per lane -> fft_points 512, R = 32 -> 1024.)
+// (Kernel template k_stft512<R, ..>: R = 16 points per lane -> fft_points 512, R = 32 -> 1024, R = 8 -> 256.)
 //
 // Two kernels instead of one fused one (the fused MMA epilogue of k_fast512c is tied to speechpy framing):
 //   k_stft512        one half-warp per frame: window, the 16 x 16 four-step register FFT of k_fast512c / k_pspec512,
@@ -36,7 +36,8 @@ constexpr int kXs = 18;                       // transpose row stride in float2 
 template <int R>
 struct Geo {
   static constexpr int kW = 32 * R, kNc = 16 * R, kF = kNc + 1;
-  static constexpr int kNS = R / 16;                   // 16-point sub-FFTs per lane in the second stage
+  static constexpr int kNS = R >= 16 ? R / 16 : 1;     // 16-point sub-FFTs per lane in the second stage
+  static constexpr int kAct = R >= 16 ? 16 : R;        // lanes of a frame that own rows in the second stage (R = 8: half of them)
   static constexpr int kXchFrame = R * kXs;            // float2 per frame
   static constexpr int kWarpFloats = 2 * kXchFrame * 2;
   static constexpr int kTwRow = 2 * R + 4;             // floats per lane row of the W_Nc table
@@ -63,7 +64,7 @@ template <int R, bool LIBROSA>
 __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, const float* __restrict__ tw_tab, float* __restrict__ power,
                                                           int64_t row0, int64_t n_rows) {
   using G = Geo<R>;
-  constexpr int kW = G::kW, kNc = G::kNc, kF = G::kF, kNS = G::kNS;
+  constexpr int kW = G::kW, kNc = G::kNc, kF = G::kF, kNS = G::kNS, kAct = G::kAct;
   extern __shared__ __align__(16) float smem[];
   float* tw_s = smem;
   float* win_s = smem + G::kTabTw;
@@ -73,12 +74,16 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fi = lane >> 4, u = lane & 15;
-  const bool isz = (u == 0);
-  const int partner = (lane & 16) | ((16 - u) & 15);
+  // second stage: lane u owns the rows k1 = ua + 16 s.  With R = 8 there are only 8 rows: lanes 8..15 shadow lanes 0..7
+  // (same loads, same shuffles, no stores).
+  const int ua = u & (kAct - 1);
+  const bool owner = u < kAct;
+  const bool isz = (ua == 0);
+  const int partner = (lane & 16) | ((kAct - ua) & (kAct - 1));
   const float4* twrow = reinterpret_cast<const float4*>(tw_s + u * G::kTwRow);
-  float2 wu[kNS];  // W_{2 Nc}^{u + 16 s}
+  float2 wu[kNS];  // W_{2 Nc}^{ua + 16 s}
 #pragma unroll
-  for (int s = 0; s < kNS; ++s) sincospif(-(float)(u + 16 * s) / (float)kNc, &wu[s].y, &wu[s].x);
+  for (int s = 0; s < kNS; ++s) sincospif(-(float)(ua + 16 * s) / (float)kNc, &wu[s].y, &wu[s].x);
   float2* xch = reinterpret_cast<float2*>(xch_s + warp * G::kWarpFloats) + fi * G::kXchFrame;
   const float2* win2 = reinterpret_cast<const float2*>(win_s) + u;  // window pairs (2m, 2m+1), m = u + 16 j
 
@@ -141,11 +146,11 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
       xch[(k1 + 1) * kXs + u] = y1;
     });
     __syncwarp();
-    // lane u takes the rows k1 = u + 16 s: gg[s][k2] = Z[u + 16 s + R k2]
+    // lane u takes the rows k1 = ua + 16 s: gg[s][k2] = Z[ua + 16 s + R k2]
     float2 gg[kNS][16];
 #pragma unroll
     for (int s = 0; s < kNS; ++s) {
-      const float4* r4 = reinterpret_cast<const float4*>(xch + (u + 16 * s) * kXs);
+      const float4* r4 = reinterpret_cast<const float4*>(xch + (ua + 16 * s) * kXs);
       sfor<0, 8>([&](auto tt) {
         constexpr int i = decltype(tt)::value;
         const float4 x = r4[i];
@@ -156,11 +161,11 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < kNS; ++s) ssfft::fft_pow2<16>(gg[s]);
-    // ---- real-FFT split: X[k] = xa / 2, X[Nc - k] = conj(xb) / 2 for k = u + 16 s + R k2 < Nc / 2 (k2 < 8).
-    // Nc - k = (R - u - 16 s) + R (15 - k2): row R - u - 16 s belongs to lane 16 - u, sub-FFT kNS - 1 - s (u > 0);
+    // ---- real-FFT split: X[k] = xa / 2, X[Nc - k] = conj(xb) / 2 for k = ua + 16 s + R k2 < Nc / 2 (k2 < 8).
+    // Nc - k = (R - ua - 16 s) + R (15 - k2): row R - ua - 16 s belongs to lane kAct - ua, sub-FFT kNS - 1 - s (ua > 0);
     // lane 0 mirrors onto itself: sub-FFT 0 onto its own entry 16 - k2, sub-FFT s >= 1 onto sub-FFT kNS - s.
-    float2* srow = (p.stft_out && stored) ? p.stft_out + (row * T_out + t) * kF : nullptr;
-    float* prow = (power && computed) ? power + (rl * T + t) * kF : nullptr;
+    float2* srow = (p.stft_out && stored && owner) ? p.stft_out + (row * T_out + t) * kF : nullptr;
+    float* prow = (power && computed && owner) ? power + (rl * T + t) * kF : nullptr;
 #pragma unroll
     for (int s = 0; s < kNS; ++s) {
       sfor<0, 8>([&](auto kk) {
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_stft512(const FrameParams p, co
         const float2 tt = ssfft::cmulf(ssfft::twmul<32, k2>(od), wu[s]);  // W_{2 Nc}^{R k2} = W32^{k2}
         const float2 xa = ssfft::cadd(e, tt), xb = ssfft::csub(e, tt);
         const float2 Xa = make_float2(scale * xa.x, scale * xa.y), Xb = make_float2(scale * xb.x, -scale * xb.y);
-        const int ka = u + 16 * s + R * k2, kb = kNc - ka;
+        const int ka = ua + 16 * s + R * k2, kb = kNc - ka;
         if (srow) {
           srow[ka] = Xa;
           srow[kb] = Xb;
@@ -272,7 +277,7 @@ int64_t power_slab_bytes() {
   return kb > 0 ? kb << 10 : 256LL << 20;
 }
 
-bool stft512_supported(const Derived& d) { return (d.W == 512 || d.W == 1024) && d.stft_ok; }
+bool stft512_supported(const Derived& d) { return (d.W == 256 || d.W == 512 || d.W == 1024) && d.stft_ok; }
 
 // scratch: power rows of the rows of one launch; sized by stft512_scratch_bytes for `rows_per_launch` rows
 size_t stft512_scratch_bytes(const FrameParams& p, int64_t* rows_per_launch) {
@@ -331,14 +336,15 @@ static int launch_stft_r(const FrameParams& p, float* scratch, int sm_count, voi
       if (me) return me;
     }
   }
-  note_kernel(R == 16 ? "k_stft512" : "k_stft1024");
+  note_kernel(R == 16 ? "k_stft512" : R == 32 ? "k_stft1024" : "k_stft256");
   return 0;
 }
 
 int launch_stft512(const FrameParams& p, float* scratch, int sm_count, void* stream) {
-  if (p.N != 512 && p.N != 1024) return -1000;
+  if (p.N != 256 && p.N != 512 && p.N != 1024) return -1000;
   if (p.n_rows <= 0 || p.T_out <= 0) return 0;
   if (p.mel_out && !scratch) return -1000;
+  if (p.N == 256) return launch_stft_r<8>(p, scratch, sm_count, stream);
   return p.N == 512 ? launch_stft_r<16>(p, scratch, sm_count, stream) : launch_stft_r<32>(p, scratch, sm_count, stream);
 }
 

@@ -94,5 +94,7 @@ sb.feature.mel_spectrogram2(o.synth_signal(150, 22050, 41), sb.SpeechConfig(**C3
 sb.processing.cmvn(o.synth_signal(40, 60 * 12, 42).reshape(40, 60, 12), True)
 sb.processing.cmvn(o.synth_signal(9, 2 * 20, 43).reshape(9, 2, 20), False)
 sb.processing.cmvn(o.synth_signal(5, 70000 * 13, 44).reshape(5, 70000, 13), True)
+sb.feature.melspectrogram_librosa(o.synth_signal(3, 3000, 45), sb.feature.librosa_config(8000, 256, 80, 40, devices=[0]), db=True)  # k_stft256
+sb.functions.stft2(o.synth_signal(2, 2001, 46), sb.SpeechConfig(8000, 256, 77.5 / 8000, 0.01, 13, 20, 0.0, 4000.0, devices=[0]))
 torch.cuda.synchronize()
 print("sanitize_small: all kernels ran")

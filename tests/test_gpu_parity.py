@@ -583,14 +583,19 @@ W512 = [dict(sample_rate=16000, fft_points=512, frame_length=256.5 / 16000, fram
         dict(sample_rate=16000, fft_points=1024, frame_length=256.5 / 16000, frame_stride=0.01, num_cepstral=13, num_filters=64,
              low_frequency=0.0, high_frequency=8000.0),
         dict(sample_rate=22050, fft_points=1024, frame_length=441.5 / 22050, frame_stride=0.01, num_cepstral=13, num_filters=96,
-             low_frequency=20.0, high_frequency=11025.0)]         # odd hop
+             low_frequency=20.0, high_frequency=11025.0),         # odd hop
+        # fft_points = 256 (8 kHz speech): 8 points per lane, half of a frame's lanes own rows in the second stage
+        dict(sample_rate=8000, fft_points=256, frame_length=80.5 / 8000, frame_stride=0.01, num_cepstral=13, num_filters=26,
+             low_frequency=0.0, high_frequency=4000.0),
+        dict(sample_rate=8000, fft_points=256, frame_length=77.5 / 8000, frame_stride=0.01, num_cepstral=13, num_filters=20,
+             low_frequency=100.0, high_frequency=3800.0)]         # odd hop
 
 
 @pytest.mark.parametrize("kw", W512)
 def test_stft512_register_fft_path_matches_generic_and_oracle(kw):
     """fft_points = 512: k_stft512 (+ k_mel_from_power) against the any-length kernel and the oracle -- complex STFT, mel and
     log-mel, ragged lengths, rows shorter than the overlap memory, row-to-row and call-to-call carry, odd frame counts"""
-    kname = b"k_stft512" if kw["fft_points"] == 512 else b"k_stft1024"
+    kname = {256: b"k_stft256", 512: b"k_stft512", 1024: b"k_stft1024"}[kw["fft_points"]]
     for n, ttd in [(5, 16000), (3, 4001), (7, 257), (2, 100), (1, 48017), (33, 2048)]:
         x = o.synth_signal(n, ttd, 2000 + ttd)
         fast, gen, oc = sb.SpeechConfig(**kw), sb.SpeechConfig(**kw, flags=GENERIC), o.SpeechConfig(**kw)
@@ -619,10 +624,12 @@ def test_stft512_register_fft_path_matches_generic_and_oracle(kw):
                 assert_spec_close(a, b, what=f"512 fast vs generic mel {n}x{ttd}")
 
 
-@pytest.mark.parametrize("n_fft", [512, 1024])
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
 def test_librosa_mode_n_fft_512_1024_register_fft_kernel(n_fft):
-    kname = b"k_stft512" if n_fft == 512 else b"k_stft1024"
+    kname = {256: b"k_stft256", 512: b"k_stft512", 1024: b"k_stft1024"}[n_fft]
     for sr, hop, n_mels, n, rows in [(16000, 160, 80, 16000 * 2 + 5, 3), (16000, 128, 40, 4000, 2), (22050, 512, 64, 9001, 4), (8000, 77, 23, 600, 1)]:
+        if hop > n_fft:  # the plan needs hop <= n_fft
+            continue
         cfg = sb.feature.librosa_config(sr, n_fft, hop, n_mels, 0.0, None)
         assert cfg.info.fast_stft == 1
         y = o.synth_signal(rows, n, 0x5EED0512 + hop)

@@ -38,7 +38,7 @@ for shape, kw, n, ttd, T, F in (("c4", C4, 1024, 480000, 3000, 201), ("c3", C3, 
 # librosa-compatible mel spectrogram (SS_FLAG_LIBROSA) on the same two shapes: n_fft = 400 on the register-FFT
 # kernel (full-spectrum tile), everything else on the any-length generic kernel
 for shape, sr, n_fft, hop, n_mels, n, ttd in (("c4", 16000, 400, 160, 80, 1024, 480000), ("c3", 22050, 2048, 512, 128, 2048, 110250),
-                                              ("n_fft 1024", 22050, 1024, 256, 128, 2048, 110250), ("n_fft 512", 16000, 512, 160, 80, 2048, 160000)):
+                                              ("n_fft 1024", 22050, 1024, 256, 128, 2048, 110250), ("n_fft 512", 16000, 512, 160, 80, 2048, 160000), ("n_fft 256", 8000, 256, 80, 40, 4096, 80000)):
   x = torch.empty((n, ttd), dtype=torch.float32, device="cuda").normal_(0, 0.1)
   T = 1 + ttd // hop
   out = torch.empty((n, n_mels, T), dtype=torch.float32, device="cuda")
