@@ -157,6 +157,21 @@ def test_invalid_configs_are_errors_not_aborts():
         sb.SpeechConfig(16000, num_cepstral=41, devices=[])            # slice ..num_cepstral out of range
 
 
+def test_plan_info_reports_the_specialised_kernels_for_the_sizes_they_serve():
+    """ss_plan_info.fast_path / fast_stft (host-only plans): which shapes have a register-FFT kernel."""
+    assert sb.SpeechConfig(**CONFIGS["c1"], devices=[]).info.fast_path == 1            # n_fft 512, speechpy framing
+    assert sb.SpeechConfig(**CONFIGS["c3"], devices=[]).info.fast_stft == 1            # fft_points 2048
+    assert sb.SpeechConfig(**CONFIGS["c4"], devices=[]).info.fast_stft == 1            # fft_points 400
+    for n_fft, hop in ((256, 80), (512, 160), (1024, 256), (2048, 512), (400, 160)):
+        assert sb.feature.librosa_config(16000, n_fft, hop, 40, devices=[]).info.fast_stft == 1, n_fft
+        kw = dict(sample_rate=16000, fft_points=n_fft, frame_length=(hop + 0.5) / 16000, frame_stride=0.01, num_cepstral=13, num_filters=26,
+                  low_frequency=0.0, high_frequency=8000.0)
+        assert sb.SpeechConfig(**kw, devices=[]).info.fast_stft == 1, n_fft
+        assert sb.SpeechConfig(**kw, devices=[], flags=_lib.SS_FLAG_FORCE_GENERIC).info.fast_stft == 0
+    for n_fft in (300, 768, 4096):                                                      # the any-length kernel
+        assert sb.feature.librosa_config(16000, n_fft, n_fft // 4, 40, devices=[]).info.fast_stft == 0, n_fft
+
+
 def test_no_cpu_fallback_without_device():
     if sb.lib.ss_device_count() > 0:
         pytest.skip("a CUDA device is visible")
